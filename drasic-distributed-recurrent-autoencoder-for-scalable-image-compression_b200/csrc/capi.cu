@@ -1,0 +1,235 @@
+// C ABI (include/drasic_b200.h) over the sm_100a kernels: argument validation, TMA descriptor
+// construction, launches.  No torch types, no allocation, no synchronisation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/drasic_b200.h"
+#include "kernels.h"
+#include "pointwise.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(int e, const char* what) {
+  if (e == 0) return 0;
+  return fail(e, "%s: %s", what, cudaGetErrorString(static_cast<cudaError_t>(e)));
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// NHWC fp16 activation plane [N,H,W,C]; box = (64 channels, bw, bh, bn) pixels, 128B swizzle,
+// out-of-bounds elements (the conv halo) read as zero.
+int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(DRASIC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
+                              static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                                 static_cast<cuuint64_t>(H) * W * C * 2};
+  const cuuint32_t box[4] = {drasic::BLOCK_K, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh),
+                             static_cast<cuuint32_t>(bn)};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DRASIC_ERR_TENSORMAP, "activation tensor map rejected (CUresult %d) N=%d H=%d W=%d C=%d box=%dx%dx%d",
+                static_cast<int>(r), N, H, W, C, bw, bh, bn);
+  return 0;
+}
+
+// packed weights [rows, K] fp16 K-major; box = (64, block_n)
+int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, int block_n) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(DRASIC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+  const cuuint32_t box[2] = {drasic::BLOCK_K, static_cast<cuuint32_t>(block_n)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DRASIC_ERR_TENSORMAP, "weight tensor map rejected (CUresult %d) rows=%d K=%d", static_cast<int>(r), rows, K);
+  return 0;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms > 0) return g_num_sms;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  g_num_sms = n;
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int drasic_version(void) { return DRASIC_ABI_VERSION; }
+const char* drasic_last_error(void) { return g_err; }
+int drasic_device_sms(void) {
+  const int n = num_sms();
+  if (n <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
+  return n;
+}
+
+size_t drasic_packed_weight_bytes(int Cin, int Co) {
+  return static_cast<size_t>(4) * Co * 9 * (Cin + Co) * 2;
+}
+
+int drasic_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
+                             int out_order, int block_n, void* out_hi, void* out_lo,
+                             float* inv_scale_out, void* scratch4, void* stream) {
+  if (!w_in || !w_h || !out_hi || !out_lo || !inv_scale_out || !scratch4)
+    return fail(DRASIC_ERR_INVALID, "pack_lstm_weights: null pointer");
+  if (Cin % 64 || Co % 64 || (block_n != 256 && block_n != 128 && block_n != 64) || (4 * Co) % block_n)
+    return fail(DRASIC_ERR_INVALID, "pack_lstm_weights: Cin=%d Co=%d block_n=%d unsupported", Cin, Co, block_n);
+  if ((in_order == DRASIC_ORDER_QUAD && Cin % 4) || (out_order == DRASIC_ORDER_QUAD && (Co / 4) % 16))
+    return fail(DRASIC_ERR_INVALID, "pack_lstm_weights: quad order needs Co/4 %% 16 == 0");
+  return cuda_fail(drasic::launch_pack_lstm_weights(
+                       w_in, w_h, Cin, Co, in_order, out_order, block_n, static_cast<__half*>(out_hi),
+                       static_cast<__half*>(out_lo), inv_scale_out, static_cast<unsigned int*>(scratch4),
+                       static_cast<cudaStream_t>(stream)),
+                   "pack_lstm_weights launch");
+}
+
+int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
+  if (!a) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: null args");
+  const int H = a->H, W = a->W, Cin = a->Cin, Co = a->Co, B = a->B_pad;
+  if (Cin % 64 || Co % 64 || Cin <= 0 || Co <= 0)
+    return fail(DRASIC_ERR_INVALID, "convlstm_fwd: channels must be multiples of 64 (Cin=%d Co=%d)", Cin, Co);
+  if (a->block_n != 256 && a->block_n != 128 && a->block_n != 64)
+    return fail(DRASIC_ERR_INVALID, "convlstm_fwd: block_n=%d", a->block_n);
+  if ((4 * Co) % a->block_n) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: 4*Co %% block_n != 0");
+  // pixel box of one M tile
+  const int bw = W < 128 ? W : 128;
+  if (bw <= 0 || 128 % bw || W % bw) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: W=%d unsupported", W);
+  const int bh = H < 128 / bw ? H : 128 / bw;
+  if (bh <= 0 || (128 / bw) % bh || H % bh) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: H=%d unsupported", H);
+  const int bn = 128 / (bw * bh);
+  if (bn > 1 && (bw != W || bh != H)) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: tile shape");
+  if (B <= 0 || B % bn) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: B_pad=%d not a multiple of %d", B, bn);
+  if (a->n_groups < 1 || a->n_groups > DRASIC_MAX_GROUPS) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: n_groups");
+  if (a->n_groups > 1 && !a->group_mtile_end) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: group_mtile_end");
+  if (!a->x_hi || !a->w_hi || !a->w_inv_scale || !a->c_state || !a->h_out_hi)
+    return fail(DRASIC_ERR_INVALID, "convlstm_fwd: null pointer");
+  if (a->split && (!a->x_lo || !a->w_lo || !a->h_out_lo)) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: split needs lo planes");
+  if (a->has_state && (!a->h_hi || (a->split && !a->h_lo))) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: has_state needs h");
+  if (a->has_state && (a->h_hi == a->h_out_hi)) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: h_out aliases h");
+  if (a->next_mode != DRASIC_NEXT_NONE && (!a->next_hi || (a->split && !a->next_f32 && !a->next_lo)))
+    return fail(DRASIC_ERR_INVALID, "convlstm_fwd: next buffers");
+  if (a->next_mode == DRASIC_NEXT_DOWN && ((H | W) & 1)) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: odd size for unshuffle");
+  if (a->next_mode == DRASIC_NEXT_UP && (Co / 4) % 16) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: Co/4 %% 16 for shuffle");
+
+  drasic::GateParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_act_map(&p.tm_x[0], a->x_hi, B, H, W, Cin, bw, bh, bn))) return rc;
+  if (a->split && (rc = make_act_map(&p.tm_x[1], a->x_lo, B, H, W, Cin, bw, bh, bn))) return rc;
+  if (a->has_state) {
+    if ((rc = make_act_map(&p.tm_h[0], a->h_hi, B, H, W, Co, bw, bh, bn))) return rc;
+    if (a->split && (rc = make_act_map(&p.tm_h[1], a->h_lo, B, H, W, Co, bw, bh, bn))) return rc;
+  }
+  const int K = 9 * (Cin + Co);
+  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * 4 * Co, K, a->block_n))) return rc;
+  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * 4 * Co, K, a->block_n))) return rc;
+  p.c_state = a->c_state;
+  p.h_out[0] = static_cast<__half*>(a->h_out_hi);
+  p.h_out[1] = static_cast<__half*>(a->h_out_lo);
+  p.next[0] = a->next_hi;
+  p.next[1] = a->next_lo;
+  p.w_inv_scale = a->w_inv_scale;
+  p.H = H; p.W = W; p.Cin = Cin; p.Co = Co;
+  p.bw = bw; p.bh = bh; p.bn = bn;
+  p.n_mtiles = static_cast<int>(static_cast<long long>(B) * H * W / 128);
+  p.n_ntiles = 4 * Co / a->block_n;
+  p.has_hidden = a->has_state ? 1 : 0;
+  p.has_cell = a->has_state ? 1 : 0;
+  p.next_mode = a->next_mode;
+  p.next_f32 = a->next_f32;
+  p.precise = a->precise;
+  p.n_groups = a->n_groups;
+  p.group_mtile_end = a->group_mtile_end;
+  const int sms = num_sms();
+  if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
+  return cuda_fail(drasic::launch_convlstm_gates(p, a->split != 0, a->block_n, sms, static_cast<cudaStream_t>(stream)),
+                   "convlstm_fwd launch");
+}
+
+int drasic_bottleneck_fwd(const drasic_bottleneck_args* a, void* stream) {
+  if (!a) return fail(DRASIC_ERR_INVALID, "bottleneck_fwd: null args");
+  if (!a->h_e3 || !a->w_e4 || !a->w_d0 || !a->perm || !a->code_out || !a->d1_in_hi || (a->split && !a->d1_in_lo))
+    return fail(DRASIC_ERR_INVALID, "bottleneck_fwd: null pointer");
+  if (a->B_pad <= 0 || a->HW <= 0 || a->Ch % 4 || a->code <= 0 || (a->code * a->HW) % 32)
+    return fail(DRASIC_ERR_INVALID, "bottleneck_fwd: shape B_pad=%d HW=%d Ch=%d code=%d", a->B_pad, a->HW, a->Ch, a->code);
+  if (a->n_enc_groups < 1 || a->n_dec_groups < 1 || a->n_enc_groups > DRASIC_MAX_GROUPS || a->n_dec_groups > DRASIC_MAX_GROUPS)
+    return fail(DRASIC_ERR_INVALID, "bottleneck_fwd: groups");
+  if ((a->n_enc_groups > 1 || a->n_dec_groups > 1) && !a->group_img_end)
+    return fail(DRASIC_ERR_INVALID, "bottleneck_fwd: group_img_end");
+  drasic::BottleneckParams p;
+  memset(&p, 0, sizeof(p));
+  p.h_e3 = a->h_e3; p.w_e4 = a->w_e4; p.w_d0 = a->w_d0; p.noise = a->noise; p.perm = a->perm;
+  p.code_out = a->code_out; p.z_out = a->z_out; p.bits_out = a->bits_out;
+  p.d1_in[0] = static_cast<__half*>(a->d1_in_hi); p.d1_in[1] = static_cast<__half*>(a->d1_in_lo);
+  p.d0_out_f32 = a->d0_out_f32;
+  p.B_pad = a->B_pad; p.HW = a->HW; p.Ch = a->Ch; p.code = a->code;
+  p.n_enc_groups = a->n_enc_groups; p.n_dec_groups = a->n_dec_groups;
+  p.precise = a->precise; p.split = a->split;
+  p.group_img_end = a->group_img_end;
+  return cuda_fail(drasic::launch_bottleneck(p, static_cast<cudaStream_t>(stream)), "bottleneck_fwd launch");
+}
+
+int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream) {
+  if (!a) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: null args");
+  if (!a->w_e0 || !a->img || !a->perm) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: null pointer");
+  if (a->mode != DRASIC_TAIL_INIT && (!a->d3_next || !a->w_d4 || !a->recon_out || !a->loss_acc))
+    return fail(DRASIC_ERR_INVALID, "tail_head_fwd: step mode needs decoder buffers");
+  if (a->mode == DRASIC_TAIL_STEP && !a->recon_prev) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: recon_prev");
+  if (a->mode < 0 || a->mode > 2 || a->loss_kind < 0 || a->loss_kind > 2) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: mode/loss");
+  if (a->C < 1 || a->C > 4 || (a->H * a->W) % 256 || ((a->H | a->W) & 1)) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: C=%d H=%d W=%d", a->C, a->H, a->W);
+  if (a->e1_in_hi && a->split && !a->e1_in_lo) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: e1_in_lo");
+  if ((a->n_enc_groups > 1 || a->n_dec_groups > 1) && !a->group_img_end)
+    return fail(DRASIC_ERR_INVALID, "tail_head_fwd: group_img_end");
+  drasic::TailParams p;
+  memset(&p, 0, sizeof(p));
+  p.d3_next = a->d3_next; p.w_d4 = a->w_d4; p.w_e0 = a->w_e0; p.b_e0 = a->b_e0; p.img = a->img;
+  p.recon_prev = a->recon_prev; p.recon_out = a->recon_out; p.dec_out = a->dec_out; p.loss_acc = a->loss_acc;
+  p.e1_in[0] = static_cast<__half*>(a->e1_in_hi); p.e1_in[1] = static_cast<__half*>(a->e1_in_lo);
+  p.perm = a->perm;
+  p.B_pad = a->B_pad; p.C = a->C; p.H = a->H; p.W = a->W; p.mode = a->mode; p.loss_kind = a->loss_kind;
+  p.n_enc_groups = a->n_enc_groups < 1 ? 1 : a->n_enc_groups;
+  p.n_dec_groups = a->n_dec_groups < 1 ? 1 : a->n_dec_groups;
+  p.precise = a->precise; p.split = a->split;
+  p.group_img_end = a->group_img_end;
+  return cuda_fail(drasic::launch_tail_head(p, static_cast<cudaStream_t>(stream)), "tail_head_fwd launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,406 @@
+// ConvLSTM gate kernel for sm_100a: implicit-GEMM 3x3 convolution of [x ; h_prev] on tcgen05
+// tensor cores (TMA-fed, TMEM accumulators) with the LSTM gate nonlinearities, the cell / hidden
+// update and the pixel (un)shuffle of the following PixelShuffleCell fused into the epilogue.
+//
+// Replaces, per cell call, the reference sequence modules/cell.py:117 (input conv), :132 (hidden
+// conv + add), :133-137 (chunk, sigmoid/tanh), :138-139 (c = f*c + i*g ; h = o*tanh(c)) and the
+// PixelShuffleCell that follows it in models/dist_codec.py:70-104 (functions/shuffle.py:4-25).
+//
+// GEMM view:  D[pixels, 4*Co] = A[pixels, 9*(Cin+Co)] * Wp^T
+//   A is never materialised: K block (src, tap, 64-channel chunk) of an M tile of 128 pixels is one
+//   TMA box of the NHWC activation tensor shifted by the tap offset (out-of-bounds = zero padding).
+//   Wp is packed once per weight version (pack.cu): K-major, gate-interleaved so one N tile of
+//   BLOCK_N columns holds the i,f,g,o pre-activations of the same BLOCK_N/4 channels.
+// Numerics: "split" mode carries every operand as fp16 hi + fp16 lo (22 significand bits after
+//   power-of-two pre-scaling) and issues hi*hi + hi*lo + lo*hi with fp32 accumulation, which is
+//   fp32-grade and keeps the emitted codes bit-exact against the fp32 reference; the non-split
+//   mode issues only hi*hi.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+// Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; two TMEM accumulators so the
+//   epilogue of tile i overlaps the MMAs of tile i+1.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace drasic {
+
+namespace {
+
+constexpr int A_TILE_BYTES = TILE_M * BLOCK_K * 2;  // 16 KB
+constexpr int SMEM_DATA_BUDGET = 196608;            // 192 KB of operand stages
+constexpr int NUM_THREADS = 192;
+
+template <bool SPLIT, int BLOCK_N>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int STAGES_RAW = SMEM_DATA_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SLOTS = BLOCK_N / 4;  // channels per N tile
+  static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float sigmoid_precise(float x) {
+  // torch CPU: 1 / (1 + exp(-x)) with ~1 ulp exp and IEEE division
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f);
+}
+
+__device__ __forceinline__ void split_store16(__half* __restrict__ hi, __half* __restrict__ lo,
+                                              const float (&v)[16], bool with_lo) {
+  // v is already multiplied by ACT_SCALE
+  alignas(16) __half h[16];
+  alignas(16) __half l[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    h[i] = __float2half_rn(v[i]);
+    l[i] = __float2half_rn(v[i] - __half2float(h[i]));
+  }
+  reinterpret_cast<uint4*>(hi)[0] = reinterpret_cast<const uint4*>(h)[0];
+  reinterpret_cast<uint4*>(hi)[1] = reinterpret_cast<const uint4*>(h)[1];
+  if (with_lo) {
+    reinterpret_cast<uint4*>(lo)[0] = reinterpret_cast<const uint4*>(l)[0];
+    reinterpret_cast<uint4*>(lo)[1] = reinterpret_cast<const uint4*>(l)[1];
+  }
+}
+
+template <bool SPLIT, int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+convlstm_gates_kernel(const __grid_constant__ GateParams p) {
+  using C = Cfg<SPLIT, BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;       // [STAGES]
+  uint64_t* tmem_full = bars + 2 * C::STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&p.tm_x[0]);
+    ptx::prefetch_tmap(&p.tm_w[0]);
+    if (SPLIT) {
+      ptx::prefetch_tmap(&p.tm_x[1]);
+      ptx::prefetch_tmap(&p.tm_w[1]);
+    }
+    if (p.has_hidden) {
+      ptx::prefetch_tmap(&p.tm_h[0]);
+      if (SPLIT) ptx::prefetch_tmap(&p.tm_h[1]);
+    }
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.n_mtiles * p.n_ntiles;
+  const int cx_chunks = p.Cin / BLOCK_K;
+  const int ch_chunks = p.Co / BLOCK_K;
+  const int nkb = 9 * cx_chunks + (p.has_hidden ? 9 * ch_chunks : 0);
+  const int tiles_x = p.W / p.bw;
+  const int tiles_per_img = (p.H / p.bh) * tiles_x;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_ntiles;
+        const int mt = tile / p.n_ntiles;
+        int n0, y0, x0;
+        if (p.bn > 1) {
+          n0 = mt * p.bn; y0 = 0; x0 = 0;
+        } else {
+          n0 = mt / tiles_per_img;
+          const int rem = mt % tiles_per_img;
+          y0 = (rem / tiles_x) * p.bh;
+          x0 = (rem % tiles_x) * p.bw;
+        }
+        int g = 0;
+        while (g + 1 < p.n_groups && mt >= p.group_mtile_end[g]) ++g;
+        const int wrow = g * 4 * p.Co + nt * BLOCK_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const bool is_h = kb >= 9 * cx_chunks;
+          const int kk = is_h ? kb - 9 * cx_chunks : kb;
+          const int chunks = is_h ? ch_chunks : cx_chunks;
+          const int tap = kk / chunks;
+          const int cc = kk - tap * chunks;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const int kcol = (is_h ? 9 * p.Cin : 0) + kk * BLOCK_K;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          const CUtensorMap* ta = is_h ? p.tm_h : p.tm_x;
+          ptx::tma_load_4d(st, &ta[0], &full_bar[stage], cc * BLOCK_K, x0 + dx, y0 + dy, n0);
+          if (SPLIT)
+            ptx::tma_load_4d(st + A_TILE_BYTES, &ta[1], &full_bar[stage], cc * BLOCK_K, x0 + dx,
+                             y0 + dy, n0);
+          uint8_t* sb = st + (SPLIT ? 2 : 1) * A_TILE_BYTES;
+          ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], kcol, wrow);
+          if (SPLIT)
+            ptx::tma_load_2d(sb + C::B_TILE_BYTES, &p.tm_w[1], &full_bar[stage], kcol, wrow);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(TILE_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;  // bytes inside the 128-byte swizzle row
+            const uint64_t da_hi = ptx::umma_desc_sw128(a_hi + koff);
+            const uint64_t db_hi = ptx::umma_desc_sw128(b_hi + koff);
+            if (SPLIT) {
+              const uint64_t da_lo = ptx::umma_desc_sw128(a_lo + koff);
+              const uint64_t db_lo = ptx::umma_desc_sw128(b_lo + koff);
+              // small terms first, then the dominant one
+              ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
+              ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+            } else {
+              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int xl = row % p.bw;
+    const int yl = (row / p.bw) % p.bh;
+    const int nl = row / (p.bw * p.bh);
+    const int H = p.H, W = p.W, Co = p.Co;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.n_ntiles;
+      const int mt = tile / p.n_ntiles;
+      int n0, y0, x0;
+      if (p.bn > 1) {
+        n0 = mt * p.bn; y0 = 0; x0 = 0;
+      } else {
+        n0 = mt / tiles_per_img;
+        const int rem = mt % tiles_per_img;
+        y0 = (rem / tiles_x) * p.bh;
+        x0 = (rem % tiles_x) * p.bw;
+      }
+      int g = 0;
+      while (g + 1 < p.n_groups && mt >= p.group_mtile_end[g]) ++g;
+      const float inv = __ldg(&p.w_inv_scale[g]);
+      const int n = n0 + nl, y = y0 + yl, x = x0 + xl;
+      const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
+
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+
+#pragma unroll 1
+      for (int j = 0; j < C::SLOTS / 16; ++j) {
+        float gi[16], gf[16], gg[16], go[16];
+        ptx::tmem_ld16(t_row + 0 * C::SLOTS + j * 16, gi);
+        ptx::tmem_ld16(t_row + 1 * C::SLOTS + j * 16, gf);
+        ptx::tmem_ld16(t_row + 2 * C::SLOTS + j * 16, gg);
+        ptx::tmem_ld16(t_row + 3 * C::SLOTS + j * 16, go);
+        ptx::tmem_ld_wait();
+        const int p0 = nt * C::SLOTS + j * 16;  // first physical channel of this chunk
+        float* cptr = p.c_state + pix * Co + p0;
+        float cv[16];
+        if (p.has_cell) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 t = reinterpret_cast<const float4*>(cptr)[v];
+            cv[4 * v + 0] = t.x; cv[4 * v + 1] = t.y; cv[4 * v + 2] = t.z; cv[4 * v + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cv[i] = 0.0f;
+        }
+        float hv[16];
+        if (p.precise) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float ig = sigmoid_precise(gi[i] * inv);
+            const float fg = sigmoid_precise(gf[i] * inv);
+            const float cg = tanhf(gg[i] * inv);
+            const float og = sigmoid_precise(go[i] * inv);
+            // reference rounding: separate multiplies and add (no fma), cell.py:138-139
+            const float cn = __fadd_rn(__fmul_rn(fg, cv[i]), __fmul_rn(ig, cg));
+            cv[i] = cn;
+            hv[i] = __fmul_rn(og, tanhf(cn));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float ig = sigmoid_fast(gi[i] * inv);
+            const float fg = sigmoid_fast(gf[i] * inv);
+            const float cg = tanh_fast(gg[i] * inv);
+            const float og = sigmoid_fast(go[i] * inv);
+            const float cn = fmaf(fg, cv[i], ig * cg);
+            cv[i] = cn;
+            hv[i] = og * tanh_fast(cn);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          reinterpret_cast<float4*>(cptr)[v] =
+              make_float4(cv[4 * v + 0], cv[4 * v + 1], cv[4 * v + 2], cv[4 * v + 3]);
+
+        // consumer copy (fused PixelShuffleCell)
+        if (p.next_mode != NEXT_NONE) {
+          size_t noff;
+          if (p.next_mode == NEXT_SAME) {
+            noff = pix * Co + p0;
+          } else if (p.next_mode == NEXT_DOWN) {
+            const size_t npix = (static_cast<size_t>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+            noff = npix * (4 * Co) + ((y & 1) * 2 + (x & 1)) * Co + p0;
+          } else {  // NEXT_UP
+            const int cq = Co >> 2;
+            const int qq = p0 / cq, cc = p0 - qq * cq;
+            const size_t npix =
+                (static_cast<size_t>(n) * (2 * H) + (2 * y + (qq >> 1))) * (2 * W) + (2 * x + (qq & 1));
+            noff = npix * cq + cc;
+          }
+          if (p.next_f32) {
+            float* np_ = reinterpret_cast<float*>(p.next[0]) + noff;
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              reinterpret_cast<float4*>(np_)[v] =
+                  make_float4(hv[4 * v + 0], hv[4 * v + 1], hv[4 * v + 2], hv[4 * v + 3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hv[i] *= ACT_SCALE;
+        split_store16(p.h_out[0] + pix * Co + p0, p.h_out[1] + pix * Co + p0, hv, SPLIT);
+        if (p.next_mode != NEXT_NONE && !p.next_f32) {
+          size_t noff;
+          if (p.next_mode == NEXT_SAME) {
+            noff = pix * Co + p0;
+          } else if (p.next_mode == NEXT_DOWN) {
+            const size_t npix = (static_cast<size_t>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+            noff = npix * (4 * Co) + ((y & 1) * 2 + (x & 1)) * Co + p0;
+          } else {
+            const int cq = Co >> 2;
+            const int qq = p0 / cq, cc = p0 - qq * cq;
+            const size_t npix =
+                (static_cast<size_t>(n) * (2 * H) + (2 * y + (qq >> 1))) * (2 * W) + (2 * x + (qq & 1));
+            noff = npix * cq + cc;
+          }
+          split_store16(reinterpret_cast<__half*>(p.next[0]) + noff,
+                        reinterpret_cast<__half*>(p.next[1]) + noff, hv, SPLIT);
+        }
+      }
+      // release the accumulator to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <bool SPLIT, int BLOCK_N>
+int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<SPLIT, BLOCK_N>;
+  auto kern = convlstm_gates_kernel<SPLIT, BLOCK_N>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int total = p.n_mtiles * p.n_ntiles;
+  const int grid = total < num_sms ? total : num_sms;
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+size_t convlstm_gates_smem_bytes(bool split, int block_n) {
+  if (split) {
+    if (block_n == 256) return Cfg<true, 256>::SMEM_BYTES;
+    if (block_n == 128) return Cfg<true, 128>::SMEM_BYTES;
+    return Cfg<true, 64>::SMEM_BYTES;
+  }
+  if (block_n == 256) return Cfg<false, 256>::SMEM_BYTES;
+  if (block_n == 128) return Cfg<false, 128>::SMEM_BYTES;
+  return Cfg<false, 64>::SMEM_BYTES;
+}
+
+int launch_convlstm_gates(const GateParams& p, bool split, int block_n, int num_sms,
+                          cudaStream_t stream) {
+  if (split) {
+    switch (block_n) {
+      case 256: return launch_t<true, 256>(p, num_sms, stream);
+      case 128: return launch_t<true, 128>(p, num_sms, stream);
+      case 64: return launch_t<true, 64>(p, num_sms, stream);
+    }
+  } else {
+    switch (block_n) {
+      case 256: return launch_t<false, 256>(p, num_sms, stream);
+      case 128: return launch_t<false, 128>(p, num_sms, stream);
+      case 64: return launch_t<false, 64>(p, num_sms, stream);
+    }
+  }
+  return static_cast<int>(cudaErrorInvalidValue);
+}
+
+}  // namespace drasic

@@ -1,0 +1,55 @@
+// Internal (non-ABI) declarations shared by the DRASIC sm_100a kernels and the C-ABI layer.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace drasic {
+
+constexpr int TILE_M = 128;     // UMMA M: pixels per output tile (= TMEM lanes)
+constexpr int BLOCK_K = 64;     // fp16 elements per K block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;      // K per tcgen05.mma for 16-bit operands
+constexpr int MAX_GROUPS = 64;  // sources (nodes) per launch
+constexpr int ACT_SHIFT = 8;    // activations are stored as fp16(a * 2^8) (+ residual term)
+constexpr float ACT_SCALE = 256.0f;
+constexpr float ACT_INV_SCALE = 1.0f / 256.0f;
+
+// physical channel order of an NHWC activation / state tensor
+enum ChanOrder : int {
+  ORDER_IDENT = 0,  // physical p == logical channel
+  ORDER_QUAD = 1,   // physical p = q*(C/4) + c  <->  logical channel c*4 + q   (q = dy*2+dx)
+};
+// where the gate kernel writes h for its consumer (reference: PixelShuffleCell between the cells,
+// modules/cell.py:147-165, functions/shuffle.py:4-25)
+enum NextMode : int {
+  NEXT_NONE = 0,
+  NEXT_SAME = 1,  // same pixel, same physical channel
+  NEXT_DOWN = 2,  // pixel_unshuffle(2): pixel (y/2,x/2), physical channel ((y&1)*2+(x&1))*Co + p
+  NEXT_UP = 3,    // pixel_shuffle(2):  own order QUAD, p = q*(Co/4)+c -> pixel (2y+q/2, 2x+q%2), ch c
+};
+
+struct GateParams {
+  CUtensorMap tm_x[2];  // layer input  NHWC fp16 {hi, lo}
+  CUtensorMap tm_h[2];  // previous hidden state NHWC fp16 {hi, lo}
+  CUtensorMap tm_w[2];  // packed gate weights [groups*4Co, 9Cin+9Co] fp16 {hi, lo}
+  float* c_state;       // [B,H,W,Co] fp32, updated in place
+  __half* h_out[2];     // new hidden state (own layout), {hi, lo}
+  void* next[2];        // consumer copy of h: fp16 {hi, lo} or fp32 (next[0])
+  const float* w_inv_scale;  // [n_groups] power of two: 1 / (ACT_SCALE * weight scale)
+  int H, W, Cin, Co;
+  int bw, bh, bn;  // TMA box (pixels): bw*bh*bn == 128
+  int n_mtiles, n_ntiles;
+  int has_hidden, has_cell;  // 0 on the first iteration (state is zero)
+  int next_mode, next_f32;
+  int precise;               // 1: IEEE exp/div/tanh (parity mode); 0: tanh.approx
+  int n_groups;
+  const int* group_mtile_end;  // device [n_groups]: group g owns m-tiles [end[g-1], end[g])
+};
+
+// launches the persistent tcgen05 gate kernel; returns a cudaError_t as int
+int launch_convlstm_gates(const GateParams& p, bool split, int block_n, int num_sms,
+                          cudaStream_t stream);
+size_t convlstm_gates_smem_bytes(bool split, int block_n);
+
+}  // namespace drasic

@@ -1,0 +1,96 @@
+// Weight packing for the gate kernel: fp32 OIHW conv weights of one ConvLSTMCell
+// (modules/cell.py:82-100: cell[0]['in'] [4Co,Cin,3,3] and cell[0]['hidden'] [4Co,Co,3,3], no bias)
+// -> K-major fp16 {hi, lo} matrix [4Co rows, 9*Cin + 9*Co] in the tile order the kernel expects:
+//   row  r = nt*BLOCK_N + gate*SLOTS + s     (SLOTS = BLOCK_N/4, physical channel p = nt*SLOTS + s)
+//   col  k = [x part: tap*Cin + pin] [h part: 9*Cin + tap*Co + ph]
+// Physical->logical channel maps follow ChanOrder (kernels.h). Values are multiplied by a per-tensor
+// power of two so that max|w| lands in [1024, 2048) (exact; undone in the gate epilogue).
+#include "kernels.h"
+
+namespace drasic {
+
+namespace {
+
+__device__ __forceinline__ int logical_of(int p, int C, int order) {
+  if (order == ORDER_QUAD) {
+    const int cq = C >> 2;
+    const int q = p / cq, c = p - q * cq;
+    return c * 4 + q;
+  }
+  return p;
+}
+
+__global__ void amax_kernel(const float* __restrict__ a, size_t na, const float* __restrict__ b,
+                            size_t nb, unsigned int* __restrict__ out) {
+  float m = 0.0f;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < na + nb;
+       i += stride) {
+    const float v = i < na ? a[i] : b[i - na];
+    m = fmaxf(m, fabsf(v));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order as uints
+}
+
+__global__ void pack_kernel(const float* __restrict__ w_in, const float* __restrict__ w_h, int Cin,
+                            int Co, int in_order, int out_order, int block_n,
+                            const unsigned int* __restrict__ amax_bits, __half* __restrict__ out_hi,
+                            __half* __restrict__ out_lo, float* __restrict__ inv_scale_out) {
+  const int K = 9 * (Cin + Co);
+  const size_t total = static_cast<size_t>(4 * Co) * K;
+  const float amax = __uint_as_float(*amax_bits);
+  int shift = 0;
+  if (amax > 0.0f && isfinite(amax)) {
+    int e;
+    frexpf(amax, &e);  // amax = m * 2^e, m in [0.5,1)  ->  amax * 2^(11-e) in [1024, 2048)
+    shift = 11 - e;
+  }
+  const float scale = ldexpf(1.0f, shift);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = ldexpf(1.0f, -(shift + ACT_SHIFT));
+  const int slots = block_n >> 2;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += stride) {
+    const int r = static_cast<int>(idx / K);
+    const int k = static_cast<int>(idx - static_cast<size_t>(r) * K);
+    const int nt = r / block_n;
+    const int rr = r - nt * block_n;
+    const int gate = rr / slots;
+    const int s = rr - gate * slots;
+    const int co = logical_of(nt * slots + s, Co, out_order);
+    const int orow = gate * Co + co;  // gates.chunk(4, 1): i, f, g, o blocks (cell.py:133)
+    float v;
+    if (k < 9 * Cin) {
+      const int tap = k / Cin, pin = k - tap * Cin;
+      const int ci = logical_of(pin, Cin, in_order);
+      v = w_in[(static_cast<size_t>(orow) * Cin + ci) * 9 + tap];
+    } else {
+      const int kk = k - 9 * Cin;
+      const int tap = kk / Co, ph = kk - tap * Co;
+      const int ch = logical_of(ph, Co, out_order);
+      v = w_h[(static_cast<size_t>(orow) * Co + ch) * 9 + tap];
+    }
+    v *= scale;
+    const __half hi = __float2half_rn(v);
+    out_hi[idx] = hi;
+    out_lo[idx] = __float2half_rn(v - __half2float(hi));
+  }
+}
+
+}  // namespace
+
+int launch_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
+                             int out_order, int block_n, __half* out_hi, __half* out_lo,
+                             float* inv_scale_out, unsigned int* scratch_amax,
+                             cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(scratch_amax, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const size_t na = static_cast<size_t>(4 * Co) * Cin * 9, nb = static_cast<size_t>(4 * Co) * Co * 9;
+  amax_kernel<<<296, 256, 0, stream>>>(w_in, na, w_h, nb, scratch_amax);
+  pack_kernel<<<1184, 256, 0, stream>>>(w_in, w_h, Cin, Co, in_order, out_order, block_n,
+                                        scratch_amax, out_hi, out_lo, inv_scale_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace drasic

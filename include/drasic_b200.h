@@ -1,0 +1,117 @@
+/*
+ * drasic_b200.h -- C ABI of the B200 (sm_100a) implementation of DRASIC's recurrent residual
+ * coding loop (ConvLSTM encoder -> sign binarizer -> ConvLSTM decoder, iterated T times).
+ *
+ * The reference (diaoenmao/DRASIC, pure PyTorch) has no FFI of its own; the entry points below are
+ * what a binding for this path replaces, one per fused kernel, cited as file:line of the reference
+ * under src/.  All functions return 0 on success or a negative drasic_status / positive
+ * cudaError_t value; drasic_last_error() gives the message of the last failure on the calling
+ * thread.  No function throws, allocates device memory, or synchronises the device: every buffer
+ * is owned by the caller, every launch is asynchronous on `stream` (a cudaStream_t).  Pointers
+ * are DEVICE pointers unless the name ends in `_host`.
+ *
+ * Layouts.  Activations and recurrent state are NHWC.  An activation tensor a (|a| <= 1) is stored
+ * as one or two fp16 planes: hi = fp16(a * 2^8) and, in split mode, lo = fp16(a * 2^8 - hi).
+ * Channels may be stored in "quad" order (DRASIC_ORDER_QUAD), the order in which the fused
+ * pixel (un)shuffle stores are contiguous: physical p = q*(C/4) + c  <->  logical channel c*4 + q.
+ * The batch is node-sorted and padded: slot s holds original image perm[s] (or -1), every node's
+ * slot range is a multiple of 8 slots, group_img_end[g] is the exclusive end slot of node g.
+ */
+#ifndef DRASIC_B200_H_
+#define DRASIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRASIC_ABI_VERSION 1
+#define DRASIC_MAX_GROUPS 64
+
+typedef enum {
+  DRASIC_OK = 0,
+  DRASIC_ERR_INVALID = -1,     /* bad argument / unsupported shape (mirrors the reference's ValueError) */
+  DRASIC_ERR_NO_DEVICE = -2,   /* no sm_100 device / driver entry point unavailable */
+  DRASIC_ERR_TENSORMAP = -3    /* cuTensorMapEncodeTiled rejected a descriptor */
+} drasic_status;
+
+enum { DRASIC_ORDER_IDENT = 0, DRASIC_ORDER_QUAD = 1 };
+enum { DRASIC_NEXT_NONE = 0, DRASIC_NEXT_SAME = 1, DRASIC_NEXT_DOWN = 2, DRASIC_NEXT_UP = 3 };
+enum { DRASIC_LOSS_MAE = 0, DRASIC_LOSS_MSE = 1, DRASIC_LOSS_BCE = 2 };
+enum { DRASIC_TAIL_INIT = 0, DRASIC_TAIL_FIRST = 1, DRASIC_TAIL_STEP = 2 };
+
+int drasic_version(void);
+const char* drasic_last_error(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int drasic_device_sms(void);
+
+/* bytes of one packed fp16 plane for a ConvLSTM cell: 4*Co * 9*(Cin+Co) * 2 */
+size_t drasic_packed_weight_bytes(int Cin, int Co);
+
+/*
+ * Pack the gate weights of one ConvLSTMCell (modules/cell.py:82-100: cell[0]['in'].weight
+ * [4Co,Cin,3,3], cell[0]['hidden'].weight [4Co,Co,3,3], fp32 OIHW, no bias) into the K-major,
+ * gate-interleaved fp16 {hi,lo} planes the gate kernel reads, scaled by a power of two.
+ * out_hi/out_lo: drasic_packed_weight_bytes each; inv_scale_out: 1 float; scratch: 4 bytes.
+ */
+int drasic_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
+                             int out_order, int block_n, void* out_hi, void* out_lo,
+                             float* inv_scale_out, void* scratch4, void* stream);
+
+/*
+ * One ConvLSTMCell step for the whole (node-grouped) batch, replacing ConvLSTMCell.forward
+ * (modules/cell.py:110-144: in-conv :117, hidden-conv :132, gates :133-137, state update :138-139)
+ * and the PixelShuffleCell that follows it (modules/cell.py:147-165).
+ */
+typedef struct {
+  const void* x_hi; const void* x_lo;   /* [B_pad,H,W,Cin] fp16 planes (lo unused unless split) */
+  const void* h_hi; const void* h_lo;   /* previous h [B_pad,H,W,Co]; unused when has_state == 0 */
+  const void* w_hi; const void* w_lo;   /* packed weights, n_groups consecutive cells */
+  const float* w_inv_scale;             /* [n_groups] from drasic_pack_lstm_weights */
+  float* c_state;                       /* [B_pad,H,W,Co] fp32, in place */
+  void* h_out_hi; void* h_out_lo;       /* new h (must not alias h_hi/h_lo) */
+  void* next_hi; void* next_lo;         /* consumer copy; fp32 tensor in next_hi when next_f32 */
+  const int* group_mtile_end;           /* device [n_groups]: exclusive end M-tile (128 pixels) per node */
+  int B_pad, H, W, Cin, Co;
+  int n_groups;
+  int has_state;                        /* 0 on iteration 0: h = c = 0 (cell.py:118-129) */
+  int next_mode, next_f32;
+  int split;                            /* 1: fp16 hi+lo operands (fp32-grade), 0: fp16 only */
+  int precise;                          /* 1: IEEE exp/div/tanh, 0: tanh.approx */
+  int block_n;                          /* N tile: 256, 128 or 64 (must match the packing) */
+} drasic_convlstm_args;
+int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream);
+
+/*
+ * Encoder tail + quantizer + bit-pack + decoder head, replacing models/dist_codec.py:83-85 (ConvCell
+ * 128->code), functions/quantize.py:9-18, models/dist_codec.py:16-18 (pack) and :89-91 (ConvCell
+ * code->128).
+ */
+typedef struct {
+  const float* h_e3; const float* w_e4; const float* w_d0; const float* noise; const int* perm;
+  float* code_out; float* z_out; uint8_t* bits_out; void* d1_in_hi; void* d1_in_lo;
+  float* d0_out_f32;
+  const int* group_img_end;       /* device [max(n_enc_groups,n_dec_groups)]: exclusive end slot per node */
+  int B_pad, HW, Ch, code, n_enc_groups, n_dec_groups, precise, split;
+} drasic_bottleneck_args;
+int drasic_bottleneck_fwd(const drasic_bottleneck_args* a, void* stream);
+
+/*
+ * Decoder tail + reconstruction / loss / residual + encoder head, replacing
+ * models/dist_codec.py:101-103 (ConvCell 32->C), :56-59 and :38, :71-74 (ConvCell C->32, unshuffle).
+ */
+typedef struct {
+  const float* d3_next; const float* w_d4; const float* w_e0; const float* b_e0;
+  const float* img; const float* recon_prev; float* recon_out; float* dec_out; double* loss_acc;
+  void* e1_in_hi; void* e1_in_lo; const int* perm;
+  const int* group_img_end;       /* device, as above */
+  int B_pad, C, H, W, mode, loss_kind, n_enc_groups, n_dec_groups, precise, split;
+} drasic_tail_head_args;
+int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRASIC_B200_H_ */

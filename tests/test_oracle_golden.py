@@ -1,0 +1,136 @@
+"""Pins oracle/drasic_oracle.py against fixtures produced by the reference's own modules
+(tests/golden/make_golden.py).  CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import drasic_oracle as O
+
+
+def digest(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd.keys()):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+@pytest.fixture(scope='module')
+def cells(golden_dir):
+    return np.load(os.path.join(golden_dir, 'cells.npz'))
+
+
+def test_shuffle_bit_exact(cells):
+    x = torch.from_numpy(cells['shuffle_in'])
+    assert np.array_equal(O.pixel_unshuffle(x, 2).numpy(), cells['unshuffle_out'])
+    assert np.array_equal(O.pixel_shuffle(x, 2).numpy(), cells['shuffle_out'])
+    # round trip
+    assert torch.equal(O.pixel_shuffle(O.pixel_unshuffle(x, 2), 2), x)
+
+
+def test_quantize_eval_edges(cells):
+    q = O.quantize(torch.from_numpy(cells['quant_in']), False).numpy()
+    assert np.array_equal(q, cells['quant_eval'], equal_nan=True)
+    # reference quirks: -0.0 -> +1, |x| > 1 and NaN pass through
+    assert q[3] == 1.0 and q[0] == -2.0 and q[9] == 1.5 and np.isnan(q[10])
+
+
+def test_quantize_train_with_given_noise(cells):
+    q = O.quantize(torch.from_numpy(cells['quant_train_in']), True, torch.from_numpy(cells['quant_train_u']))
+    assert np.array_equal(q.numpy(), cells['quant_train'])
+
+
+def test_quantize_backward_identity():
+    x = torch.linspace(-0.9, 0.9, 7, requires_grad=True)
+    O.quantize(x, False).backward(torch.arange(7.0))
+    assert torch.equal(x.grad, torch.arange(7.0))
+
+
+@pytest.mark.parametrize('tag,cin,co,hw', [('lstm_a', 128, 128, 4), ('lstm_b', 64, 64, 8)])
+def test_convlstm_cell(cells, tag, cin, co, hw):
+    import torch.nn as nn
+    torch.manual_seed(21)
+    w_in = nn.Conv2d(cin, 4 * co, 3, 1, 1, bias=False).weight.detach()
+    w_h = nn.Conv2d(co, 4 * co, 3, 1, 1, bias=False).weight.detach()
+    sd = {'cell.cell.0.in.cell.cell.main.weight': w_in, 'cell.cell.0.hidden.cell.cell.main.weight': w_h}
+    assert digest(sd) == str(cells[tag + '_digest'])
+    gi = torch.Generator().manual_seed(22)
+    state = None
+    torch.set_num_threads(1)
+    for t in range(3):
+        x = torch.rand(2, cin, hw, hw, generator=gi) * 2 - 1
+        h, state = O.convlstm_cell(x, state, w_in, w_h)
+        np.testing.assert_allclose(h.numpy(), cells[tag + '_h'][t], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(state[1].numpy(), cells[tag + '_c'][t], rtol=0, atol=1e-6)
+
+
+def test_conv_cell(cells):
+    y = O.conv_cell(torch.from_numpy(cells['convcell_in']), torch.from_numpy(cells['convcell_w']),
+                    torch.from_numpy(cells['convcell_b']))
+    np.testing.assert_allclose(y.numpy(), cells['convcell_out'], rtol=0, atol=1e-6)
+
+
+def test_loop_mnist_single_source(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'loop_mnist_m1.npz'))
+    sd = O.init_state_dict(num_channel=1, code_size=8, num_node=1, seed=0)
+    assert list(sd.keys()) == [str(k) for k in g['keys']]
+    assert digest(sd) == str(g['digest'])
+    torch.set_num_threads(1)
+    with torch.no_grad():
+        out = O.codec_forward(sd, torch.from_numpy(g['img']), torch.from_numpy(g['label']), 16, 1)
+    codes = torch.stack(out['code_pm1']).numpy().astype(np.int8)
+    assert np.array_equal(codes, g['codes'])                       # bit-exact codes
+    np.testing.assert_allclose(torch.stack(out['z']).numpy(), g['z'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out['img'][0].numpy(), g['recon_first'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out['img'][-1].numpy(), g['recon_last'], rtol=0, atol=1e-5)
+    ps = [O.psnr(r, torch.from_numpy(g['img'])) for r in out['img']]
+    np.testing.assert_allclose(ps, g['psnr'], rtol=0, atol=1e-3)
+    assert abs(out['loss'].item() - float(g['loss'])) < 1e-6
+    # reference pack() is degenerate: every byte 0xFF, only nbytes matters (BPP)
+    assert [c.nbytes for c in out['code']] == list(g['code_nbytes'])
+    assert tuple(out['code'][-1].shape) == tuple(g['code_shape_last'])
+    assert np.array_equal(np.unique(out['code'][-1]), g['code_byte_values'])
+    assert O.bpp(out['code'][-1], torch.from_numpy(g['img'])) == 2.0
+
+
+def test_loop_cifar_two_sources_eval_and_train(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'loop_cifar_m2.npz'))
+    sd = O.init_state_dict(num_channel=3, code_size=8, num_node=2, seed=3)
+    assert digest(sd) == str(g['digest'])
+    img, label = torch.from_numpy(g['img']), torch.from_numpy(g['label'])
+    torch.set_num_threads(1)
+    with torch.no_grad():
+        out = O.codec_forward(sd, img, label, 4, 2)
+    assert np.array_equal(torch.stack(out['code_pm1']).numpy().astype(np.int8), g['codes'])
+    np.testing.assert_allclose(torch.stack(out['img']).numpy(), g['recon'], rtol=0, atol=1e-6)
+    assert abs(out['loss'].item() - float(g['loss'])) < 1e-6
+    # training: stochastic binarizer with the recorded uniforms, full BPTT
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    noise = [torch.from_numpy(n) for n in g['train_noise']]
+    out = O.codec_forward(sdg, img, label, 4, 2, training=True, noise=noise)
+    assert np.array_equal(torch.stack(out['code_pm1']).numpy().astype(np.int8), g['train_codes'])
+    assert abs(out['loss'].item() - float(g['train_loss'])) < 1e-6
+    out['loss'].backward()
+    norms = {str(k): v for k, v in zip(g['grad_keys'], g['grad_norms'])}
+    for k, p in sdg.items():
+        assert abs(float(p.grad.double().norm()) - norms[k]) <= 1e-4 * max(norms[k], 1e-6), k
+    np.testing.assert_allclose(sdg['model.encoder.0.0.cell.cell.main.weight'].grad.numpy(), g['g_e0_w'], rtol=1e-3, atol=1e-7)
+    np.testing.assert_allclose(sdg['model.decoder.7.cell.cell.main.weight'].grad.numpy(), g['g_d4_w'], rtol=1e-3, atol=1e-7)
+    np.testing.assert_allclose(sdg['model.decoder.5.cell.cell.0.in.cell.cell.main.weight'].grad[:8, :8].numpy(),
+                               g['g_d3_in_slice'], rtol=1e-3, atol=1e-8)
+
+
+def test_loop_sep_codec(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'loop_sep_m2.npz'))
+    sd = O.init_state_dict(num_channel=3, code_size=8, num_node=2, separate=True, seed=6)
+    assert list(sd.keys()) == [str(k) for k in g['keys']]
+    assert digest(sd) == str(g['digest'])
+    torch.set_num_threads(1)
+    with torch.no_grad():
+        out = O.codec_forward(sd, torch.from_numpy(g['img']), torch.from_numpy(g['label']), 3, 2, separate=True)
+    assert np.array_equal(torch.stack(out['code_pm1']).numpy().astype(np.int8), g['codes'])
+    np.testing.assert_allclose(torch.stack(out['img']).numpy(), g['recon'], rtol=0, atol=1e-6)
+    assert abs(out['loss'].item() - float(g['loss'])) < 1e-6
