@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI in include/drasic_b200.h (libdrasic_b200.so, built by
+__graft_entry__.build()).  There is no fallback: a missing library or a failing call raises."""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, 'libdrasic_b200.so')
+
+ORDER_IDENT, ORDER_QUAD = 0, 1
+NEXT_NONE, NEXT_SAME, NEXT_DOWN, NEXT_UP = 0, 1, 2, 3
+LOSS_KINDS = {'mae': 0, 'mse': 1, 'bce': 2}
+TAIL_INIT, TAIL_FIRST, TAIL_STEP = 0, 1, 2
+
+vp, ip, fp = C.c_void_p, C.c_int, C.c_void_p
+
+
+class ConvLSTMArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('x_hi', 'x_lo', 'h_hi', 'h_lo', 'w_hi', 'w_lo', 'w_inv_scale', 'c_state',
+                                  'h_out_hi', 'h_out_lo', 'next_hi', 'next_lo', 'group_mtile_end')] + \
+               [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'has_state', 'next_mode',
+                                  'next_f32', 'split', 'precise', 'block_n')]
+
+
+class BottleneckArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('h_e3', 'w_e4', 'w_d0', 'noise', 'perm', 'code_out', 'z_out', 'bits_out',
+                                  'd1_in_hi', 'd1_in_lo', 'd0_out_f32', 'group_img_end')] + \
+               [(n, ip) for n in ('B_pad', 'HW', 'Ch', 'code', 'n_enc_groups', 'n_dec_groups', 'precise', 'split')]
+
+
+class TailHeadArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('d3_next', 'w_d4', 'w_e0', 'b_e0', 'img', 'recon_prev', 'recon_out',
+                                  'dec_out', 'loss_acc', 'e1_in_hi', 'e1_in_lo', 'perm', 'group_img_end')] + \
+               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'mode', 'loss_kind', 'n_enc_groups', 'n_dec_groups',
+                                  'precise', 'split')]
+
+
+# every symbol include/drasic_b200.h declares (tests check the library exports all of them)
+SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes',
+           'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd')
+
+_lib = None
+
+
+class DrasicError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DrasicError('{} not found: build the CUDA extension first (python -c "import __graft_entry__ as g; '
+                          'g.build()"); there is no CPU fallback'.format(LIB_PATH))
+    L = C.CDLL(LIB_PATH)
+    L.drasic_version.restype = C.c_int
+    L.drasic_last_error.restype = C.c_char_p
+    L.drasic_device_sms.restype = C.c_int
+    L.drasic_packed_weight_bytes.restype = C.c_size_t
+    L.drasic_packed_weight_bytes.argtypes = [C.c_int, C.c_int]
+    L.drasic_pack_lstm_weights.restype = C.c_int
+    L.drasic_pack_lstm_weights.argtypes = [vp, vp, ip, ip, ip, ip, ip, vp, vp, vp, vp, vp]
+    L.drasic_convlstm_fwd.restype = C.c_int
+    L.drasic_convlstm_fwd.argtypes = [C.POINTER(ConvLSTMArgs), vp]
+    L.drasic_bottleneck_fwd.restype = C.c_int
+    L.drasic_bottleneck_fwd.argtypes = [C.POINTER(BottleneckArgs), vp]
+    L.drasic_tail_head_fwd.restype = C.c_int
+    L.drasic_tail_head_fwd.argtypes = [C.POINTER(TailHeadArgs), vp]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().drasic_last_error().decode(errors='replace')
+        if rc == -1:
+            raise ValueError('Not valid {}: {}'.format(what, msg))   # mirrors the reference's ValueError
+        raise DrasicError('{} failed (code {}): {}'.format(what, rc, msg))
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else t.data_ptr()
