@@ -232,4 +232,17 @@ int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream) {
   return cuda_fail(drasic::launch_tail_head(p, static_cast<cudaStream_t>(stream)), "tail_head_fwd launch");
 }
 
+int drasic_conv1x1_fwd(const float* x, const float* w, const float* b, float* y, int N, int Cin,
+                       int Cout, int HW, int act, void* stream) {
+  if (!x || !w || !y || N <= 0 || Cin <= 0 || Cout <= 0 || HW <= 0) return fail(DRASIC_ERR_INVALID, "conv1x1_fwd: bad argument");
+  if (act < 0 || act > 7) return fail(DRASIC_ERR_INVALID, "conv1x1_fwd: activation %d", act);
+  return cuda_fail(drasic::launch_conv1x1(x, w, b, y, N, Cin, Cout, HW, act, static_cast<cudaStream_t>(stream)), "conv1x1_fwd launch");
+}
+
+int drasic_quantize_fwd(const float* x, const float* u, float* y, size_t n, void* stream) {
+  if (!x || !y) return fail(DRASIC_ERR_INVALID, "quantize_fwd: null pointer");
+  if (n == 0) return 0;
+  return cuda_fail(drasic::launch_quantize(x, u, y, n, static_cast<cudaStream_t>(stream)), "quantize_fwd launch");
+}
+
 }  // extern "C"

@@ -253,6 +253,59 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_head_kernel(const TailParam
   }
 }
 
+
+// ------------------------------------------------------------------ stand-alone cells
+// ConvCell with a 1x1 kernel called outside the fused loop (modules/cell.py:49-72): NCHW fp32 in/out.
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_TANH: return tanhf(v);
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_SIGMOID: return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+    case ACT_HARDTANH: return fminf(fmaxf(v, -1.0f), 1.0f);
+    case ACT_ELU: case ACT_CELU: return v > 0.0f ? v : expm1f(v);
+    case ACT_SELU: return 1.0507009873554804934193349852946f * (v > 0.0f ? v : 1.6732632423543772848170429916717f * expm1f(v));
+    default: return v;
+  }
+}
+
+__global__ void conv1x1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                               const float* __restrict__ b, float* __restrict__ y, int N, int Cin,
+                               int Cout, int HW, int act) {
+  const size_t total = static_cast<size_t>(N) * Cout * HW;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total; idx += stride) {
+    const int pix = static_cast<int>(idx % HW);
+    const int o = static_cast<int>((idx / HW) % Cout);
+    const size_t n = idx / (static_cast<size_t>(HW) * Cout);
+    const float* xr = x + n * Cin * HW + pix;
+    const float* wr = w + static_cast<size_t>(o) * Cin;
+    double acc = 0.0;
+    for (int c = 0; c < Cin; ++c)
+      acc = fma(static_cast<double>(__ldg(wr + c)), static_cast<double>(xr[static_cast<size_t>(c) * HW]), acc);
+    if (b) acc += static_cast<double>(b[o]);
+    y[idx] = apply_act(static_cast<float>(acc), act);
+  }
+}
+
+// Quantize.forward (functions/quantize.py:9-18), element-wise; u == nullptr -> deterministic sign
+__global__ void quantize_kernel(const float* __restrict__ x, const float* __restrict__ u,
+                                float* __restrict__ y, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const float z = x[i];
+    float q = z;
+    if (u) {
+      const float pr = (z + 1.0f) / 2.0f;
+      if (pr >= u[i]) q = 1.0f;
+      else if (pr < u[i]) q = -1.0f;
+    } else {
+      if (z >= 0.0f && z <= 1.0f) q = 1.0f;
+      else if (z >= -1.0f && z < 0.0f) q = -1.0f;
+    }
+    y[i] = q;
+  }
+}
+
 }  // namespace
 
 int launch_bottleneck(const BottleneckParams& p, cudaStream_t stream) {
@@ -268,4 +321,19 @@ int launch_tail_head(const TailParams& p, cudaStream_t stream) {
   return static_cast<int>(cudaGetLastError());
 }
 
+}  // namespace drasic
+
+namespace drasic {
+int launch_conv1x1(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout,
+                   int HW, int act, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(N) * Cout * HW;
+  const int blocks = static_cast<int>(total / 256 + 1 < 148 * 8 ? total / 256 + 1 : 148 * 8);
+  conv1x1_kernel<<<blocks, 256, 0, stream>>>(x, w, b, y, N, Cin, Cout, HW, act);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_quantize(const float* x, const float* u, float* y, size_t n, cudaStream_t stream) {
+  const int blocks = static_cast<int>(n / 256 + 1 < 148 * 8 ? n / 256 + 1 : 148 * 8);
+  quantize_kernel<<<blocks, 256, 0, stream>>>(x, u, y, n);
+  return static_cast<int>(cudaGetLastError());
+}
 }  // namespace drasic

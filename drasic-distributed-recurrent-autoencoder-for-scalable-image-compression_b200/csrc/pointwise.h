@@ -4,6 +4,7 @@
 
 namespace drasic {
 
+enum ActKind : int { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3, ACT_HARDTANH = 4, ACT_ELU = 5, ACT_SELU = 6, ACT_CELU = 7 };  // modules/cell.py:23-46
 enum LossKind : int { LOSS_MAE = 0, LOSS_MSE = 1, LOSS_BCE = 2 };  // dist_codec.py:24-34
 enum TailMode : int {
   TAIL_INIT = 0,   // before iteration 0: x = img*2-1 -> encoder head only
@@ -49,6 +50,9 @@ struct TailParams {
 
 int launch_bottleneck(const BottleneckParams& p, cudaStream_t stream);
 int launch_tail_head(const TailParams& p, cudaStream_t stream);
+int launch_conv1x1(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout,
+                   int HW, int act, cudaStream_t stream);
+int launch_quantize(const float* x, const float* u, float* y, size_t n, cudaStream_t stream);
 int launch_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
                              int out_order, int block_n, __half* out_hi, __half* out_lo,
                              float* inv_scale_out, unsigned int* scratch_amax, cudaStream_t stream);

@@ -10,6 +10,7 @@ ORDER_IDENT, ORDER_QUAD = 0, 1
 NEXT_NONE, NEXT_SAME, NEXT_DOWN, NEXT_UP = 0, 1, 2, 3
 LOSS_KINDS = {'mae': 0, 'mse': 1, 'bce': 2}
 TAIL_INIT, TAIL_FIRST, TAIL_STEP = 0, 1, 2
+ACT_KINDS = {'none': 0, 'tanh': 1, 'relu': 2, 'sigmoid': 3, 'hardtanh': 4, 'elu': 5, 'selu': 6, 'celu': 7}
 
 vp, ip, fp = C.c_void_p, C.c_int, C.c_void_p
 
@@ -36,7 +37,8 @@ class TailHeadArgs(C.Structure):
 
 # every symbol include/drasic_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes',
-           'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd')
+           'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
+           'drasic_conv1x1_fwd', 'drasic_quantize_fwd')
 
 _lib = None
 
@@ -66,6 +68,10 @@ def lib():
     L.drasic_bottleneck_fwd.argtypes = [C.POINTER(BottleneckArgs), vp]
     L.drasic_tail_head_fwd.restype = C.c_int
     L.drasic_tail_head_fwd.argtypes = [C.POINTER(TailHeadArgs), vp]
+    L.drasic_conv1x1_fwd.restype = C.c_int
+    L.drasic_conv1x1_fwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, vp]
+    L.drasic_quantize_fwd.restype = C.c_int
+    L.drasic_quantize_fwd.argtypes = [vp, vp, vp, C.c_size_t, vp]
     _lib = L
     return L
 

@@ -1,0 +1,157 @@
+"""Shared implementation of the two codec Models (reference models/dist_codec.py:10-65 and
+models/sep_codec.py:10-66): the architecture spec builders and the fused forward that hands the whole
+T-iteration residual loop to engine.CodecEngine."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import config
+from engine.codec import CodecEngine
+from modules.cell import ConvCell, ConvLSTMCell, PixelShuffleCell
+from utils import apply_fn
+from .utils import make_model
+
+
+def _conv(cin, cout, bias):
+    return {'cell': 'ConvCell', 'input_size': cin, 'output_size': cout, 'kernel_size': 1, 'stride': 1,
+            'padding': 0, 'bias': bias, 'activation': config.PARAM['activation'],
+            'normalization': config.PARAM['normalization']}
+
+
+def _lstm(cin, cout):
+    return {'cell': 'ConvLSTMCell', 'input_size': cin, 'output_size': cout, 'kernel_size': 3, 'stride': 1,
+            'padding': 1, 'bias': False, 'num_layers': 1, 'activation': config.PARAM['activation']}
+
+
+def _shuffle(mode):
+    return {'cell': 'PixelShuffleCell', 'mode': mode, 'scale_factor': 2}
+
+
+def encoder_spec(head_bias):
+    """C -> 32 @HxW | down | LSTM 128->128 | down | LSTM 512->128 | down | LSTM 512->128 | 128 -> code
+    (dist_codec.py:70-86; the head conv has a bias in dist_codec and none in sep_codec.py:73)"""
+    return (_conv(config.PARAM['num_channel'], 32, head_bias), _shuffle('down'), _lstm(128, 128),
+            _shuffle('down'), _lstm(512, 128), _shuffle('down'), _lstm(512, 128),
+            _conv(128, config.PARAM['code_size'], False))
+
+
+def decoder_spec():
+    """code -> 128 | LSTM 128->512 | up | LSTM 128->512 | up | LSTM 128->128 | up | 32 -> C
+    (dist_codec.py:88-104)"""
+    return (_conv(config.PARAM['code_size'], 128, False), _lstm(128, 512), _shuffle('up'), _lstm(128, 512),
+            _shuffle('up'), _lstm(128, 128), _shuffle('up'), _conv(32, config.PARAM['num_channel'], False))
+
+
+_ENC_KINDS = (ConvCell, PixelShuffleCell, ConvLSTMCell, PixelShuffleCell, ConvLSTMCell, PixelShuffleCell,
+              ConvLSTMCell, ConvCell)
+_DEC_KINDS = (ConvCell, ConvLSTMCell, PixelShuffleCell, ConvLSTMCell, PixelShuffleCell, ConvLSTMCell,
+              PixelShuffleCell, ConvCell)
+
+
+class _LoopFunction(torch.autograd.Function):
+    """The whole T-iteration loop as one autograd node: forward launches the fused kernels, backward
+    (backward-through-time) is provided by the engine when it has been built with training support."""
+
+    @staticmethod
+    def forward(ctx, model, img, label, noise, *params):
+        out = model._run_engine(img, label, noise)
+        ctx.model = model
+        ctx.saved = out
+        ctx.mark_non_differentiable(out['recon'], out['codes'], out['bits'])
+        loss = CodecEngine.loss_from_acc(out['loss_acc'], img.numel())
+        return loss, out['recon'], out['codes'], out['bits']
+
+    @staticmethod
+    def backward(ctx, g_loss, g_recon, g_codes, g_bits):
+        grads = ctx.model._engine.backward(ctx.saved, g_loss)
+        return (None, None, None, None) + tuple(grads)
+
+
+class CodecModel(nn.Module):
+    separate = False
+
+    def __init__(self):
+        super(CodecModel, self).__init__()
+        self.model = make_model(config.PARAM['model'])
+        self._engine = None
+        self._engine_key = None
+
+    # ---- reference API -------------------------------------------------------------------------
+    def pack(self, code):
+        """dist_codec.py:16-18.  (-1 and +1 are both non-zero, so every byte is 0xFF; only the size of
+        the result is consumed downstream, metrics.py:84-89.)"""
+        return np.packbits(code.detach().cpu().numpy().astype(np.int8)).reshape(-1, 1)
+
+    def unpack(self, code):
+        """dist_codec.py:20-22"""
+        return torch.from_numpy(code.astype(np.float32)).to(config.PARAM['device'])
+
+    def loss_fn(self, output, target):
+        """dist_codec.py:24-34"""
+        kind = config.PARAM['loss_fn']
+        if kind == 'bce':
+            return F.binary_cross_entropy(output, target)
+        if kind == 'mse':
+            return F.mse_loss(output, target)
+        if kind == 'mae':
+            return F.l1_loss(output, target)
+        raise ValueError('Not valid loss function')
+
+    # ---- fused path ----------------------------------------------------------------------------
+    def _check_architecture(self):
+        M = config.PARAM['num_node']
+        enc = self.model['encoder']
+        decs = list(self.model['decoder']) if self.separate else [self.model['decoder']]
+        if len(enc) != M or (self.separate and len(decs) != M):
+            raise ValueError('Not valid model: num_node does not match the module tree')
+        for seq, kinds in [(e, _ENC_KINDS) for e in enc] + [(d, _DEC_KINDS) for d in decs]:
+            if len(seq) != len(kinds) or any(not isinstance(c.cell, k) for c, k in zip(seq, kinds)):
+                raise ValueError('Not valid model: the B200 path implements the dist_codec/sep_codec architecture')
+            for c in seq:
+                if isinstance(c.cell, ConvLSTMCell):
+                    c.cell._check_supported()
+                elif isinstance(c.cell, ConvCell) and c.cell.activation_mode != 'tanh':
+                    raise ValueError('Not valid activation for the fused B200 path (tanh)')
+        if config.PARAM.get('normalization', 'none') != 'none':
+            raise ValueError('Not valid normalization for the B200 path (only none)')
+
+    def _run_engine(self, img, label, noise):
+        key = (config.PARAM['num_channel'], config.PARAM['code_size'], config.PARAM['num_node'],
+               config.PARAM.get('precision', 'parity'))
+        if self._engine_key != key:
+            self._check_architecture()
+            self._engine = CodecEngine(key[0], key[1], key[2], separate=self.separate, precision=key[3])
+            self._engine_key = key
+        sd = {k: v for k, v in self.named_parameters()}
+        return self._engine.forward(sd, img, label, config.PARAM['num_iter'], training=self.training,
+                                    noise=noise, loss_kind=config.PARAM['loss_fn'])
+
+    def forward(self, input, noise=None):
+        """input: {'img': [B,C,H,W] in [0,1], 'label': [B] node ids}; returns {'loss', 'img': list of T
+        cumulative reconstructions, 'code': list of T cumulative packed codes} like the reference
+        (dist_codec.py:36-65), plus 'code_pm1' ([T,B,code,H/8,W/8] raw +-1 symbols) and 'bits'
+        ([T,B,code*H*W/512] uint8, the real 1-bit/symbol stream)."""
+        if config.PARAM['loss_fn'] not in ('bce', 'mse', 'mae'):
+            raise ValueError('Not valid loss function')
+        img, label = input['img'], input['label']
+        params = [p for p in self.parameters()]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad:
+            loss, recon, codes, bits = _LoopFunction.apply(self, img, label, noise, *params)
+        else:
+            res = self._run_engine(img, label, noise)
+            loss = CodecEngine.loss_from_acc(res['loss_acc'], img.numel())
+            recon, codes, bits = res['recon'], res['codes'], res['bits']
+        T = recon.shape[0]
+        output = {'loss': loss, 'img': [recon[t] for t in range(T)], 'code': [], 'code_pm1': codes, 'bits': bits}
+        if config.PARAM.get('pack_mode', 'reference') == 'bits':
+            b = bits.cpu().numpy()                                  # one D2H per forward
+            output['code'] = [np.ascontiguousarray(b[:t + 1].transpose(1, 2, 0).reshape(-1, t + 1)) for t in range(T)]
+        else:
+            c = codes.detach().cpu().numpy().astype(np.int8)        # one D2H per forward (reference: one per iteration)
+            per_iter = [np.packbits(c[t]).reshape(-1, 1) for t in range(T)]
+            for t in range(T):
+                output['code'].append(per_iter[t] if t == 0 else np.concatenate((output['code'][t - 1], per_iter[t]), axis=1))
+        apply_fn(self, 'free_hidden')                               # dist_codec.py:64
+        return output

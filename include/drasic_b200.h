@@ -111,6 +111,18 @@ typedef struct {
 } drasic_tail_head_args;
 int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream);
 
+/*
+ * Stand-alone cells (called outside the fused loop; NCHW fp32 like the reference).
+ * drasic_conv1x1_fwd: ConvCell.forward with kernel_size 1 (modules/cell.py:69-72): y = act(w*x + b);
+ *   x [N,Cin,HW], w [Cout,Cin], b nullable [Cout], y [N,Cout,HW].
+ * drasic_quantize_fwd: Quantize.forward (functions/quantize.py:9-18); u nullable = eval mode.
+ */
+enum { DRASIC_ACT_NONE = 0, DRASIC_ACT_TANH = 1, DRASIC_ACT_RELU = 2, DRASIC_ACT_SIGMOID = 3,
+       DRASIC_ACT_HARDTANH = 4, DRASIC_ACT_ELU = 5, DRASIC_ACT_SELU = 6, DRASIC_ACT_CELU = 7 };
+int drasic_conv1x1_fwd(const float* x, const float* w, const float* b, float* y, int N, int Cin,
+                       int Cout, int HW, int act, void* stream);
+int drasic_quantize_fwd(const float* x, const float* u, float* y, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

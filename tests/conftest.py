@@ -18,3 +18,33 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+def build_model(name, data_name, num_node, num_iter, seed=0, device='cuda', precision='parity', code_size=8,
+                loss_fn='mae', pack_mode='reference'):
+    """the reference's own construction sequence (train_model.py:39-58) against the B200 packages"""
+    import torch
+    import config
+    config.init()
+    config.PARAM['device'] = device
+    config.PARAM['data_name'] = data_name
+    config.PARAM['control'] = {'normalization': 'none', 'activation': 'tanh', 'num_iter': str(num_iter),
+                               'code_size': str(code_size), 'num_node': str(num_node)}
+    config.PARAM['precision'] = precision
+    config.PARAM['loss_fn'] = loss_fn
+    config.PARAM['pack_mode'] = pack_mode
+    import utils
+    utils.process_control_name()
+    import models
+    torch.manual_seed(seed)
+    m = getattr(models, name)()
+    return m.to(device)
+
+
+def sd_digest(sd):
+    import hashlib
+    h = hashlib.sha256()
+    for k in sorted(sd.keys()):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()

@@ -1,0 +1,131 @@
+"""Host-side logic of the drop-in packages: batch plan, module tree / state_dict contract, error
+behaviour, layout helpers.  CPU only (no kernel launches)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_model, sd_digest
+from engine import binding as B
+from engine.cell import from_nhwc, to_planes
+from engine.codec import BatchPlan, PAD
+
+
+def test_batch_plan_sorts_pads_and_keeps_order():
+    label = np.array([2, 0, 2, 2, 0, 3, 2])
+    p = BatchPlan(label, 4, 'cpu')
+    assert p.B == 7 and p.B_pad == 3 * PAD                 # node 1 is empty: no slots
+    assert list(p.group_img_end_host) == [8, 8, 16, 24]
+    assert list(p.perm_host[:2]) == [1, 4] and list(p.perm_host[8:12]) == [0, 2, 3, 6] and p.perm_host[16] == 5
+    assert (p.perm_host[[2, 7, 12, 15, 17, 23]] == -1).all()
+    valid = p.perm_host[p.perm_host >= 0]
+    assert sorted(valid.tolist()) == list(range(7))
+    assert list(p.mtile_end(16).numpy()) == [1, 1, 2, 3]   # 4x4 layer: 8 images per 128-pixel tile
+    assert list(p.mtile_end(256).numpy()) == [16, 16, 32, 48]
+
+
+def test_batch_plan_rejects_bad_labels_like_the_reference():
+    with pytest.raises(IndexError):
+        BatchPlan(np.array([0, 4]), 4, 'cpu')
+
+
+def test_batch_plan_large_ragged():
+    rng = np.random.RandomState(2)
+    label = rng.randint(0, 8, size=1000)
+    p = BatchPlan(label, 8, 'cpu')
+    assert p.B_pad % PAD == 0 and p.B_pad >= 1000
+    for j in range(8):
+        lo = 0 if j == 0 else p.group_img_end_host[j - 1]
+        idx = p.perm_host[lo:p.group_img_end_host[j]]
+        idx = idx[idx >= 0]
+        assert (label[idx] == j).all() and (np.diff(idx) > 0).all()
+
+
+@pytest.mark.parametrize('name,data,M,seed,golden', [('dist_codec', 'MNIST', 1, 0, 'loop_mnist_m1.npz'),
+                                                     ('dist_codec', 'CIFAR10', 2, 3, 'loop_cifar_m2.npz'),
+                                                     ('sep_codec', 'CIFAR10', 2, 6, 'loop_sep_m2.npz')])
+def test_state_dict_contract_matches_reference(golden_dir, name, data, M, seed, golden):
+    g = np.load(os.path.join(golden_dir, golden))
+    m = build_model(name, data, M, 4, seed=seed, device='cpu')
+    sd = m.state_dict()
+    if 'keys' in g:
+        assert list(sd.keys()) == [str(k) for k in g['keys']]
+    assert sd_digest(sd) == str(g['digest'])               # same keys, shapes, dtypes and seeded values
+    assert all(v.dtype == torch.float32 for v in sd.values())
+    # load_state_dict round trip (test_model.py:46)
+    m2 = build_model(name, data, M, 4, seed=seed + 1, device='cpu')
+    m2.load_state_dict(sd)
+    assert sd_digest(m2.state_dict()) == str(g['digest'])
+
+
+def test_module_tree_and_reference_api_surface():
+    import config
+    import modules
+    m = build_model('dist_codec', 'CIFAR10', 3, 16, device='cpu')
+    assert set(config.PARAM['model'].keys()) == {'encoder', 'quantizer', 'decoder'}   # factory writes PARAM['model']
+    assert len(m.model['encoder']) == 3 and len(m.model['encoder'][0]) == 8 and len(m.model['decoder']) == 8
+    lstm = m.model['encoder'][1][2].cell
+    assert isinstance(lstm, modules.ConvLSTMCell) and lstm.hidden is None
+    lstm.free_hidden()
+    for attr in ('pack', 'unpack', 'loss_fn', 'forward'):
+        assert hasattr(m, attr)
+    code = torch.tensor([[1.0, -1.0] * 8])
+    packed = m.pack(code)
+    assert packed.dtype == np.uint8 and (packed == 0xFF).all()                        # degenerate, as the reference
+    n_par = sum(p.numel() for p in m.parameters())
+    assert n_par == 3 * 7079040 + 24773728
+
+
+def test_error_behaviour_mirrors_reference():
+    import config
+    import modules
+    config.init()
+    with pytest.raises(ValueError, match='Not valid'):
+        modules.Cell({'cell': 'NoSuchCell'})
+    with pytest.raises(ValueError, match='Not valid activation'):
+        modules.Cell({'cell': 'Activation', 'mode': 'bogus'})
+    with pytest.raises(ValueError, match='Not valid normalization'):
+        modules.Cell({'cell': 'Normalization', 'mode': 'bogus', 'input_size': 4})
+    with pytest.raises(ValueError, match='Not valid model mode'):
+        modules.Cell({'cell': 'PixelShuffleCell', 'mode': 'sideways', 'scale_factor': 2})
+    from models.utils import make_model
+    with pytest.raises(ValueError, match='Not valid model format'):
+        make_model(3)
+    m = build_model('dist_codec', 'MNIST', 1, 2, device='cpu', loss_fn='huber')
+    with pytest.raises(ValueError, match='Not valid loss function'):
+        m({'img': torch.rand(1, 1, 32, 32), 'label': torch.zeros(1, dtype=torch.long)})
+
+
+def test_no_cpu_fallback():
+    m = build_model('dist_codec', 'MNIST', 1, 2, device='cpu')
+    with pytest.raises(B.DrasicError, match='no CPU path'):
+        m({'img': torch.rand(2, 1, 32, 32), 'label': torch.zeros(2, dtype=torch.long)})
+    import modules
+    cell = modules.Cell({'cell': 'ConvLSTMCell', 'input_size': 64, 'output_size': 64, 'kernel_size': 3, 'stride': 1,
+                         'padding': 1, 'bias': False, 'num_layers': 1, 'activation': 'tanh'})
+    with pytest.raises(B.DrasicError, match='no CPU path'):
+        cell(torch.rand(1, 64, 8, 8))
+    q = modules.Cell({'cell': 'QuantizationCell'})
+    with pytest.raises(B.DrasicError, match='no CPU path'):
+        q(torch.rand(4))
+
+
+def test_shuffle_functions_match_golden(golden_dir):
+    import functions
+    g = np.load(os.path.join(golden_dir, 'cells.npz'))
+    x = torch.from_numpy(g['shuffle_in'])
+    assert np.array_equal(functions.pixel_unshuffle(x, 2).numpy(), g['unshuffle_out'])
+    assert np.array_equal(functions.pixel_shuffle(x, 2).numpy(), g['shuffle_out'])
+
+
+@pytest.mark.parametrize('order', [B.ORDER_IDENT, B.ORDER_QUAD])
+def test_plane_layout_round_trip(order):
+    x = torch.rand(3, 16, 4, 4) * 2 - 1
+    hi, lo = to_planes(x, 1, pad_to=8, order=order)
+    assert hi.shape == (8, 4, 4, 16) and hi.dtype == torch.float16
+    rec = (hi.float() + lo.float()) / 256.0
+    back = from_nhwc(rec, 3, order=order)
+    assert (back - x).abs().max() < 2e-7          # hi + lo carries ~22 significand bits
+    if order == B.ORDER_QUAD:                     # physical p = q*(C/4)+c  <->  logical c*4+q
+        assert torch.allclose(rec[0, 1, 2, 1 * 4 + 3], x[0, 3 * 4 + 1, 1, 2], atol=2e-7)
