@@ -1,0 +1,291 @@
+"""Benchmark of DRASIC's recurrent residual coding loop on B200 (see BASELINE.json / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--mode eval|train]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (T=16 iterations of encode -> binarize -> decode over the
+residual) over one batch of synthetic CIFAR-shaped images from 8 sources.  Rank 0 prints ONE JSON line.
+`--impl reference` times the CPU oracle (the reference's algorithm on torch CPU ops, all host threads)
+on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'drasic-distributed-recurrent-autoencoder-for-scalable-image-compression_b200')
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+T_ITER = 16
+M_NODES = 8
+CHANNELS = 3
+FLOP_PER_IMG_FWD = 57.083e9        # SURVEY 8d / BASELINE.md 3: dense forward count at T=16, C=3
+METRIC = 'images/s train & encode+decode at T=16 (CIFAR-10 32x32), 1/2/4/8 B200; PSNR parity'
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1401.4), d.get('bf16_tflops', 1679.4), d.get('hbm_gbs', 6544.3), 'measured'
+    return 1400.0, 1590.0, 6650.0, 'fallback'
+
+
+class ClockSampler(object):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        # median over the upper half of the samples = clocks under load (the first samples are idle)
+        load = sm[len(sm) // 2:] if sm else []
+        return {'sm_mhz': load[len(load) // 2] if load else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def synth_batch(batch, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(batch, CHANNELS, 32, 32, generator=g)
+    label = torch.randint(0, M_NODES, (batch,), generator=g)        # "split by random subsets"
+    return img, label
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """the reference's algorithm (oracle port: torch CPU fp32 ops in the reference's order) on host cores"""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from oracle import drasic_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.init_state_dict(CHANNELS, 8, M_NODES, seed=0)
+    # size the per-step sample so the whole run stays within a few minutes
+    img, label = synth_batch(8, 1)
+    with torch.no_grad():
+        O.codec_forward(sd, img, label, 2, M_NODES)                 # warm the thread pool / oneDNN primitives
+        t0 = time.perf_counter()
+        O.codec_forward(sd, img, label, T_ITER, M_NODES)
+        t8 = time.perf_counter() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    sample = int(max(8, min(64, 8 * budget / max(t8, 1e-3))) // 8 * 8)
+    img, label = synth_batch(sample, 2)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.codec_forward(sd, img, label, T_ITER, M_NODES)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.codec_forward(sd, img, label, T_ITER, M_NODES)
+        dt = (time.perf_counter() - t0) / args.steps
+    v = sample / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'cifar10_32x32_m8_random_subsets_T16_eval_encode_decode', 'sample_batch': sample,
+                   'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                         'sample': 'oracle/drasic_oracle.py codec_forward, eval, B={} M=8 T=16 per step'.format(sample)},
+        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from oracle import drasic_oracle as O          # used only by the cpu_baseline leg at the end
+    from engine.codec import CodecEngine
+    import config
+    config.init()
+    config.PARAM.update(device='cuda', data_name='CIFAR10', precision=args.precision, pack_mode='reference')
+    config.PARAM['control'] = {'normalization': 'none', 'activation': 'tanh', 'num_iter': str(T_ITER),
+                               'code_size': '8', 'num_node': str(M_NODES)}
+    import utils
+    utils.process_control_name()
+    import models
+    torch.manual_seed(0)
+    model = models.dist_codec().to(dev)
+    model.train(False)
+    sd = {k: v for k, v in model.named_parameters()}
+    B = args.batch
+    # each rank codes its own shard of the global batch (samples are independent: no data-path collective)
+    img_h, label_h = synth_batch(B, 1000 + rank)
+    img, label = img_h.to(dev), label_h.to(dev)
+    label_np = label_h.numpy()
+    eng = CodecEngine(CHANNELS, 8, M_NODES, precision=args.precision)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            eng.forward(sd, img, label, T_ITER, label_host=label_np)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            eng.forward(sd, img, label, T_ITER, label_host=label_np)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = eng.launches
+        clocks = sampler.stop() if sampler else None
+
+        # ---- per-kernel timing on the launching stream (separate pass, events around every launch)
+        eng.profile = []
+        for _ in range(2):
+            eng.forward(sd, img, label, T_ITER, label_host=label_np)
+        torch.cuda.synchronize()
+        prof = eng.profile_summary()
+        eng.profile = None
+
+        # ---- end to end through the public API with host buffers
+        pin_img, pin_label = img_h.pin_memory(), label_h.pin_memory()
+        def e2e_step():
+            out = model({'img': pin_img.to(dev, non_blocking=True), 'label': pin_label.to(dev, non_blocking=True)})
+            return out['loss'].item(), out['code'][-1].nbytes       # D2H: loss scalar + all codes (inside forward)
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+
+    t_ms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t_ms.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sust, burst, hbm, how = measured_peaks()
+    gate = [(k, v) for k, v in prof.items() if k.startswith('gates_')]
+    g_n = sum(v[0] for _, v in gate)
+    g_ms = sum(v[1] for _, v in gate)
+    g_fl = sum(v[2] for _, v in gate)
+    all_ms = sum(v[1] for v in prof.values())
+    achieved = g_fl / (g_ms * 1e-3) / 1e12
+    mma_per_mac = 3 if args.precision == 'parity' else 1
+    line = {
+        'metric': METRIC, 'value': world * B / ms * 1e3, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'f16x2-split (fp32-grade, fp32 accumulate)' if args.precision == 'parity' else 'f16 (fp32 accumulate)',
+        'data': 'synthetic',
+        'config': {'workload': 'cifar10_32x32_m8_random_subsets_T16_eval_encode_decode', 'batch_per_gpu': B,
+                   'global_batch': world * B, 'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8,
+                   'precision': args.precision, 'parallelism': 'batch-sharded replicas x{}'.format(world),
+                   'l2': 'per-step working set (activations+state, ~1 MB/image) exceeds the 126 MB L2'},
+        'e2e': {'value': world * B / e2e_ms * 1e3, 'unit': 'images/s',
+                'h2d_bytes_per_step': B * CHANNELS * 32 * 32 * 4 + B * 8,
+                'd2h_bytes_per_step': T_ITER * B * 128 * 4 + 4,
+                'api': 'models.dist_codec() Model.forward on pinned host img/label; loss.item() and packed codes read back'},
+        'gpu_launches': launches * args.steps,
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'convlstm_gates_kernel (6 layers x 16 iterations)',
+                     'achieved': achieved, 'peak': sust, 'unit': 'TFLOP/s', 'frac': achieved / sust,
+                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained ({}); burst {}'.format(how, burst),
+                     'traffic': None, 'launches': g_n, 'avg_launch_ms': g_ms / max(g_n, 1),
+                     'share_of_step': g_ms / all_ms, 'tensor_mma_per_algorithmic_mac': mma_per_mac,
+                     'tensor_issue_tflops': achieved * mma_per_mac, 'tensor_issue_frac': achieved * mma_per_mac / sust},
+        'kernels_ms_per_step': {k: v[1] / 2 for k, v in sorted(prof.items())},
+        'algorithmic_tflops': world * B / ms * 1e3 * FLOP_PER_IMG_FWD / 1e12,
+    }
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sdc = {k: v.detach().cpu() for k, v in sd.items()}
+        ci, cl = synth_batch(256, 7)
+        with torch.no_grad():
+            O.codec_forward(sdc, ci[:8], cl[:8], 2, M_NODES)
+            t0 = time.perf_counter()
+            O.codec_forward(sdc, ci, cl, T_ITER, M_NODES)
+            dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': 256 / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                'sample': 'oracle codec_forward eval, B=256 M=8 T=16, one pass ({:.1f} s)'.format(dt)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='images per GPU per step')
+    ap.add_argument('--precision', default='parity', choices=['parity', 'fast'])
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

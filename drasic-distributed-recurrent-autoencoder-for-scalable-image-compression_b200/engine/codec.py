@@ -84,6 +84,7 @@ class CodecEngine(object):
         self._wcache = {}
         self._sms = None
         self.launches = 0   # kernels launched by the last forward() (bench.py reports it)
+        self.profile = None  # set to [] to collect (label, flops, start_event, end_event) per launch
 
     # ------------------------------------------------------------------ helpers
     def sms(self):
@@ -93,6 +94,24 @@ class CodecEngine(object):
                 raise B.DrasicError('no CUDA device: ' + B.lib().drasic_last_error().decode())
             self._sms = n
         return self._sms
+
+    def _timed(self, label, flops, fn):
+        if self.profile is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self.profile.append((label, flops, e0, e1))
+        return r
+
+    def profile_summary(self):
+        """{label: (launches, total ms, total algorithmic flops)} after a synchronize"""
+        out = {}
+        for label, flops, e0, e1 in self.profile or []:
+            n, ms, fl = out.get(label, (0, 0.0, 0.0))
+            out[label] = (n + 1, ms + e0.elapsed_time(e1), fl + flops)
+        return out
 
     def _block_n(self, n_mtiles, co):
         for bn in (256, 128, 64):
@@ -250,7 +269,7 @@ class CodecEngine(object):
             a.loss_kind = B.LOSS_KINDS[loss_kind]
             a.n_enc_groups, a.n_dec_groups = self.M, self.Md
             a.precise, a.split = self.precise, self.split
-            B.check(L.drasic_tail_head_fwd(a, stream), 'tail_head_fwd')
+            self._timed('tail_head', 0.0, lambda: B.check(L.drasic_tail_head_fwd(a, stream), 'tail_head_fwd'))
             self.launches += 1
 
         def gate(ly, x_planes, t):
@@ -269,7 +288,10 @@ class CodecEngine(object):
             a.has_state = 1 if t > 0 else 0
             a.next_mode, a.next_f32 = ly.next_mode, ly.next_f32
             a.split, a.precise, a.block_n = self.split, self.precise, ly.block_n
-            B.check(L.drasic_convlstm_fwd(a, stream), 'convlstm_fwd')
+            # algorithmic FLOPs of this launch: real images only, hidden conv skipped on zero state
+            k = 9 * (ly.cin + (ly.co if t > 0 else 0))
+            flops = 2.0 * Bn * ly.h * ly.w * 4 * ly.co * k
+            self._timed('gates_' + ly.name, flops, lambda: B.check(L.drasic_convlstm_fwd(a, stream), 'convlstm_fwd'))
             self.launches += 1
             return Lb['next']
 
@@ -290,7 +312,7 @@ class CodecEngine(object):
             a.B_pad, a.HW, a.Ch, a.code = Bp, hc * wc, 128, code
             a.n_enc_groups, a.n_dec_groups = self.M, self.Md
             a.precise, a.split = self.precise, self.split
-            B.check(L.drasic_bottleneck_fwd(a, stream), 'bottleneck_fwd')
+            self._timed('bottleneck', 0.0, lambda a=a: B.check(L.drasic_bottleneck_fwd(a, stream), 'bottleneck_fwd'))
             self.launches += 1
             x = A['d1_in']
             for ly in layers[3:]:
