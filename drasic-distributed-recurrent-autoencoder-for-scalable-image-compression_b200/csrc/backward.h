@@ -1,0 +1,103 @@
+// Parameter blocks of the backward-through-time kernels (backward.cu, wgrad.cu).  Together they
+// replace what autograd runs for `output['loss'].backward()` (reference train_model.py:115) over the
+// loop of models/dist_codec.py:36-65.
+#pragma once
+#include "kernels.h"
+
+namespace drasic {
+
+// LSTM cell pointwise backward (modules/cell.py:133-139 differentiated), one launch per (layer, t)
+struct LstmBwdParams {
+  const __half* gates;     // [P, 4, Co] activated gates saved by the forward
+  const float* c_t;        // [P, Co]
+  const float* c_prev;     // nullable (t == 0)
+  const float* dh_above;   // [P, Co] gradient from the consumer of h_t
+  const float* dh_rec;     // nullable (t == T-1): gradient from the hidden conv of step t+1
+  float* dc;               // [P, Co] in/out carry: dL/dc_t from step t+1 in, dL/dc_{t-1} out
+  int has_dc;              // 0 at t == T-1 (carry is zero)
+  float* dgates;           // [P, 4, Co] fp32 pre-activation gate gradients
+  unsigned int* amax_bits; // max |dgates| as float bits (atomicMax)
+  size_t n_pix;            // P = B_pad*H*W
+  int Co;
+};
+
+// fp32 -> fp16 {hi, lo} planes with an exact power-of-two scale derived from amax
+struct ConvertParams {
+  const float* src;
+  __half* hi;
+  __half* lo;               // nullable
+  const unsigned int* amax_bits;
+  float* inv_scale_out;     // device scalar: 1/scale
+  size_t n;
+};
+
+struct WgradParams {
+  CUtensorMap tm_g[2];      // dG planes [B,H,W,4Co] fp16 {hi, lo}, box = 64 ch x 64 pixels
+  CUtensorMap tm_x[2];      // layer input planes [B,H,W,Cin], same pixel box (shifted by the tap)
+  CUtensorMap tm_h[2];      // h_{t-1} planes [B,H,W,Co]
+  float* gw;                // [groups][4Co][9(Cin+Co)] fp32 packed-order weight gradient (atomic accumulate)
+  const float* g_inv_scale; // device scalar: 1/scale of the dG planes
+  const int* group_kb_end;  // device [n_groups]: exclusive end k-block (64 pixels) per node; null = 1 group
+  int H, W, Cin, Co;
+  int kbw, kbh, kbn;        // pixel box of one K block: kbw*kbh*kbn == 64
+  int n_kb;                 // total K blocks = B_pad*H*W/64
+  int has_h;                // 0 at t == 0
+  int n_groups, m_tiles, n_tiles_x, n_tiles_h, k_splits;
+};
+
+struct BottleneckBwdParams {
+  const float* dd0;        // [B_pad, HW, Ch] gradient w.r.t. the decoder-head output (from D1 dgrad)
+  const float* h_e3;       // [B_pad, HW, Ch] saved encoder ConvLSTM output of this iteration
+  const float* z;          // [B, code, HW] saved pre-quantizer activations (original order)
+  const float* codes;      // [B, code, HW] emitted symbols (original order)
+  const float* w_e4;       // [n_enc_groups][code, Ch]
+  const float* w_d0;       // [n_dec_groups][Ch, code]
+  const int* perm;
+  const int* group_img_end;
+  float* dh_e3;            // [B_pad, HW, Ch] gradient w.r.t. the encoder ConvLSTM output
+  float* dw_e4;            // [n_enc_groups][code, Ch] accumulated
+  float* dw_d0;            // [n_dec_groups][Ch, code] accumulated
+  int B_pad, HW, Ch, code, n_enc_groups, n_dec_groups;
+};
+
+struct TailBwdParams {
+  const float* d3_next;    // [B_pad,H,W,32] saved shuffled decoder ConvLSTM output of iteration t
+  const float* w_d4;       // [n_dec_groups][C,32]
+  const float* img;        // [B,C,H,W]
+  const float* recon_t;    // [B,C,H,W] reconstruction after iteration t
+  float* gacc;             // [B,C,H,W] running dL/d(recon) accumulator (see backward.cu)
+  float* dh_d3;            // [B_pad,H/2,W/2,128] gradient w.r.t. D3's h (own QUAD layout)
+  float* dw_d4;            // [n_dec_groups][C,32] accumulated
+  const int* perm;
+  const int* group_img_end;
+  float loss_scale;        // 1 / (T * B*C*H*W)
+  int B_pad, C, H, W, first, loss_kind, n_dec_groups, has_acc;
+};
+
+struct HeadBwdParams {
+  const float* du1;        // [B_pad,H/2,W/2,128] gradient w.r.t. the first encoder ConvLSTM input
+  const float* w_e0;       // [n_enc_groups][32,C]
+  const float* b_e0;       // nullable
+  const float* img;
+  const float* recon_prev; // nullable (t == 0: x = img*2-1)
+  float* gacc;             // [B,C,H,W]: -= dL/dx_t when propagate != 0
+  float* dw_e0;            // [n_enc_groups][32,C]
+  float* db_e0;            // nullable [n_enc_groups][32]
+  const int* perm;
+  const int* group_img_end;
+  int B_pad, C, H, W, first, propagate, n_enc_groups;
+};
+
+int launch_lstm_bwd(const LstmBwdParams& p, cudaStream_t stream);
+int launch_convert_scale(const ConvertParams& p, cudaStream_t stream);
+int launch_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
+                              int out_order, __half* out_hi, __half* out_lo, float* inv_scale_out,
+                              unsigned int* scratch_amax, cudaStream_t stream);
+int launch_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,
+                        float* dw_h, cudaStream_t stream);
+int launch_wgrad(const WgradParams& p, bool split, int num_sms, cudaStream_t stream);
+int launch_bottleneck_bwd(const BottleneckBwdParams& p, cudaStream_t stream);
+int launch_tail_bwd(const TailBwdParams& p, cudaStream_t stream);
+int launch_head_bwd(const HeadBwdParams& p, cudaStream_t stream);
+
+}  // namespace drasic

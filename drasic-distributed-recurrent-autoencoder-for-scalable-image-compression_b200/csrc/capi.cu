@@ -7,6 +7,7 @@
 #include "../../include/drasic_b200.h"
 #include "kernels.h"
 #include "pointwise.h"
+#include "backward.h"
 
 namespace {
 
@@ -162,6 +163,9 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * 4 * Co, K, a->block_n))) return rc;
   if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * 4 * Co, K, a->block_n))) return rc;
   p.c_state = a->c_state;
+  p.c_prev = a->c_prev;
+  p.gates_out = static_cast<__half*>(a->gates_out);
+  p.w_group_rows = 4 * Co;
   p.h_out[0] = static_cast<__half*>(a->h_out_hi);
   p.h_out[1] = static_cast<__half*>(a->h_out_lo);
   p.next[0] = a->next_hi;
@@ -230,6 +234,165 @@ int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream) {
   p.precise = a->precise; p.split = a->split;
   p.group_img_end = a->group_img_end;
   return cuda_fail(drasic::launch_tail_head(p, static_cast<cudaStream_t>(stream)), "tail_head_fwd launch");
+}
+
+// pixel box helper shared by the conv GEMMs: bw*bh*bn == npix
+static int pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
+  *bw = W < npix ? W : npix;
+  if (*bw <= 0 || npix % *bw || W % *bw) return -1;
+  *bh = H < npix / *bw ? H : npix / *bw;
+  if (*bh <= 0 || (npix / *bw) % *bh || H % *bh) return -1;
+  *bn = npix / (*bw * *bh);
+  if (*bn > 1 && (*bw != W || *bh != H)) return -1;
+  return 0;
+}
+
+int drasic_lstm_bwd_pointwise(const void* gates, const float* c_t, const float* c_prev,
+                              const float* dh_above, const float* dh_rec, float* dc, int has_dc,
+                              float* dgates, void* amax_bits, size_t n_pix, int Co, void* stream) {
+  if (!gates || !c_t || !dh_above || !dc || !dgates || !amax_bits || Co % 8 || n_pix == 0)
+    return fail(DRASIC_ERR_INVALID, "lstm_bwd_pointwise: bad argument");
+  drasic::LstmBwdParams p;
+  p.gates = static_cast<const __half*>(gates); p.c_t = c_t; p.c_prev = c_prev; p.dh_above = dh_above;
+  p.dh_rec = dh_rec; p.dc = dc; p.has_dc = has_dc; p.dgates = dgates;
+  p.amax_bits = static_cast<unsigned int*>(amax_bits); p.n_pix = n_pix; p.Co = Co;
+  return cuda_fail(drasic::launch_lstm_bwd(p, static_cast<cudaStream_t>(stream)), "lstm_bwd_pointwise launch");
+}
+
+int drasic_convert_scale(const float* src, void* hi, void* lo, const void* amax_bits,
+                         float* inv_scale_out, size_t n, void* stream) {
+  if (!src || !hi || !amax_bits || !inv_scale_out || n == 0 || n % 8)
+    return fail(DRASIC_ERR_INVALID, "convert_scale: bad argument");
+  drasic::ConvertParams p;
+  p.src = src; p.hi = static_cast<__half*>(hi); p.lo = static_cast<__half*>(lo);
+  p.amax_bits = static_cast<const unsigned int*>(amax_bits); p.inv_scale_out = inv_scale_out; p.n = n;
+  return cuda_fail(drasic::launch_convert_scale(p, static_cast<cudaStream_t>(stream)), "convert_scale launch");
+}
+
+int drasic_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
+                              int out_order, void* out_hi, void* out_lo, float* inv_scale_out,
+                              void* scratch4, void* stream) {
+  if (!w_in || !w_h || !out_hi || !out_lo || !inv_scale_out || !scratch4)
+    return fail(DRASIC_ERR_INVALID, "pack_dgrad_weights: null pointer");
+  if (Cin % 64 || Co % 64) return fail(DRASIC_ERR_INVALID, "pack_dgrad_weights: Cin=%d Co=%d", Cin, Co);
+  return cuda_fail(drasic::launch_pack_dgrad_weights(w_in, w_h, Cin, Co, in_order, out_order,
+                                                     static_cast<__half*>(out_hi), static_cast<__half*>(out_lo),
+                                                     inv_scale_out, static_cast<unsigned int*>(scratch4),
+                                                     static_cast<cudaStream_t>(stream)),
+                   "pack_dgrad_weights launch");
+}
+
+int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
+  if (!a) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: null args");
+  const int H = a->H, W = a->W, Cin = a->Cin, Co = a->Co, B = a->B_pad;
+  if (Cin % 64 || Co % 64 || Cin <= 0 || Co <= 0) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: channels");
+  int bw, bh, bn;
+  if (pixel_box(H, W, 128, &bw, &bh, &bn)) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: H=%d W=%d unsupported", H, W);
+  if (B <= 0 || B % bn) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: B_pad=%d", B);
+  if (!a->dg_hi || !a->w_hi || !a->w_inv_scale || !a->dg_inv_scale || !a->dx_out || (a->split && (!a->dg_lo || !a->w_lo)))
+    return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: null pointer");
+  if (a->n_groups < 1 || a->n_groups > DRASIC_MAX_GROUPS || (a->n_groups > 1 && !a->group_mtile_end))
+    return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: groups");
+  if (a->dx_mode < 0 || a->dx_mode > 2 || (a->dx_mode == DRASIC_DX_INV_DOWN && Cin % 64) || (a->dx_mode == DRASIC_DX_INV_UP && ((H | W) & 1)))
+    return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: dx_mode");
+  drasic::GateParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  const int Cg = 4 * Co, Nout = Cin + Co, K = 9 * Cg;
+  if ((rc = make_act_map(&p.tm_x[0], a->dg_hi, B, H, W, Cg, bw, bh, bn))) return rc;
+  if (a->split && (rc = make_act_map(&p.tm_x[1], a->dg_lo, B, H, W, Cg, bw, bh, bn))) return rc;
+  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * Nout, K, 256))) return rc;
+  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * Nout, K, 256))) return rc;
+  p.w_inv_scale = a->w_inv_scale; p.a_inv_scale = a->dg_inv_scale;
+  p.H = H; p.W = W; p.Cin = Cg; p.Co = Co;
+  p.bw = bw; p.bh = bh; p.bn = bn;
+  p.n_mtiles = static_cast<int>(static_cast<long long>(B) * H * W / 128);
+  p.n_ntiles = (Nout + 255) / 256;
+  p.n_groups = a->n_groups; p.group_mtile_end = a->group_mtile_end;
+  p.w_group_rows = Nout; p.n_out = Nout; p.n_x = Cin; p.dx_mode = a->dx_mode;
+  p.dx_out = a->dx_out; p.dhrec_out = a->dhrec_out;
+  const int sms = num_sms();
+  if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
+  return cuda_fail(drasic::launch_convlstm_dgrad(p, a->split != 0, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_data launch");
+}
+
+int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream) {
+  if (!a) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: null args");
+  const int H = a->H, W = a->W, Cin = a->Cin, Co = a->Co, B = a->B_pad;
+  if (Cin % 64 || Co % 128 || Cin <= 0 || Co <= 0) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: channels");
+  int kbw, kbh, kbn;
+  if (pixel_box(H, W, 64, &kbw, &kbh, &kbn)) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: H=%d W=%d unsupported", H, W);
+  if (B <= 0 || B % kbn) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: B_pad=%d", B);
+  if (!a->dg_hi || !a->x_hi || !a->gw || !a->dg_inv_scale || (a->split && (!a->dg_lo || !a->x_lo)))
+    return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: null pointer");
+  if (a->has_h && (!a->h_hi || (a->split && !a->h_lo))) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: h planes");
+  if (a->n_groups < 1 || a->n_groups > DRASIC_MAX_GROUPS || (a->n_groups > 1 && !a->group_kb_end) || a->k_splits < 1)
+    return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: groups / k_splits");
+  drasic::WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_act_map(&p.tm_g[0], a->dg_hi, B, H, W, 4 * Co, kbw, kbh, kbn))) return rc;
+  if (a->split && (rc = make_act_map(&p.tm_g[1], a->dg_lo, B, H, W, 4 * Co, kbw, kbh, kbn))) return rc;
+  if ((rc = make_act_map(&p.tm_x[0], a->x_hi, B, H, W, Cin, kbw, kbh, kbn))) return rc;
+  if (a->split && (rc = make_act_map(&p.tm_x[1], a->x_lo, B, H, W, Cin, kbw, kbh, kbn))) return rc;
+  if (a->has_h) {
+    if ((rc = make_act_map(&p.tm_h[0], a->h_hi, B, H, W, Co, kbw, kbh, kbn))) return rc;
+    if (a->split && (rc = make_act_map(&p.tm_h[1], a->h_lo, B, H, W, Co, kbw, kbh, kbn))) return rc;
+  }
+  p.gw = a->gw; p.g_inv_scale = a->dg_inv_scale; p.group_kb_end = a->n_groups > 1 ? a->group_kb_end : nullptr;
+  p.H = H; p.W = W; p.Cin = Cin; p.Co = Co; p.kbw = kbw; p.kbh = kbh; p.kbn = kbn;
+  p.n_kb = static_cast<int>(static_cast<long long>(B) * H * W / 64);
+  p.has_h = a->has_h ? 1 : 0; p.n_groups = a->n_groups; p.m_tiles = 4 * Co / 128;
+  p.n_tiles_x = (9 * (Cin / 64) + 3) / 4; p.n_tiles_h = (9 * (Co / 64) + 3) / 4; p.k_splits = a->k_splits;
+  const int sms = num_sms();
+  if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
+  return cuda_fail(drasic::launch_wgrad(p, a->split != 0, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_weight launch");
+}
+
+int drasic_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,
+                        float* dw_h, void* stream) {
+  if (!gw || !dw_in || !dw_h || Cin <= 0 || Co <= 0) return fail(DRASIC_ERR_INVALID, "unpack_wgrad: bad argument");
+  return cuda_fail(drasic::launch_unpack_wgrad(gw, Cin, Co, in_order, out_order, dw_in, dw_h, static_cast<cudaStream_t>(stream)), "unpack_wgrad launch");
+}
+
+int drasic_bottleneck_bwd(const drasic_bottleneck_bwd_args* a, void* stream) {
+  if (!a || !a->dd0 || !a->h_e3 || !a->z || !a->codes || !a->w_e4 || !a->w_d0 || !a->perm || !a->dh_e3 || !a->dw_e4 || !a->dw_d0)
+    return fail(DRASIC_ERR_INVALID, "bottleneck_bwd: null pointer");
+  if (a->B_pad <= 0 || a->HW <= 0 || a->Ch <= 0 || a->code <= 0) return fail(DRASIC_ERR_INVALID, "bottleneck_bwd: shape");
+  if ((a->n_enc_groups > 1 || a->n_dec_groups > 1) && !a->group_img_end) return fail(DRASIC_ERR_INVALID, "bottleneck_bwd: group_img_end");
+  drasic::BottleneckBwdParams p;
+  p.dd0 = a->dd0; p.h_e3 = a->h_e3; p.z = a->z; p.codes = a->codes; p.w_e4 = a->w_e4; p.w_d0 = a->w_d0;
+  p.perm = a->perm; p.group_img_end = a->group_img_end; p.dh_e3 = a->dh_e3; p.dw_e4 = a->dw_e4; p.dw_d0 = a->dw_d0;
+  p.B_pad = a->B_pad; p.HW = a->HW; p.Ch = a->Ch; p.code = a->code;
+  p.n_enc_groups = a->n_enc_groups < 1 ? 1 : a->n_enc_groups; p.n_dec_groups = a->n_dec_groups < 1 ? 1 : a->n_dec_groups;
+  return cuda_fail(drasic::launch_bottleneck_bwd(p, static_cast<cudaStream_t>(stream)), "bottleneck_bwd launch");
+}
+
+int drasic_tail_bwd(const drasic_tail_bwd_args* a, void* stream) {
+  if (!a || !a->d3_next || !a->w_d4 || !a->img || !a->recon_t || !a->gacc || !a->dh_d3 || !a->dw_d4 || !a->perm)
+    return fail(DRASIC_ERR_INVALID, "tail_bwd: null pointer");
+  if (a->C < 1 || a->C > 4 || (a->H * a->W) % 256 || ((a->H | a->W) & 1) || a->loss_kind < 0 || a->loss_kind > 2)
+    return fail(DRASIC_ERR_INVALID, "tail_bwd: shape / loss");
+  if (a->n_dec_groups > 1 && !a->group_img_end) return fail(DRASIC_ERR_INVALID, "tail_bwd: group_img_end");
+  drasic::TailBwdParams p;
+  p.d3_next = a->d3_next; p.w_d4 = a->w_d4; p.img = a->img; p.recon_t = a->recon_t; p.gacc = a->gacc;
+  p.dh_d3 = a->dh_d3; p.dw_d4 = a->dw_d4; p.perm = a->perm; p.group_img_end = a->group_img_end;
+  p.loss_scale = a->loss_scale; p.B_pad = a->B_pad; p.C = a->C; p.H = a->H; p.W = a->W; p.first = a->first;
+  p.loss_kind = a->loss_kind; p.n_dec_groups = a->n_dec_groups < 1 ? 1 : a->n_dec_groups; p.has_acc = a->has_acc;
+  return cuda_fail(drasic::launch_tail_bwd(p, static_cast<cudaStream_t>(stream)), "tail_bwd launch");
+}
+
+int drasic_head_bwd(const drasic_head_bwd_args* a, void* stream) {
+  if (!a || !a->du1 || !a->w_e0 || !a->img || !a->gacc || !a->dw_e0 || !a->perm) return fail(DRASIC_ERR_INVALID, "head_bwd: null pointer");
+  if (!a->first && !a->recon_prev) return fail(DRASIC_ERR_INVALID, "head_bwd: recon_prev");
+  if (a->C < 1 || a->C > 4 || (a->H * a->W) % 256 || ((a->H | a->W) & 1)) return fail(DRASIC_ERR_INVALID, "head_bwd: shape");
+  if (a->n_enc_groups > 1 && !a->group_img_end) return fail(DRASIC_ERR_INVALID, "head_bwd: group_img_end");
+  drasic::HeadBwdParams p;
+  p.du1 = a->du1; p.w_e0 = a->w_e0; p.b_e0 = a->b_e0; p.img = a->img; p.recon_prev = a->recon_prev; p.gacc = a->gacc;
+  p.dw_e0 = a->dw_e0; p.db_e0 = a->db_e0; p.perm = a->perm; p.group_img_end = a->group_img_end;
+  p.B_pad = a->B_pad; p.C = a->C; p.H = a->H; p.W = a->W; p.first = a->first; p.propagate = a->propagate;
+  p.n_enc_groups = a->n_enc_groups < 1 ? 1 : a->n_enc_groups;
+  return cuda_fail(drasic::launch_head_bwd(p, static_cast<cudaStream_t>(stream)), "head_bwd launch");
 }
 
 int drasic_conv1x1_fwd(const float* x, const float* w, const float* b, float* y, int N, int Cin,

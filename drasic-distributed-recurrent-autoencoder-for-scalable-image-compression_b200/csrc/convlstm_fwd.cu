@@ -1,20 +1,22 @@
-// ConvLSTM gate kernel for sm_100a: implicit-GEMM 3x3 convolution of [x ; h_prev] on tcgen05
-// tensor cores (TMA-fed, TMEM accumulators) with the LSTM gate nonlinearities, the cell / hidden
-// update and the pixel (un)shuffle of the following PixelShuffleCell fused into the epilogue.
+// Implicit-GEMM 3x3 convolution kernel for sm_100a (tcgen05 tensor cores, TMA-fed, TMEM accumulators)
+// with two fused epilogues:
 //
-// Replaces, per cell call, the reference sequence modules/cell.py:117 (input conv), :132 (hidden
-// conv + add), :133-137 (chunk, sigmoid/tanh), :138-139 (c = f*c + i*g ; h = o*tanh(c)) and the
-// PixelShuffleCell that follows it in models/dist_codec.py:70-104 (functions/shuffle.py:4-25).
+//  EPI_GATES  ConvLSTM cell step: gates = W_in*x + W_h*h_prev, gate nonlinearities, cell / hidden
+//             update and the pixel (un)shuffle of the following PixelShuffleCell.  Replaces, per cell
+//             call, reference modules/cell.py:117 (input conv), :132 (hidden conv + add), :133-137
+//             (chunk, sigmoid/tanh), :138-139 (c = f*c + i*g ; h = o*tanh(c)) and the PixelShuffleCell
+//             after it in models/dist_codec.py:70-104 (functions/shuffle.py:4-25).
+//  EPI_DGRAD  backward-data of the same cell (what autograd runs for train_model.py:115):
+//             [dX | dH_prev] = conv3x3^T(dGates) with W_in and W_h concatenated along N, the input
+//             gradient routed through the inverse (un)shuffle to the producing layer.
 //
-// GEMM view:  D[pixels, 4*Co] = A[pixels, 9*(Cin+Co)] * Wp^T
+// GEMM view:  D[pixels, N] = A[pixels, 9*C] * Wp^T
 //   A is never materialised: K block (src, tap, 64-channel chunk) of an M tile of 128 pixels is one
-//   TMA box of the NHWC activation tensor shifted by the tap offset (out-of-bounds = zero padding).
-//   Wp is packed once per weight version (pack.cu): K-major, gate-interleaved so one N tile of
-//   BLOCK_N columns holds the i,f,g,o pre-activations of the same BLOCK_N/4 channels.
+//   TMA box of an NHWC fp16 plane shifted by the tap offset (out-of-bounds = zero padding).
+//   Wp is packed once per weight version (pack.cu), K-major.
 // Numerics: "split" mode carries every operand as fp16 hi + fp16 lo (22 significand bits after
-//   power-of-two pre-scaling) and issues hi*hi + hi*lo + lo*hi with fp32 accumulation, which is
-//   fp32-grade and keeps the emitted codes bit-exact against the fp32 reference; the non-split
-//   mode issues only hi*hi.
+//   power-of-two pre-scaling) and issues lo*hi + hi*lo + hi*hi with fp32 accumulation (fp32-grade);
+//   the non-split mode issues only hi*hi.
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
 // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; two TMEM accumulators so the
 //   epilogue of tile i overlaps the MMAs of tile i+1.
@@ -35,7 +37,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int STAGES_RAW = SMEM_DATA_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SLOTS = BLOCK_N / 4;  // channels per N tile
+  static constexpr int SLOTS = BLOCK_N / 4;  // channels per N tile (gates epilogue)
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -70,10 +72,169 @@ __device__ __forceinline__ void split_store16(__half* __restrict__ hi, __half* _
     reinterpret_cast<uint4*>(lo)[1] = reinterpret_cast<const uint4*>(l)[1];
   }
 }
+__device__ __forceinline__ void store_half16(__half* __restrict__ dst, const float (&v)[16]) {
+  alignas(16) __half h[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[i] = __float2half_rn(v[i]);
+  reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(h)[0];
+  reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(h)[1];
+}
+__device__ __forceinline__ void store_f32x16(float* __restrict__ dst, const float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
 
+struct TileCoord {
+  int n0, y0, x0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const GateParams& p, int mt, int tiles_x, int tiles_per_img) {
+  TileCoord t;
+  if (p.bn > 1) {
+    t.n0 = mt * p.bn; t.y0 = 0; t.x0 = 0;
+  } else {
+    t.n0 = mt / tiles_per_img;
+    const int rem = mt % tiles_per_img;
+    t.y0 = (rem / tiles_x) * p.bh;
+    t.x0 = (rem % tiles_x) * p.bw;
+  }
+  return t;
+}
+__device__ __forceinline__ int group_of(const GateParams& p, int mt) {
+  int g = 0;
+  while (g + 1 < p.n_groups && mt >= p.group_mtile_end[g]) ++g;
+  return g;
+}
+
+// ---------------------------------------------------------------- epilogues (one tile row per thread)
+// ConvLSTM gates: the N tile holds i,f,g,o of SLOTS channels (columns gate*SLOTS + s)
 template <bool SPLIT, int BLOCK_N>
+__device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_row, int nt, int g, int n,
+                                               int y, int x) {
+  using C = Cfg<SPLIT, BLOCK_N>;
+  const int H = p.H, W = p.W, Co = p.Co;
+  const float inv = __ldg(&p.w_inv_scale[g]);
+  const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
+#pragma unroll 1
+  for (int j = 0; j < C::SLOTS / 16; ++j) {
+    float gi[16], gf[16], gg[16], go[16];
+    ptx::tmem_ld16(t_row + 0 * C::SLOTS + j * 16, gi);
+    ptx::tmem_ld16(t_row + 1 * C::SLOTS + j * 16, gf);
+    ptx::tmem_ld16(t_row + 2 * C::SLOTS + j * 16, gg);
+    ptx::tmem_ld16(t_row + 3 * C::SLOTS + j * 16, go);
+    ptx::tmem_ld_wait();
+    const int p0 = nt * C::SLOTS + j * 16;  // first physical channel of this chunk
+    float cv[16];
+    if (p.has_cell) {
+      const float* cp = (p.c_prev ? p.c_prev : p.c_state) + pix * Co + p0;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 t = reinterpret_cast<const float4*>(cp)[v];
+        cv[4 * v + 0] = t.x; cv[4 * v + 1] = t.y; cv[4 * v + 2] = t.z; cv[4 * v + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cv[i] = 0.0f;
+    }
+    float hv[16];
+    if (p.precise) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        gi[i] = sigmoid_precise(gi[i] * inv);
+        gf[i] = sigmoid_precise(gf[i] * inv);
+        gg[i] = tanhf(gg[i] * inv);
+        go[i] = sigmoid_precise(go[i] * inv);
+        // reference rounding: separate multiplies and add (no fma), cell.py:138-139
+        const float cn = __fadd_rn(__fmul_rn(gf[i], cv[i]), __fmul_rn(gi[i], gg[i]));
+        cv[i] = cn;
+        hv[i] = __fmul_rn(go[i], tanhf(cn));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        gi[i] = sigmoid_fast(gi[i] * inv);
+        gf[i] = sigmoid_fast(gf[i] * inv);
+        gg[i] = tanh_fast(gg[i] * inv);
+        go[i] = sigmoid_fast(go[i] * inv);
+        const float cn = fmaf(gf[i], cv[i], gi[i] * gg[i]);
+        cv[i] = cn;
+        hv[i] = go[i] * tanh_fast(cn);
+      }
+    }
+    store_f32x16(p.c_state + pix * Co + p0, cv);
+    if (p.gates_out) {  // training: keep the activated gates for backward, [pix][gate][Co]
+      __half* gp = p.gates_out + pix * (4 * Co) + p0;
+      store_half16(gp, gi);
+      store_half16(gp + Co, gf);
+      store_half16(gp + 2 * Co, gg);
+      store_half16(gp + 3 * Co, go);
+    }
+    // consumer copy (fused PixelShuffleCell)
+    size_t noff = 0;
+    if (p.next_mode == NEXT_SAME) {
+      noff = pix * Co + p0;
+    } else if (p.next_mode == NEXT_DOWN) {
+      const size_t npix = (static_cast<size_t>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+      noff = npix * (4 * Co) + ((y & 1) * 2 + (x & 1)) * Co + p0;
+    } else if (p.next_mode == NEXT_UP) {
+      const int cq = Co >> 2;
+      const int qq = p0 / cq, cc = p0 - qq * cq;
+      const size_t npix =
+          (static_cast<size_t>(n) * (2 * H) + (2 * y + (qq >> 1))) * (2 * W) + (2 * x + (qq & 1));
+      noff = npix * cq + cc;
+    }
+    if (p.next_mode != NEXT_NONE && p.next_f32) store_f32x16(reinterpret_cast<float*>(p.next[0]) + noff, hv);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hv[i] *= ACT_SCALE;
+    split_store16(p.h_out[0] + pix * Co + p0, p.h_out[1] + pix * Co + p0, hv, SPLIT);
+    if (p.next_mode != NEXT_NONE && !p.next_f32)
+      split_store16(reinterpret_cast<__half*>(p.next[0]) + noff, reinterpret_cast<__half*>(p.next[1]) + noff,
+                    hv, SPLIT);
+  }
+}
+
+// dgrad: columns are output channels [dX (n_x) | dH_prev (n_out - n_x)], fp32 stores
+template <bool SPLIT, int BLOCK_N>
+__device__ __forceinline__ void epilogue_dgrad(const GateParams& p, uint32_t t_row, int nt, int g, int n,
+                                               int y, int x) {
+  const int H = p.H, W = p.W;
+  const float inv = __ldg(&p.w_inv_scale[g]) * __ldg(p.a_inv_scale);
+  const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
+  const int col0 = nt * BLOCK_N;
+  const int width = min(BLOCK_N, p.n_out - col0);
+#pragma unroll 1
+  for (int j = 0; j < width / 16; ++j) {
+    float v[16];
+    ptx::tmem_ld16(t_row + j * 16, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= inv;
+    const int c = col0 + j * 16;
+    if (c < p.n_x) {
+      size_t off;
+      if (p.dx_mode == DX_SAME) {
+        off = pix * p.n_x + c;
+      } else if (p.dx_mode == DX_INV_DOWN) {
+        const int cp = p.n_x >> 2;  // producer's channel count
+        const int qq = c / cp, cc = c - qq * cp;
+        const size_t ppix =
+            (static_cast<size_t>(n) * (2 * H) + (2 * y + (qq >> 1))) * (2 * W) + (2 * x + (qq & 1));
+        off = ppix * cp + cc;
+      } else {  // DX_INV_UP
+        const int qq = (y & 1) * 2 + (x & 1);
+        const size_t ppix = (static_cast<size_t>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+        off = ppix * (4 * p.n_x) + qq * p.n_x + c;
+      }
+      store_f32x16(p.dx_out + off, v);
+    } else if (p.dhrec_out) {
+      store_f32x16(p.dhrec_out + pix * (p.n_out - p.n_x) + (c - p.n_x), v);
+    }
+  }
+}
+
+template <bool SPLIT, int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-convlstm_gates_kernel(const __grid_constant__ GateParams p) {
+conv_gemm_kernel(const __grid_constant__ GateParams p) {
   using C = Cfg<SPLIT, BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -134,18 +295,8 @@ convlstm_gates_kernel(const __grid_constant__ GateParams p) {
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_ntiles;
         const int mt = tile / p.n_ntiles;
-        int n0, y0, x0;
-        if (p.bn > 1) {
-          n0 = mt * p.bn; y0 = 0; x0 = 0;
-        } else {
-          n0 = mt / tiles_per_img;
-          const int rem = mt % tiles_per_img;
-          y0 = (rem / tiles_x) * p.bh;
-          x0 = (rem % tiles_x) * p.bw;
-        }
-        int g = 0;
-        while (g + 1 < p.n_groups && mt >= p.group_mtile_end[g]) ++g;
-        const int wrow = g * 4 * p.Co + nt * BLOCK_N;
+        const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
+        const int wrow = group_of(p, mt) * p.w_group_rows + nt * BLOCK_N;
         for (int kb = 0; kb < nkb; ++kb) {
           const bool is_h = kb >= 9 * cx_chunks;
           const int kk = is_h ? kb - 9 * cx_chunks : kb;
@@ -158,10 +309,10 @@ convlstm_gates_kernel(const __grid_constant__ GateParams p) {
           ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           const CUtensorMap* ta = is_h ? p.tm_h : p.tm_x;
-          ptx::tma_load_4d(st, &ta[0], &full_bar[stage], cc * BLOCK_K, x0 + dx, y0 + dy, n0);
+          ptx::tma_load_4d(st, &ta[0], &full_bar[stage], cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
           if (SPLIT)
-            ptx::tma_load_4d(st + A_TILE_BYTES, &ta[1], &full_bar[stage], cc * BLOCK_K, x0 + dx,
-                             y0 + dy, n0);
+            ptx::tma_load_4d(st + A_TILE_BYTES, &ta[1], &full_bar[stage], cc * BLOCK_K, tc.x0 + dx,
+                             tc.y0 + dy, tc.n0);
           uint8_t* sb = st + (SPLIT ? 2 : 1) * A_TILE_BYTES;
           ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], kcol, wrow);
           if (SPLIT)
@@ -173,11 +324,14 @@ convlstm_gates_kernel(const __grid_constant__ GateParams p) {
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(TILE_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        // dgrad: the last N tile of a row may be narrower than BLOCK_N (UMMA N is a runtime field)
+        int width = BLOCK_N;
+        if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - (tile % p.n_ntiles) * BLOCK_N);
+        const uint32_t idesc = ptx::umma_idesc_f16(TILE_M, width);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -219,127 +373,21 @@ convlstm_gates_kernel(const __grid_constant__ GateParams p) {
     const int xl = row % p.bw;
     const int yl = (row / p.bw) % p.bh;
     const int nl = row / (p.bw * p.bh);
-    const int H = p.H, W = p.W, Co = p.Co;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.n_ntiles;
       const int mt = tile / p.n_ntiles;
-      int n0, y0, x0;
-      if (p.bn > 1) {
-        n0 = mt * p.bn; y0 = 0; x0 = 0;
-      } else {
-        n0 = mt / tiles_per_img;
-        const int rem = mt % tiles_per_img;
-        y0 = (rem / tiles_x) * p.bh;
-        x0 = (rem % tiles_x) * p.bw;
-      }
-      int g = 0;
-      while (g + 1 < p.n_groups && mt >= p.group_mtile_end[g]) ++g;
-      const float inv = __ldg(&p.w_inv_scale[g]);
-      const int n = n0 + nl, y = y0 + yl, x = x0 + xl;
-      const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
-
+      const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
+      const int g = group_of(p, mt);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-
-#pragma unroll 1
-      for (int j = 0; j < C::SLOTS / 16; ++j) {
-        float gi[16], gf[16], gg[16], go[16];
-        ptx::tmem_ld16(t_row + 0 * C::SLOTS + j * 16, gi);
-        ptx::tmem_ld16(t_row + 1 * C::SLOTS + j * 16, gf);
-        ptx::tmem_ld16(t_row + 2 * C::SLOTS + j * 16, gg);
-        ptx::tmem_ld16(t_row + 3 * C::SLOTS + j * 16, go);
-        ptx::tmem_ld_wait();
-        const int p0 = nt * C::SLOTS + j * 16;  // first physical channel of this chunk
-        float* cptr = p.c_state + pix * Co + p0;
-        float cv[16];
-        if (p.has_cell) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const float4 t = reinterpret_cast<const float4*>(cptr)[v];
-            cv[4 * v + 0] = t.x; cv[4 * v + 1] = t.y; cv[4 * v + 2] = t.z; cv[4 * v + 3] = t.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) cv[i] = 0.0f;
-        }
-        float hv[16];
-        if (p.precise) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float ig = sigmoid_precise(gi[i] * inv);
-            const float fg = sigmoid_precise(gf[i] * inv);
-            const float cg = tanhf(gg[i] * inv);
-            const float og = sigmoid_precise(go[i] * inv);
-            // reference rounding: separate multiplies and add (no fma), cell.py:138-139
-            const float cn = __fadd_rn(__fmul_rn(fg, cv[i]), __fmul_rn(ig, cg));
-            cv[i] = cn;
-            hv[i] = __fmul_rn(og, tanhf(cn));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float ig = sigmoid_fast(gi[i] * inv);
-            const float fg = sigmoid_fast(gf[i] * inv);
-            const float cg = tanh_fast(gg[i] * inv);
-            const float og = sigmoid_fast(go[i] * inv);
-            const float cn = fmaf(fg, cv[i], ig * cg);
-            cv[i] = cn;
-            hv[i] = og * tanh_fast(cn);
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          reinterpret_cast<float4*>(cptr)[v] =
-              make_float4(cv[4 * v + 0], cv[4 * v + 1], cv[4 * v + 2], cv[4 * v + 3]);
-
-        // consumer copy (fused PixelShuffleCell)
-        if (p.next_mode != NEXT_NONE) {
-          size_t noff;
-          if (p.next_mode == NEXT_SAME) {
-            noff = pix * Co + p0;
-          } else if (p.next_mode == NEXT_DOWN) {
-            const size_t npix = (static_cast<size_t>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
-            noff = npix * (4 * Co) + ((y & 1) * 2 + (x & 1)) * Co + p0;
-          } else {  // NEXT_UP
-            const int cq = Co >> 2;
-            const int qq = p0 / cq, cc = p0 - qq * cq;
-            const size_t npix =
-                (static_cast<size_t>(n) * (2 * H) + (2 * y + (qq >> 1))) * (2 * W) + (2 * x + (qq & 1));
-            noff = npix * cq + cc;
-          }
-          if (p.next_f32) {
-            float* np_ = reinterpret_cast<float*>(p.next[0]) + noff;
-#pragma unroll
-            for (int v = 0; v < 4; ++v)
-              reinterpret_cast<float4*>(np_)[v] =
-                  make_float4(hv[4 * v + 0], hv[4 * v + 1], hv[4 * v + 2], hv[4 * v + 3]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) hv[i] *= ACT_SCALE;
-        split_store16(p.h_out[0] + pix * Co + p0, p.h_out[1] + pix * Co + p0, hv, SPLIT);
-        if (p.next_mode != NEXT_NONE && !p.next_f32) {
-          size_t noff;
-          if (p.next_mode == NEXT_SAME) {
-            noff = pix * Co + p0;
-          } else if (p.next_mode == NEXT_DOWN) {
-            const size_t npix = (static_cast<size_t>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
-            noff = npix * (4 * Co) + ((y & 1) * 2 + (x & 1)) * Co + p0;
-          } else {
-            const int cq = Co >> 2;
-            const int qq = p0 / cq, cc = p0 - qq * cq;
-            const size_t npix =
-                (static_cast<size_t>(n) * (2 * H) + (2 * y + (qq >> 1))) * (2 * W) + (2 * x + (qq & 1));
-            noff = npix * cq + cc;
-          }
-          split_store16(reinterpret_cast<__half*>(p.next[0]) + noff,
-                        reinterpret_cast<__half*>(p.next[1]) + noff, hv, SPLIT);
-        }
-      }
+      if (EPI == EPI_GATES)
+        epilogue_gates<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl);
+      else
+        epilogue_dgrad<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl);
       // release the accumulator to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
@@ -355,10 +403,10 @@ convlstm_gates_kernel(const __grid_constant__ GateParams p) {
   }
 }
 
-template <bool SPLIT, int BLOCK_N>
+template <bool SPLIT, int BLOCK_N, int EPI>
 int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<SPLIT, BLOCK_N>;
-  auto kern = convlstm_gates_kernel<SPLIT, BLOCK_N>;
+  auto kern = conv_gemm_kernel<SPLIT, BLOCK_N, EPI>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e =
@@ -389,18 +437,23 @@ int launch_convlstm_gates(const GateParams& p, bool split, int block_n, int num_
                           cudaStream_t stream) {
   if (split) {
     switch (block_n) {
-      case 256: return launch_t<true, 256>(p, num_sms, stream);
-      case 128: return launch_t<true, 128>(p, num_sms, stream);
-      case 64: return launch_t<true, 64>(p, num_sms, stream);
+      case 256: return launch_t<true, 256, EPI_GATES>(p, num_sms, stream);
+      case 128: return launch_t<true, 128, EPI_GATES>(p, num_sms, stream);
+      case 64: return launch_t<true, 64, EPI_GATES>(p, num_sms, stream);
     }
   } else {
     switch (block_n) {
-      case 256: return launch_t<false, 256>(p, num_sms, stream);
-      case 128: return launch_t<false, 128>(p, num_sms, stream);
-      case 64: return launch_t<false, 64>(p, num_sms, stream);
+      case 256: return launch_t<false, 256, EPI_GATES>(p, num_sms, stream);
+      case 128: return launch_t<false, 128, EPI_GATES>(p, num_sms, stream);
+      case 64: return launch_t<false, 64, EPI_GATES>(p, num_sms, stream);
     }
   }
   return static_cast<int>(cudaErrorInvalidValue);
+}
+
+int launch_convlstm_dgrad(const GateParams& p, bool split, int num_sms, cudaStream_t stream) {
+  return split ? launch_t<true, 256, EPI_DGRAD>(p, num_sms, stream)
+               : launch_t<false, 256, EPI_DGRAD>(p, num_sms, stream);
 }
 
 }  // namespace drasic

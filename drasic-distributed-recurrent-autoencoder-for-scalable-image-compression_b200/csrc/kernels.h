@@ -28,12 +28,20 @@ enum NextMode : int {
   NEXT_DOWN = 2,  // pixel_unshuffle(2): pixel (y/2,x/2), physical channel ((y&1)*2+(x&1))*Co + p
   NEXT_UP = 3,    // pixel_shuffle(2):  own order QUAD, p = q*(Co/4)+c -> pixel (2y+q/2, 2x+q%2), ch c
 };
+// where the dgrad kernel routes the input gradient (the inverse of the producer's NextMode)
+enum DxMode : int {
+  DX_SAME = 0,      // same pixel / channel (consumer is a pointwise kernel)
+  DX_INV_DOWN = 1,  // input came through pixel_unshuffle: ch q*Cp+c at (y,x) -> producer (2y+q/2, 2x+q%2), ch c
+  DX_INV_UP = 2,    // input came through pixel_shuffle:  ch c at (Y,X) -> producer (Y/2, X/2), ch q*Cin+c
+};
 
 struct GateParams {
   CUtensorMap tm_x[2];  // layer input  NHWC fp16 {hi, lo}
   CUtensorMap tm_h[2];  // previous hidden state NHWC fp16 {hi, lo}
   CUtensorMap tm_w[2];  // packed gate weights [groups*4Co, 9Cin+9Co] fp16 {hi, lo}
-  float* c_state;       // [B,H,W,Co] fp32, updated in place
+  float* c_state;       // [B,H,W,Co] fp32 new cell state (in place when c_prev == nullptr)
+  const float* c_prev;  // nullable: previous cell state in a separate buffer (training keeps every c_t)
+  __half* gates_out;    // nullable: post-activation gates [B,H,W,4,Co] fp16, saved for backward
   __half* h_out[2];     // new hidden state (own layout), {hi, lo}
   void* next[2];        // consumer copy of h: fp16 {hi, lo} or fp32 (next[0])
   const float* w_inv_scale;  // [n_groups] power of two: 1 / (ACT_SCALE * weight scale)
@@ -45,11 +53,22 @@ struct GateParams {
   int precise;               // 1: IEEE exp/div/tanh (parity mode); 0: tanh.approx
   int n_groups;
   const int* group_mtile_end;  // device [n_groups]: group g owns m-tiles [end[g-1], end[g])
+  // ---- dgrad epilogue (EPI_DGRAD): D[pixels, Nout] = conv3x3^T(dG) ; Cin here = 4*Co of the layer
+  int w_group_rows;            // weight-matrix rows per group (4Co for gates, Nout rounded for dgrad)
+  int n_out;                   // dgrad: output columns = layer Cin + layer Co
+  int n_x;                     // dgrad: columns [0,n_x) are dX, [n_x,n_out) are dH_{t-1}
+  int dx_mode;                 // DxMode
+  float* dx_out;               // dgrad: fp32 gradient w.r.t. the layer input, routed by dx_mode
+  float* dhrec_out;            // dgrad: fp32 [B,H,W,n_out-n_x] gradient w.r.t. h_{t-1} (nullable at t=0)
+  const float* a_inv_scale;    // dgrad: device scalar, 1 / scale of the fp16 dG planes
 };
+
+enum EpiKind : int { EPI_GATES = 0, EPI_DGRAD = 1 };
 
 // launches the persistent tcgen05 gate kernel; returns a cudaError_t as int
 int launch_convlstm_gates(const GateParams& p, bool split, int block_n, int num_sms,
                           cudaStream_t stream);
+int launch_convlstm_dgrad(const GateParams& p, bool split, int num_sms, cudaStream_t stream);
 size_t convlstm_gates_smem_bytes(bool split, int block_n);
 
 }  // namespace drasic

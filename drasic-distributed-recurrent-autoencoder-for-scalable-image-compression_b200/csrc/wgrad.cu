@@ -1,0 +1,273 @@
+// Weight-gradient GEMM of a ConvLSTM cell for sm_100a (tcgen05, TMA, TMEM) -- the wgrad half of what
+// autograd runs for `loss.backward()` (reference train_model.py:115) through modules/cell.py:117,132:
+//
+//   dW_in[gch, ci, tap] = sum_pixels dG[pix, gch] * X[pix + tap, ci]
+//   dW_h [gch, ch, tap] = sum_pixels dG[pix, gch] * H_prev[pix + tap, ch]
+//
+// GEMM view: D[M = 128 gate channels, N = up to 256 (tap, channel) columns] += A^T B over K = pixels.
+// Both operands are NHWC fp16 planes, i.e. MN-major with respect to K = pixels: a K block of 64
+// pixels is loaded as TMA boxes of (64 channels x 64 pixels) -- 2 boxes of dG for A, up to 4 boxes of
+// the tap-shifted activation plane for B (out-of-bounds pixels read as zero = conv padding) -- and fed
+// to tcgen05.mma through MN-major SWIZZLE_128B descriptors.  One launch covers one (layer, iteration);
+// tiles are (node, m-tile, n-tile, k-split) and accumulate into the fp32 packed-order gradient with
+// vector atomics, so iterations, k-splits and launches compose by addition.
+// Roles / pipeline are those of the gate kernel: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue.
+#include "backward.h"
+#include "ptx.cuh"
+
+namespace drasic {
+
+namespace {
+
+constexpr int WG_THREADS = 192;
+constexpr int BOX_BYTES = 64 * 64 * 2;       // one (64 ch x 64 pixel) fp16 box = 8 KB
+constexpr int WG_BLOCK_N = 256;
+constexpr int WG_DATA_BUDGET = 196608;
+
+template <bool SPLIT>
+struct WCfg {
+  static constexpr int A_BYTES = 2 * BOX_BYTES;   // 128 gate channels
+  static constexpr int B_BYTES = 4 * BOX_BYTES;   // 256 columns
+  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = WG_DATA_BUDGET / STAGE_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * WG_BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+// MN-major SWIZZLE_128B operand: 64 contiguous MN elements (128 B) per K row, 8 K rows per 1024-byte
+// swizzle atom, atoms stacked along K (SBO = 1024), next 64 MN elements LBO = 8192 bytes further.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(BOX_BYTES >> 4) << 16;  // LBO
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;      // SBO
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;               // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+struct WTile {
+  int g, mt, is_h, u0, nunits, kb_lo, kb_hi;
+};
+
+__device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile) {
+  const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
+  WTile t;
+  const int ks = tile % p.k_splits;
+  int r = tile / p.k_splits;
+  const int nt = r % nt_total;
+  r /= nt_total;
+  t.mt = r % p.m_tiles;
+  t.g = r / p.m_tiles;
+  t.is_h = nt >= p.n_tiles_x;
+  const int ntl = t.is_h ? nt - p.n_tiles_x : nt;
+  const int units = 9 * ((t.is_h ? p.Co : p.Cin) / 64);
+  t.u0 = ntl * 4;
+  t.nunits = min(4, units - t.u0);
+  const int g_lo = (t.g == 0 || !p.group_kb_end) ? 0 : p.group_kb_end[t.g - 1];
+  const int g_hi = p.group_kb_end ? p.group_kb_end[t.g] : p.n_kb;
+  const int len = g_hi - g_lo;
+  const int per = (len + p.k_splits - 1) / p.k_splits;
+  t.kb_lo = min(g_hi, g_lo + ks * per);
+  t.kb_hi = min(g_hi, t.kb_lo + per);
+  return t;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using C = WCfg<SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&p.tm_g[0]);
+    ptx::prefetch_tmap(&p.tm_x[0]);
+    if (p.has_h) ptx::prefetch_tmap(&p.tm_h[0]);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
+  const int total_tiles = p.n_groups * p.m_tiles * nt_total * p.k_splits;
+  const int HW = p.H * p.W;
+  const int kb_per_img = HW >= 64 ? HW / 64 : 1;   // HW < 64: one K block spans kbn images
+  const int kbx = p.W / p.kbw;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const WTile t = decode_tile(p, tile);
+        const CUtensorMap* tb = t.is_h ? p.tm_h : p.tm_x;
+        const int cpu = (t.is_h ? p.Co : p.Cin) / 64;
+        const uint32_t bytes = (SPLIT ? 2 : 1) * (C::A_BYTES + t.nunits * BOX_BYTES);
+        for (int kb = t.kb_lo; kb < t.kb_hi; ++kb) {
+          int n0, y0, x0;
+          if (HW >= 64) {
+            n0 = kb / kb_per_img;
+            const int rem = kb - n0 * kb_per_img;
+            y0 = (rem / kbx) * p.kbh;
+            x0 = (rem % kbx) * p.kbw;
+          } else {
+            n0 = kb * p.kbn; y0 = 0; x0 = 0;
+          }
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], bytes);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
+            uint8_t* sa = st + pl * C::A_BYTES;
+            uint8_t* sb = st + (SPLIT ? 2 : 1) * C::A_BYTES + pl * C::B_BYTES;
+            ptx::tma_load_4d(sa, &p.tm_g[pl], &full_bar[stage], t.mt * 128, x0, y0, n0);
+            ptx::tma_load_4d(sa + BOX_BYTES, &p.tm_g[pl], &full_bar[stage], t.mt * 128 + 64, x0, y0, n0);
+            for (int u = 0; u < t.nunits; ++u) {
+              const int unit = t.u0 + u;
+              const int tap = unit / cpu, chunk = unit - tap * cpu;
+              ptx::tma_load_4d(sb + u * BOX_BYTES, &tb[pl], &full_bar[stage], chunk * 64, x0 + tap % 3 - 1,
+                               y0 + tap / 3 - 1, n0);
+            }
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const WTile t = decode_tile(p, tile);
+        if (t.kb_hi <= t.kb_lo) continue;  // empty node / empty k-split: nothing to add
+        const uint32_t idesc = idesc_mn(128, t.nunits * 64);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ++it;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * WG_BLOCK_N;
+        for (int kb = t.kb_lo; kb < t.kb_hi; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + C::A_BYTES;
+          const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * C::A_BYTES;
+          const uint32_t b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {            // 4 x UMMA_K(16 pixels) per 64-pixel K block
+            const uint32_t koff = k * 16 * 128;    // 16 K rows of 128 bytes
+            const uint64_t da_hi = umma_desc_mn_sw128(a_hi + koff);
+            const uint64_t db_hi = umma_desc_mn_sw128(b_hi + koff);
+            const uint32_t first = (kb != t.kb_lo || k != 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint64_t da_lo = umma_desc_mn_sw128(a_lo + koff);
+              const uint64_t db_lo = umma_desc_mn_sw128(b_lo + koff);
+              ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, first);
+              ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+            } else {
+              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, first);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================================================== epilogue: fp32 vector atomics
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int Kw = 9 * (p.Cin + p.Co);
+    const float scale = __ldg(p.g_inv_scale) * ACT_INV_SCALE;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const WTile t = decode_tile(p, tile);
+      if (t.kb_hi <= t.kb_lo) continue;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ++it;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * WG_BLOCK_N;
+      float* dst = p.gw + (static_cast<size_t>(t.g) * 4 * p.Co + t.mt * 128 + row) * Kw +
+                   (t.is_h ? 9 * p.Cin : 0) + t.u0 * 64;
+#pragma unroll 1
+      for (int j = 0; j < t.nunits * 4; ++j) {
+        float v[16];
+        ptx::tmem_ld16(t_row + j * 16, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          atomicAdd(reinterpret_cast<float4*>(dst + j * 16) + qd,
+                    make_float4(v[4 * qd] * scale, v[4 * qd + 1] * scale, v[4 * qd + 2] * scale, v[4 * qd + 3] * scale));
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <bool SPLIT>
+int launch_w(const WgradParams& p, int num_sms, cudaStream_t stream) {
+  using C = WCfg<SPLIT>;
+  auto kern = wgrad_kernel<SPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
+  const int total = p.n_groups * p.m_tiles * nt_total * p.k_splits;
+  const int grid = total < num_sms ? total : num_sms;
+  kern<<<grid, WG_THREADS, C::SMEM_BYTES, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+int launch_wgrad(const WgradParams& p, bool split, int num_sms, cudaStream_t stream) {
+  return split ? launch_w<true>(p, num_sms, stream) : launch_w<false>(p, num_sms, stream);
+}
+
+}  // namespace drasic

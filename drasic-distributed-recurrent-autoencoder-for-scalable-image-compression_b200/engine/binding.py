@@ -17,7 +17,8 @@ vp, ip, fp = C.c_void_p, C.c_int, C.c_void_p
 
 class ConvLSTMArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('x_hi', 'x_lo', 'h_hi', 'h_lo', 'w_hi', 'w_lo', 'w_inv_scale', 'c_state',
-                                  'h_out_hi', 'h_out_lo', 'next_hi', 'next_lo', 'group_mtile_end')] + \
+                                  'c_prev', 'gates_out', 'h_out_hi', 'h_out_lo', 'next_hi', 'next_lo',
+                                  'group_mtile_end')] + \
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'has_state', 'next_mode',
                                   'next_f32', 'split', 'precise', 'block_n')]
 
@@ -35,10 +36,44 @@ class TailHeadArgs(C.Structure):
                                   'precise', 'split')]
 
 
+class DgradArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('dg_hi', 'dg_lo', 'w_hi', 'w_lo', 'w_inv_scale', 'dg_inv_scale', 'dx_out',
+                                  'dhrec_out', 'group_mtile_end')] + \
+               [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'dx_mode', 'split')]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('dg_hi', 'dg_lo', 'x_hi', 'x_lo', 'h_hi', 'h_lo', 'gw', 'dg_inv_scale',
+                                  'group_kb_end')] + \
+               [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'has_h', 'split', 'k_splits')]
+
+
+class BottleneckBwdArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('dd0', 'h_e3', 'z', 'codes', 'w_e4', 'w_d0', 'perm', 'group_img_end', 'dh_e3',
+                                  'dw_e4', 'dw_d0')] + \
+               [(n, ip) for n in ('B_pad', 'HW', 'Ch', 'code', 'n_enc_groups', 'n_dec_groups')]
+
+
+class TailBwdArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('d3_next', 'w_d4', 'img', 'recon_t', 'gacc', 'dh_d3', 'dw_d4', 'perm',
+                                  'group_img_end')] + [('loss_scale', C.c_float)] + \
+               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'loss_kind', 'n_dec_groups', 'has_acc')]
+
+
+class HeadBwdArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('du1', 'w_e0', 'b_e0', 'img', 'recon_prev', 'gacc', 'dw_e0', 'db_e0', 'perm',
+                                  'group_img_end')] + \
+               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'propagate', 'n_enc_groups')]
+
+
+DX_SAME, DX_INV_DOWN, DX_INV_UP = 0, 1, 2
+
 # every symbol include/drasic_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes',
            'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
-           'drasic_conv1x1_fwd', 'drasic_quantize_fwd')
+           'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_pointwise', 'drasic_convert_scale',
+           'drasic_pack_dgrad_weights', 'drasic_convlstm_bwd_data', 'drasic_convlstm_bwd_weight',
+           'drasic_unpack_wgrad', 'drasic_bottleneck_bwd', 'drasic_tail_bwd', 'drasic_head_bwd')
 
 _lib = None
 
@@ -72,6 +107,24 @@ def lib():
     L.drasic_conv1x1_fwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, vp]
     L.drasic_quantize_fwd.restype = C.c_int
     L.drasic_quantize_fwd.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.drasic_lstm_bwd_pointwise.restype = C.c_int
+    L.drasic_lstm_bwd_pointwise.argtypes = [vp, vp, vp, vp, vp, vp, ip, vp, vp, C.c_size_t, ip, vp]
+    L.drasic_convert_scale.restype = C.c_int
+    L.drasic_convert_scale.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.drasic_pack_dgrad_weights.restype = C.c_int
+    L.drasic_pack_dgrad_weights.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, vp]
+    L.drasic_convlstm_bwd_data.restype = C.c_int
+    L.drasic_convlstm_bwd_data.argtypes = [C.POINTER(DgradArgs), vp]
+    L.drasic_convlstm_bwd_weight.restype = C.c_int
+    L.drasic_convlstm_bwd_weight.argtypes = [C.POINTER(WgradArgs), vp]
+    L.drasic_unpack_wgrad.restype = C.c_int
+    L.drasic_unpack_wgrad.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp]
+    L.drasic_bottleneck_bwd.restype = C.c_int
+    L.drasic_bottleneck_bwd.argtypes = [C.POINTER(BottleneckBwdArgs), vp]
+    L.drasic_tail_bwd.restype = C.c_int
+    L.drasic_tail_bwd.argtypes = [C.POINTER(TailBwdArgs), vp]
+    L.drasic_head_bwd.restype = C.c_int
+    L.drasic_head_bwd.argtypes = [C.POINTER(HeadBwdArgs), vp]
     _lib = L
     return L
 

@@ -119,30 +119,36 @@ class CodecEngine(object):
                 return bn
         return 64
 
-    def _get_arena(self, B_pad, H, W, device):
-        key = (B_pad, H, W, str(device))
+    def _get_arena(self, B_pad, H, W, device, T=0):
+        """T == 0: inference arena (h ping-pongs, c in place, one buffer per edge).  T > 0: training
+        arena that keeps every iteration's h, c, gates and layer inputs for backward-through-time.
+        Buffers are zero-initialised once and reused; padding slots therefore always hold finite data."""
+        key = (B_pad, H, W, str(device), T)
         if self._arena_key == key:
             return self._arena
-        A = {}
+        self._arena = None          # release the previous arena before allocating the next
+        A = {'T': T}
+        n_t = max(T, 1)
         f16 = dict(dtype=torch.float16, device=device)
         f32 = dict(dtype=torch.float32, device=device)
 
-        def planes(*shape):
-            return [torch.zeros(shape, **f16), torch.zeros(shape, **f16) if self.split else None]
-        A['e1_in'] = planes(B_pad, H // 2, W // 2, 128)
-        A['d1_in'] = planes(B_pad, H // 8, W // 8, 128)
+        def planes(n, *shape):
+            return [[torch.zeros(shape, **f16), torch.zeros(shape, **f16) if self.split else None] for _ in range(n)]
+        A['e1_in'] = planes(n_t, B_pad, H // 2, W // 2, 128)
+        A['d1_in'] = planes(n_t, B_pad, H // 8, W // 8, 128)
         for (name, cin, co, div, _, _, nmode, nf32) in ENC_LAYERS + DEC_LAYERS:
             h, w = H // div, W // div
             L = {}
-            L['h'] = [planes(B_pad, h, w, co), planes(B_pad, h, w, co)]   # ping-pong
-            L['c'] = torch.zeros((B_pad, h, w, co), **f32)
+            L['h'] = planes(T if T else 2, B_pad, h, w, co)
+            L['c'] = [torch.zeros((B_pad, h, w, co), **f32) for _ in range(n_t)]
+            L['gates'] = [torch.zeros((B_pad, h, w, 4, co), **f16) for _ in range(T)]
             if nmode == B.NEXT_DOWN:
-                L['next'] = planes(B_pad, h // 2, w // 2, 4 * co)
+                nshape = (B_pad, h // 2, w // 2, 4 * co)
             elif nmode == B.NEXT_UP:
-                L['next'] = [torch.zeros((B_pad, 2 * h, 2 * w, co // 4), **f32), None] if nf32 else \
-                    planes(B_pad, 2 * h, 2 * w, co // 4)
+                nshape = (B_pad, 2 * h, 2 * w, co // 4)
             else:
-                L['next'] = [torch.zeros((B_pad, h, w, co), **f32), None] if nf32 else planes(B_pad, h, w, co)
+                nshape = (B_pad, h, w, co)
+            L['next'] = [[torch.zeros(nshape, **f32), None] for _ in range(n_t)] if nf32 else planes(n_t, *nshape)
             A[name] = L
         self._arena, self._arena_key = A, key
         return A
@@ -178,7 +184,7 @@ class CodecEngine(object):
 
     # ------------------------------------------------------------------ the loop
     def forward(self, sd, img, label, num_iter, training=False, noise=None, loss_kind='mae',
-                label_host=None, want_z=False):
+                label_host=None, want_z=False, save_for_backward=False):
         """sd: mapping reference state_dict key -> fp32 CUDA tensor.  img [B,C,H,W] fp32 in [0,1],
         label [B] node ids.  noise: None (eval / deterministic sign) or [T,B,code,H/8,W/8] uniforms.
         Returns dict(recon [T,B,C,H,W], codes [T,B,code,H/8,W/8], bits [T,B,code*HW/64/8] uint8,
@@ -202,7 +208,9 @@ class CodecEngine(object):
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
-        A = self._get_arena(Bp, H, W, dev)
+        A = self._get_arena(Bp, H, W, dev, T if save_for_backward else 0)
+        keep = save_for_backward
+        want_z = want_z or keep
         code, hc, wc = self.code, H // 8, W // 8
         if training and noise is None:
             noise = torch.rand((T, Bn, code, hc, wc), device=dev, dtype=torch.float32)
@@ -227,6 +235,7 @@ class CodecEngine(object):
             ly = _Layer()
             ly.name, ly.cin, ly.co, ly.h, ly.w = name, cin, co, h, w
             ly.next_mode, ly.next_f32 = nmode, nf32
+            ly.in_order, ly.out_order, ly.is_enc, ly.idx, ly.prefs = io, oo, is_enc, idx, prefs
             ly.block_n = self._block_n(n_mtiles, co)
             ly.groups = len(prefs)
             ly.hi, ly.lo, ly.inv, _ = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
@@ -256,14 +265,15 @@ class CodecEngine(object):
             a = B.TailHeadArgs()
             last = (mode != B.TAIL_INIT and t == T - 1)
             if mode != B.TAIL_INIT:
-                a.d3_next = P(A['D3']['next'][0])
+                a.d3_next = P(A['D3']['next'][t if keep else 0][0])
                 a.w_d4 = P(w_d4)
                 a.recon_out = recon[t].data_ptr()
                 a.recon_prev = recon[t - 1].data_ptr() if mode == B.TAIL_STEP else None
                 a.loss_acc = loss_acc[t].data_ptr()
             a.w_e0, a.b_e0, a.img, a.perm = P(w_e0), P(b_e0), P(img), P(plan.perm)
             if not last:
-                a.e1_in_hi, a.e1_in_lo = P(A['e1_in'][0]), P(A['e1_in'][1])
+                e1 = A['e1_in'][(t + 1) if keep else 0]
+                a.e1_in_hi, a.e1_in_lo = P(e1[0]), P(e1[1])
             a.group_img_end = P(plan.group_img_end)
             a.B_pad, a.C, a.H, a.W, a.mode = Bp, Cc, H, W, mode
             a.loss_kind = B.LOSS_KINDS[loss_kind]
@@ -274,14 +284,23 @@ class CodecEngine(object):
 
         def gate(ly, x_planes, t):
             Lb = A[ly.name]
-            cur, prv = Lb['h'][t & 1], Lb['h'][(t & 1) ^ 1]
             a = B.ConvLSTMArgs()
+            if keep:
+                cur, prv = Lb['h'][t], Lb['h'][t - 1] if t > 0 else Lb['h'][t]
+                a.c_state = P(Lb['c'][t])
+                a.c_prev = P(Lb['c'][t - 1]) if t > 0 else None
+                a.gates_out = P(Lb['gates'][t])
+                nxt = Lb['next'][t]
+            else:
+                cur, prv = Lb['h'][t & 1], Lb['h'][(t & 1) ^ 1]
+                a.c_state = P(Lb['c'][0])
+                nxt = Lb['next'][0]
             a.x_hi, a.x_lo = P(x_planes[0]), P(x_planes[1])
-            a.h_hi, a.h_lo = P(prv[0]), P(prv[1])
+            if t > 0:
+                a.h_hi, a.h_lo = P(prv[0]), P(prv[1])
             a.w_hi, a.w_lo, a.w_inv_scale = P(ly.hi), P(ly.lo), P(ly.inv)
-            a.c_state = P(Lb['c'])
             a.h_out_hi, a.h_out_lo = P(cur[0]), P(cur[1])
-            a.next_hi, a.next_lo = P(Lb['next'][0]), P(Lb['next'][1])
+            a.next_hi, a.next_lo = P(nxt[0]), P(nxt[1])
             a.group_mtile_end = P(ly.mtile_end)
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups = ly.groups
@@ -293,11 +312,11 @@ class CodecEngine(object):
             flops = 2.0 * Bn * ly.h * ly.w * 4 * ly.co * k
             self._timed('gates_' + ly.name, flops, lambda: B.check(L.drasic_convlstm_fwd(a, stream), 'convlstm_fwd'))
             self.launches += 1
-            return Lb['next']
+            return nxt
 
         tail(B.TAIL_INIT, -1)
         for t in range(T):
-            x = A['e1_in']
+            x = A['e1_in'][t if keep else 0]
             for ly in layers[:3]:
                 x = gate(ly, x, t)
             a = B.BottleneckArgs()
@@ -307,14 +326,15 @@ class CodecEngine(object):
             a.code_out = codes[t].data_ptr()
             a.z_out = zbuf[t].data_ptr() if zbuf is not None else None
             a.bits_out = bits[t].data_ptr()
-            a.d1_in_hi, a.d1_in_lo = P(A['d1_in'][0]), P(A['d1_in'][1])
+            d1 = A['d1_in'][t if keep else 0]
+            a.d1_in_hi, a.d1_in_lo = P(d1[0]), P(d1[1])
             a.group_img_end = P(plan.group_img_end)
             a.B_pad, a.HW, a.Ch, a.code = Bp, hc * wc, 128, code
             a.n_enc_groups, a.n_dec_groups = self.M, self.Md
             a.precise, a.split = self.precise, self.split
             self._timed('bottleneck', 0.0, lambda a=a: B.check(L.drasic_bottleneck_fwd(a, stream), 'bottleneck_fwd'))
             self.launches += 1
-            x = A['d1_in']
+            x = d1
             for ly in layers[3:]:
                 x = gate(ly, x, t)
             tail(B.TAIL_FIRST if t == 0 else B.TAIL_STEP, t)
@@ -323,7 +343,194 @@ class CodecEngine(object):
             out['z'] = zbuf
         # keep the small stacked weights alive until the stream has consumed them
         out['_keep'] = (w_e0, b_e0, w_e4, w_d0, w_d4, noise, img)
+        if keep:
+            self._gen = getattr(self, '_gen', 0) + 1
+            out['_bwd'] = dict(gen=self._gen, A=A, layers=layers, sd=sd, img=img, T=T, loss_kind=loss_kind, w_e0=w_e0, b_e0=b_e0,
+                               w_e4=w_e4, w_d0=w_d0, w_d4=w_d4, enc_pref=enc_pref, dec_pref=dec_pref,
+                               shape=(Bn, Cc, H, W))
         return out
+
+    # ------------------------------------------------------------------ backward through time
+    def _packed_dgrad(self, ly, sd, stream):
+        def lstm_w(prefix, idx):
+            base = '{}.{}.cell.cell.0.'.format(prefix, idx)
+            return sd[base + 'in.cell.cell.main.weight'], sd[base + 'hidden.cell.cell.main.weight']
+        weights = [lstm_w(p, ly.idx) for p in ly.prefs]
+        key = tuple((w.data_ptr(), w._version) for pair in weights for w in pair)
+        hit = self._wcache.get('dgrad_' + ly.name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        L = B.lib()
+        dev = weights[0][0].device
+        G, n_out, K = len(weights), ly.cin + ly.co, 36 * ly.co
+        hi = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
+        lo = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
+        inv = torch.empty((G,), dtype=torch.float32, device=dev)
+        scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
+        plane = n_out * K * 2
+        for g, (w_in, w_h) in enumerate(weights):
+            w_in, w_h = w_in.detach().contiguous(), w_h.detach().contiguous()
+            B.check(L.drasic_pack_dgrad_weights(w_in.data_ptr(), w_h.data_ptr(), ly.cin, ly.co, ly.in_order,
+                                                ly.out_order, hi.data_ptr() + g * plane, lo.data_ptr() + g * plane,
+                                                inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
+                    'pack_dgrad_weights')
+            self.launches += 2
+        val = (hi, lo, inv)
+        self._wcache['dgrad_' + ly.name] = (key, val)
+        return val
+
+    def _bwd_buffers(self, layers, Bp, H, W, dev):
+        key = (Bp, H, W, str(dev))
+        if getattr(self, '_bwd_key', None) == key:
+            return self._bwd_buf
+        self._bwd_buf = None
+        f32 = dict(dtype=torch.float32, device=dev)
+        f16 = dict(dtype=torch.float16, device=dev)
+        W_ = {}
+        for ly in layers:
+            n = (Bp, ly.h, ly.w, ly.co)
+            W_[ly.name] = dict(dh_above=torch.zeros(n, **f32), dh_rec=torch.zeros(n, **f32), dc=torch.zeros(n, **f32),
+                               dgates=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f32),
+                               dg_hi=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16),
+                               dg_lo=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16) if self.split else None,
+                               amax=torch.zeros((1,), dtype=torch.int32, device=dev),
+                               inv=torch.ones((1,), **f32))
+        W_['du1'] = torch.zeros((Bp, H // 2, W // 2, 128), **f32)
+        W_['dd0'] = torch.zeros((Bp, H // 8, W // 8, 128), **f32)
+        self._bwd_buf, self._bwd_key = W_, key
+        return W_
+
+    def backward(self, out, g_loss=None):
+        """Backward-through-time for the forward that produced `out` (save_for_backward=True).
+        Returns {state_dict key: fp32 gradient} for every parameter of the codec."""
+        ctx = out['_bwd']
+        if ctx['gen'] != getattr(self, '_gen', 0):
+            raise RuntimeError('backward() must follow the forward() that saved its state: the per-iteration '
+                               'arena of this engine has been overwritten by a later forward')
+        plan = out['plan']
+        A, layers, sd, img, T = ctx['A'], ctx['layers'], ctx['sd'], ctx['img'], ctx['T']
+        Bn, Cc, H, W = ctx['shape']
+        L = B.lib()
+        dev = img.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        Bp = plan.B_pad
+        P = B.ptr
+        code, hc, wc = self.code, H // 8, W // 8
+        WB = self._bwd_buffers(layers, Bp, H, W, dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        gacc = torch.empty((Bn, Cc, H, W), **f32)
+        dw_e0 = torch.zeros_like(ctx['w_e0'])
+        db_e0 = torch.zeros_like(ctx['b_e0']) if ctx['b_e0'] is not None else None
+        dw_e4, dw_d0, dw_d4 = torch.zeros_like(ctx['w_e4']), torch.zeros_like(ctx['w_d0']), torch.zeros_like(ctx['w_d4'])
+        gw = {ly.name: torch.zeros((ly.groups, 4 * ly.co, 9 * (ly.cin + ly.co)), **f32) for ly in layers}
+        dpk = {ly.name: self._packed_dgrad(ly, sd, stream) for ly in layers}
+        by = {ly.name: ly for ly in layers}
+        sms = self.sms()
+        kb_end = {}
+
+        def group_kb_end(ly):
+            hw = ly.h * ly.w
+            if hw not in kb_end:
+                e = (plan.group_img_end_host.astype(np.int64) * hw) // 64
+                kb_end[hw] = torch.from_numpy(e.astype(np.int32)).to(dev)
+            return kb_end[hw]
+
+        # where each layer's input lives / where its input gradient goes
+        x_of = {'E1': lambda t: A['e1_in'][t], 'E2': lambda t: A['E1']['next'][t], 'E3': lambda t: A['E2']['next'][t],
+                'D1': lambda t: A['d1_in'][t], 'D2': lambda t: A['D1']['next'][t], 'D3': lambda t: A['D2']['next'][t]}
+        dx_of = {'E1': (WB['du1'], B.DX_SAME), 'E2': (WB['E1']['dh_above'], B.DX_INV_DOWN),
+                 'E3': (WB['E2']['dh_above'], B.DX_INV_DOWN), 'D1': (WB['dd0'], B.DX_SAME),
+                 'D2': (WB['D1']['dh_above'], B.DX_INV_UP), 'D3': (WB['D2']['dh_above'], B.DX_INV_UP)}
+
+        def lstm_layer_bwd(ly, t):
+            Lb, wb = A[ly.name], WB[ly.name]
+            n_pix = Bp * ly.h * ly.w
+            wb['amax'].zero_()
+            B.check(L.drasic_lstm_bwd_pointwise(P(Lb['gates'][t]), P(Lb['c'][t]), P(Lb['c'][t - 1]) if t > 0 else None,
+                                                P(wb['dh_above']), P(wb['dh_rec']) if t < T - 1 else None, P(wb['dc']),
+                                                1 if t < T - 1 else 0, P(wb['dgates']), P(wb['amax']), n_pix, ly.co,
+                                                stream), 'lstm_bwd_pointwise')
+            B.check(L.drasic_convert_scale(P(wb['dgates']), P(wb['dg_hi']), P(wb['dg_lo']), P(wb['amax']), P(wb['inv']),
+                                           n_pix * 4 * ly.co, stream), 'convert_scale')
+            hi, lo, inv = dpk[ly.name]
+            a = B.DgradArgs()
+            a.dg_hi, a.dg_lo, a.w_hi, a.w_lo = P(wb['dg_hi']), P(wb['dg_lo']), P(hi), P(lo)
+            a.w_inv_scale, a.dg_inv_scale = P(inv), P(wb['inv'])
+            a.dx_out = P(dx_of[ly.name][0])
+            a.dhrec_out = P(wb['dh_rec']) if t > 0 else None
+            a.group_mtile_end = P(ly.mtile_end)
+            a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
+            a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.split
+            fl = 2.0 * Bn * ly.h * ly.w * 36 * ly.co * (ly.cin + (ly.co if t > 0 else 0))
+            self._timed('dgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_data(a, stream), 'convlstm_bwd_data'))
+            w = B.WgradArgs()
+            xp = x_of[ly.name](t)
+            w.dg_hi, w.dg_lo, w.x_hi, w.x_lo = P(wb['dg_hi']), P(wb['dg_lo']), P(xp[0]), P(xp[1])
+            if t > 0:
+                w.h_hi, w.h_lo = P(Lb['h'][t - 1][0]), P(Lb['h'][t - 1][1])
+            w.gw, w.dg_inv_scale = P(gw[ly.name]), P(wb['inv'])
+            w.group_kb_end = P(group_kb_end(ly)) if ly.groups > 1 else None
+            w.B_pad, w.H, w.W, w.Cin, w.Co = Bp, ly.h, ly.w, ly.cin, ly.co
+            w.n_groups, w.has_h, w.split = ly.groups, 1 if t > 0 else 0, self.split
+            tiles = ly.groups * (4 * ly.co // 128) * ((9 * ly.cin // 64 + 3) // 4 + ((9 * ly.co // 64 + 3) // 4 if t > 0 else 0))
+            kb_per_group = max(1, Bp * ly.h * ly.w // 64 // ly.groups)
+            w.k_splits = int(max(1, min((3 * sms + tiles - 1) // tiles, kb_per_group // 16)))
+            self._timed('wgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_weight(w, stream), 'convlstm_bwd_weight'))
+            self.launches += 5
+
+        loss_scale = 1.0 / (T * float(Bn * Cc * H * W))
+        for t in range(T - 1, -1, -1):
+            a = B.TailBwdArgs()
+            a.d3_next, a.w_d4, a.img = P(A['D3']['next'][t][0]), P(ctx['w_d4']), P(img)
+            a.recon_t, a.gacc, a.dh_d3, a.dw_d4 = out['recon'][t].data_ptr(), P(gacc), P(WB['D3']['dh_above']), P(dw_d4)
+            a.perm, a.group_img_end = P(plan.perm), P(plan.group_img_end)
+            a.loss_scale = loss_scale
+            a.B_pad, a.C, a.H, a.W = Bp, Cc, H, W
+            a.first, a.loss_kind, a.n_dec_groups, a.has_acc = int(t == 0), B.LOSS_KINDS[ctx['loss_kind']], self.Md, int(t < T - 1)
+            self._timed('tail_bwd', 0.0, lambda: B.check(L.drasic_tail_bwd(a, stream), 'tail_bwd'))
+            for name in ('D3', 'D2', 'D1'):
+                lstm_layer_bwd(by[name], t)
+            b = B.BottleneckBwdArgs()
+            b.dd0, b.h_e3 = P(WB['dd0']), P(A['E3']['next'][t][0])
+            b.z, b.codes = out['z'][t].data_ptr(), out['codes'][t].data_ptr()
+            b.w_e4, b.w_d0, b.perm, b.group_img_end = P(ctx['w_e4']), P(ctx['w_d0']), P(plan.perm), P(plan.group_img_end)
+            b.dh_e3, b.dw_e4, b.dw_d0 = P(WB['E3']['dh_above']), P(dw_e4), P(dw_d0)
+            b.B_pad, b.HW, b.Ch, b.code, b.n_enc_groups, b.n_dec_groups = Bp, hc * wc, 128, code, self.M, self.Md
+            self._timed('bottleneck_bwd', 0.0, lambda: B.check(L.drasic_bottleneck_bwd(b, stream), 'bottleneck_bwd'))
+            for name in ('E3', 'E2', 'E1'):
+                lstm_layer_bwd(by[name], t)
+            h = B.HeadBwdArgs()
+            h.du1, h.w_e0, h.b_e0, h.img = P(WB['du1']), P(ctx['w_e0']), P(ctx['b_e0']), P(img)
+            h.recon_prev = out['recon'][t - 1].data_ptr() if t > 0 else None
+            h.gacc, h.dw_e0, h.db_e0 = P(gacc), P(dw_e0), P(db_e0)
+            h.perm, h.group_img_end = P(plan.perm), P(plan.group_img_end)
+            h.B_pad, h.C, h.H, h.W = Bp, Cc, H, W
+            h.first, h.propagate, h.n_enc_groups = int(t == 0), int((not self.separate) and t > 0), self.M
+            self._timed('head_bwd', 0.0, lambda: B.check(L.drasic_head_bwd(h, stream), 'head_bwd'))
+            self.launches += 3
+
+        grads = {}
+        for ly in layers:
+            for g, pref in enumerate(ly.prefs):
+                base = '{}.{}.cell.cell.0.'.format(pref, ly.idx)
+                dwi = torch.empty((4 * ly.co, ly.cin, 3, 3), **f32)
+                dwh = torch.empty((4 * ly.co, ly.co, 3, 3), **f32)
+                B.check(L.drasic_unpack_wgrad(gw[ly.name][g].data_ptr(), ly.cin, ly.co, ly.in_order, ly.out_order,
+                                              dwi.data_ptr(), dwh.data_ptr(), stream), 'unpack_wgrad')
+                self.launches += 1
+                grads[base + 'in.cell.cell.main.weight'] = dwi
+                grads[base + 'hidden.cell.cell.main.weight'] = dwh
+        for j, pref in enumerate(ctx['enc_pref']):
+            grads[pref + '.0.cell.cell.main.weight'] = dw_e0[j].reshape(sd[pref + '.0.cell.cell.main.weight'].shape)
+            if db_e0 is not None:
+                grads[pref + '.0.cell.cell.main.bias'] = db_e0[j]
+            grads[pref + '.7.cell.cell.main.weight'] = dw_e4[j].reshape(sd[pref + '.7.cell.cell.main.weight'].shape)
+        for j, pref in enumerate(ctx['dec_pref']):
+            grads[pref + '.0.cell.cell.main.weight'] = dw_d0[j].reshape(sd[pref + '.0.cell.cell.main.weight'].shape)
+            grads[pref + '.7.cell.cell.main.weight'] = dw_d4[j].reshape(sd[pref + '.7.cell.cell.main.weight'].shape)
+        if g_loss is not None:
+            grads = {k: v * g_loss for k, v in grads.items()}
+        return grads
 
     @staticmethod
     def loss_from_acc(loss_acc, numel):

@@ -55,8 +55,9 @@ class _LoopFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, img, label, noise, *params):
-        out = model._run_engine(img, label, noise)
+        out = model._run_engine(img, label, noise, save_for_backward=True)
         ctx.model = model
+        ctx.names = [k for k, _ in model.named_parameters()]
         ctx.saved = out
         ctx.mark_non_differentiable(out['recon'], out['codes'], out['bits'])
         loss = CodecEngine.loss_from_acc(out['loss_acc'], img.numel())
@@ -65,7 +66,7 @@ class _LoopFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_recon, g_codes, g_bits):
         grads = ctx.model._engine.backward(ctx.saved, g_loss)
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads[k] for k in ctx.names)
 
 
 class CodecModel(nn.Module):
@@ -116,7 +117,7 @@ class CodecModel(nn.Module):
         if config.PARAM.get('normalization', 'none') != 'none':
             raise ValueError('Not valid normalization for the B200 path (only none)')
 
-    def _run_engine(self, img, label, noise):
+    def _run_engine(self, img, label, noise, save_for_backward=False):
         key = (config.PARAM['num_channel'], config.PARAM['code_size'], config.PARAM['num_node'],
                config.PARAM.get('precision', 'parity'))
         if self._engine_key != key:
@@ -125,7 +126,8 @@ class CodecModel(nn.Module):
             self._engine_key = key
         sd = {k: v for k, v in self.named_parameters()}
         return self._engine.forward(sd, img, label, config.PARAM['num_iter'], training=self.training,
-                                    noise=noise, loss_kind=config.PARAM['loss_fn'])
+                                    noise=noise, loss_kind=config.PARAM['loss_fn'],
+                                    save_for_backward=save_for_backward)
 
     def forward(self, input, noise=None):
         """input: {'img': [B,C,H,W] in [0,1], 'label': [B] node ids}; returns {'loss', 'img': list of T

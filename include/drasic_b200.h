@@ -70,7 +70,9 @@ typedef struct {
   const void* h_hi; const void* h_lo;   /* previous h [B_pad,H,W,Co]; unused when has_state == 0 */
   const void* w_hi; const void* w_lo;   /* packed weights, n_groups consecutive cells */
   const float* w_inv_scale;             /* [n_groups] from drasic_pack_lstm_weights */
-  float* c_state;                       /* [B_pad,H,W,Co] fp32, in place */
+  float* c_state;                       /* [B_pad,H,W,Co] fp32 new cell state (in place when c_prev is NULL) */
+  const float* c_prev;                  /* nullable: previous cell state kept in its own buffer (training) */
+  void* gates_out;                      /* nullable: activated gates [B_pad,H,W,4,Co] fp16 saved for backward */
   void* h_out_hi; void* h_out_lo;       /* new h (must not alias h_hi/h_lo) */
   void* next_hi; void* next_lo;         /* consumer copy; fp32 tensor in next_hi when next_f32 */
   const int* group_mtile_end;           /* device [n_groups]: exclusive end M-tile (128 pixels) per node */
@@ -110,6 +112,84 @@ typedef struct {
   int B_pad, C, H, W, mode, loss_kind, n_enc_groups, n_dec_groups, precise, split;
 } drasic_tail_head_args;
 int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward-through-time: what autograd executes for `output['loss'].backward()` (train_model.py:115)
+ * over the loop of models/dist_codec.py:36-65.  Gradients travel as fp32; the tensor-core GEMMs read
+ * them as fp16 {hi,lo} planes scaled by an exact per-tensor power of two (drasic_convert_scale).
+ */
+enum { DRASIC_DX_SAME = 0, DRASIC_DX_INV_DOWN = 1, DRASIC_DX_INV_UP = 2 };
+
+/* LSTM cell pointwise backward (modules/cell.py:133-139 differentiated): dgates fp32 [P,4,Co],
+ * dc carry in/out, running max|dgates| (float bits, atomicMax; clear before the launch). */
+int drasic_lstm_bwd_pointwise(const void* gates, const float* c_t, const float* c_prev,
+                              const float* dh_above, const float* dh_rec, float* dc, int has_dc,
+                              float* dgates, void* amax_bits, size_t n_pix, int Co, void* stream);
+
+/* fp32 -> fp16 {hi,lo} planes scaled by 2^k so that amax lands in [2^13, 2^14); writes 2^-k. n % 8 == 0 */
+int drasic_convert_scale(const float* src, void* hi, void* lo, const void* amax_bits,
+                         float* inv_scale_out, size_t n, void* stream);
+
+/* conv-transpose weights of one cell for the dgrad GEMM: rows = Cin+Co input channels (physical
+ * order), K = 9 taps (flipped) x 4Co gate channels.  Planes of (Cin+Co)*36*Co fp16 each. */
+int drasic_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
+                              int out_order, void* out_hi, void* out_lo, float* inv_scale_out,
+                              void* scratch4, void* stream);
+
+/* backward-data of one ConvLSTMCell step: [dX | dH_prev] = conv3x3^T(dGates) on tcgen05, the input
+ * gradient routed through the inverse pixel (un)shuffle (dx_mode) into the producer's layout. */
+typedef struct {
+  const void* dg_hi; const void* dg_lo;   /* [B_pad,H,W,4Co] fp16 planes of the gate gradients */
+  const void* w_hi; const void* w_lo;     /* from drasic_pack_dgrad_weights, n_groups consecutive cells */
+  const float* w_inv_scale;               /* [n_groups] */
+  const float* dg_inv_scale;              /* device scalar from drasic_convert_scale */
+  float* dx_out;                          /* fp32, layout per dx_mode */
+  float* dhrec_out;                       /* nullable: fp32 [B_pad,H,W,Co] gradient w.r.t. h_{t-1} */
+  const int* group_mtile_end;
+  int B_pad, H, W, Cin, Co, n_groups, dx_mode, split;
+} drasic_dgrad_args;
+int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream);
+
+/* backward-weight of one ConvLSTMCell step, accumulated (atomics) into the packed-order fp32 gradient
+ * gw [n_groups][4Co][9*(Cin+Co)]; drasic_unpack_wgrad turns it into the OIHW gradients. */
+typedef struct {
+  const void* dg_hi; const void* dg_lo;   /* [B_pad,H,W,4Co] */
+  const void* x_hi; const void* x_lo;     /* layer input planes [B_pad,H,W,Cin] of this iteration */
+  const void* h_hi; const void* h_lo;     /* h_{t-1} planes [B_pad,H,W,Co]; unused when has_h == 0 */
+  float* gw;
+  const float* dg_inv_scale;
+  const int* group_kb_end;                /* device [n_groups]: exclusive end 64-pixel block per node */
+  int B_pad, H, W, Cin, Co, n_groups, has_h, split, k_splits;
+} drasic_wgrad_args;
+int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream);
+int drasic_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,
+                        float* dw_h, void* stream);
+
+/* backward of drasic_bottleneck_fwd (straight-through quantizer, functions/quantize.py:21-22) */
+typedef struct {
+  const float* dd0; const float* h_e3; const float* z; const float* codes; const float* w_e4;
+  const float* w_d0; const int* perm; const int* group_img_end; float* dh_e3; float* dw_e4; float* dw_d0;
+  int B_pad, HW, Ch, code, n_enc_groups, n_dec_groups;
+} drasic_bottleneck_bwd_args;
+int drasic_bottleneck_bwd(const drasic_bottleneck_bwd_args* a, void* stream);
+
+/* backward of the decoder-tail half of drasic_tail_head_fwd for iteration t; maintains the running
+ * gradient w.r.t. the cumulative reconstruction (gacc) */
+typedef struct {
+  const float* d3_next; const float* w_d4; const float* img; const float* recon_t; float* gacc;
+  float* dh_d3; float* dw_d4; const int* perm; const int* group_img_end;
+  float loss_scale;
+  int B_pad, C, H, W, first, loss_kind, n_dec_groups, has_acc;
+} drasic_tail_bwd_args;
+int drasic_tail_bwd(const drasic_tail_bwd_args* a, void* stream);
+
+/* backward of the encoder-head half for iteration t */
+typedef struct {
+  const float* du1; const float* w_e0; const float* b_e0; const float* img; const float* recon_prev;
+  float* gacc; float* dw_e0; float* db_e0; const int* perm; const int* group_img_end;
+  int B_pad, C, H, W, first, propagate, n_enc_groups;
+} drasic_head_bwd_args;
+int drasic_head_bwd(const drasic_head_bwd_args* a, void* stream);
 
 /*
  * Stand-alone cells (called outside the fused loop; NCHW fp32 like the reference).

@@ -147,7 +147,88 @@ def stage_bench():
                   (prec, M, Bn, ms, wall * 1e3, Bn / ms * 1e3, 57.083e9 * Bn / ms / 1e9))
 
 
-STAGES = {'info': stage_info, 'cell_small': stage_cell_small, 'cell_shapes': stage_cell_shapes,
+def train_case(tag, num_channel, num_node, T, B_, seed, precision, separate=False, img=None, label=None, noise=None):
+    sd = O.init_state_dict(num_channel=num_channel, code_size=8, num_node=num_node, separate=separate, seed=seed)
+    if img is None:
+        g = torch.Generator().manual_seed(seed + 100)
+        img = torch.rand(B_, num_channel, 32, 32, generator=g)
+        label = torch.randint(0, num_node, (B_,), generator=g)
+        noise = torch.rand(T, B_, 8, 4, 4, generator=g)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    t0 = time.time()
+    ref = O.codec_forward(sdg, img, label, T, num_node, training=True, noise=[n for n in noise], separate=separate)
+    ref['loss'].backward()
+    t_ref = time.time() - t0
+    eng = CodecEngine(num_channel, 8, num_node, separate=separate, precision=precision)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    out = eng.forward(sdc, img.cuda(), label.cuda(), T, training=True, noise=noise.cuda(), save_for_backward=True)
+    grads = eng.backward(out)
+    torch.cuda.synchronize()
+    loss = CodecEngine.loss_from_acc(out['loss_acc'], img.numel()).item()
+    mism = int((out['codes'].cpu() != torch.stack(ref['code_pm1'])).sum())
+    print(tag, precision, 'loss %.8f ref %.8f code mismatches %d  (oracle fwd+bwd %.1fs)' % (loss, ref['loss'].item(), mism, t_ref))
+    worst = []
+    for k, v in sdg.items():
+        gr, gg = v.grad.double(), grads[k].cpu().double()
+        rel = ((gg - gr).norm() / max(gr.norm().item(), 1e-30)).item()
+        cos = (torch.dot(gg.flatten(), gr.flatten()) / max(gg.norm().item() * gr.norm().item(), 1e-30)).item()
+        worst.append((rel, cos, k, gr.norm().item(), gg.norm().item()))
+    worst.sort(reverse=True)
+    for rel, cos, k, nr, ng in worst[:10]:
+        print('   rel_err %.2e cos %.6f |ref| %.3e |ours| %.3e  %s' % (rel, cos, nr, ng, k))
+    print('   median rel_err %.2e over %d tensors' % (sorted(w[0] for w in worst)[len(worst) // 2], len(worst)))
+
+
+def stage_train_small():
+    g = np.load(os.path.join(ROOT, 'tests/golden/loop_cifar_m2.npz'))
+    for prec in ('parity', 'fast'):
+        train_case('cifar_m2 golden train', 3, 2, 4, 6, 3, prec, img=torch.from_numpy(g['img']),
+                   label=torch.from_numpy(g['label']), noise=torch.from_numpy(g['train_noise']))
+    train_case('mnist_m1 T=3', 1, 1, 3, 8, 1, 'parity')
+    train_case('sep_m2 T=3', 3, 2, 3, 10, 2, 'parity', separate=True)
+
+
+def stage_train_medium():
+    for prec in ('parity', 'fast'):
+        train_case('cifar_m8 B=32 T=8', 3, 8, 8, 32, 5, prec)
+
+
+def stage_train_bench():
+    for prec in ('parity', 'fast'):
+        for (M, Bn) in [(8, 256), (8, 1024)]:
+            sd = {k: v.cuda() for k, v in O.init_state_dict(3, 8, M, seed=0).items()}
+            eng = CodecEngine(3, 8, M, precision=prec)
+            g = torch.Generator().manual_seed(1)
+            img = torch.rand(Bn, 3, 32, 32, generator=g).cuda()
+            lab_h = torch.randint(0, M, (Bn,), generator=g)
+            lab = lab_h.cuda()
+            def step():
+                out = eng.forward(sd, img, lab, 16, training=True, label_host=lab_h.numpy(), save_for_backward=True)
+                return eng.backward(out)
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            eng.profile = []
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            prof = eng.profile_summary()
+            eng.profile = None
+            print('train bench %s M=%d B=%d: %.1f ms/step -> %.0f img/s (%.1f algorithmic TFLOP/s) mem %.1f GB' %
+                  (prec, M, Bn, ms, Bn / ms * 1e3, 3 * 57.083e9 * Bn / ms / 1e9, torch.cuda.max_memory_allocated() / 2**30))
+            grp = {}
+            for k, (n, t, fl) in prof.items():
+                kk = k.split('_')[0]
+                a = grp.setdefault(kk, [0, 0.0, 0.0]); a[0] += n; a[1] += t; a[2] += fl
+            print('   ', {k: '%d launches %.1f ms %.0f TF/s' % (v[0], v[1], v[2] / max(v[1], 1e-9) / 1e9) for k, v in grp.items()})
+            del eng
+            torch.cuda.empty_cache()
+
+
+STAGES = {'info': stage_info, 'train_small': stage_train_small, 'train_medium': stage_train_medium,
+          'train_bench': stage_train_bench, 'cell_small': stage_cell_small, 'cell_shapes': stage_cell_shapes,
           'loop_small': stage_loop_small, 'loop_medium': stage_loop_medium, 'bench': stage_bench}
 
 if __name__ == '__main__':
