@@ -86,6 +86,11 @@ class ClockSampler(object):
                 'samples': len(sm)}
 
 
+def workload_name(mode):
+    return ('cifar10_32x32_m8_random_subsets_T16_train_step_fwd_bptt_adam' if mode == 'train'
+            else 'cifar10_32x32_m8_random_subsets_T16_eval_encode_decode')
+
+
 def synth_batch(batch, seed):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -104,33 +109,45 @@ def run_reference(args):
     from oracle import drasic_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    train = args.mode == 'train'
     sd = O.init_state_dict(CHANNELS, 8, M_NODES, seed=0)
+    if train:
+        sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+
+    def step(img, label, n_iter=T_ITER):
+        if train:                                                    # forward + full BPTT, like train_model.py:113-115
+            for v in sd.values():
+                v.grad = None
+            out = O.codec_forward(sd, img, label, n_iter, M_NODES, training=True)
+            out['loss'].backward()
+        else:
+            with torch.no_grad():
+                O.codec_forward(sd, img, label, n_iter, M_NODES)
     # size the per-step sample so the whole run stays within a few minutes
     img, label = synth_batch(8, 1)
-    with torch.no_grad():
-        O.codec_forward(sd, img, label, 2, M_NODES)                 # warm the thread pool / oneDNN primitives
-        t0 = time.perf_counter()
-        O.codec_forward(sd, img, label, T_ITER, M_NODES)
-        t8 = time.perf_counter() - t0
+    step(img, label, 2)                                              # warm the thread pool / oneDNN primitives
+    t0 = time.perf_counter()
+    step(img, label)
+    t8 = time.perf_counter() - t0
     budget = 150.0 / max(1, args.steps + args.warmup)
     sample = int(max(8, min(64, 8 * budget / max(t8, 1e-3))) // 8 * 8)
     img, label = synth_batch(sample, 2)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            O.codec_forward(sd, img, label, T_ITER, M_NODES)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.codec_forward(sd, img, label, T_ITER, M_NODES)
-        dt = (time.perf_counter() - t0) / args.steps
+    for _ in range(args.warmup):
+        step(img, label)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(img, label)
+    dt = (time.perf_counter() - t0) / args.steps
     v = sample / dt
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'cifar10_32x32_m8_random_subsets_T16_eval_encode_decode', 'sample_batch': sample,
+        'config': {'workload': workload_name(args.mode), 'sample_batch': sample,
                    'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': 'oracle/drasic_oracle.py codec_forward, eval, B={} M=8 T=16 per step'.format(sample)},
+                         'sample': 'oracle/drasic_oracle.py codec_forward{}, B={} M=8 T=16 per step'.format(
+                             ' + backward (stochastic binarizer, full BPTT)' if train else ' (eval)', sample)},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -152,7 +169,8 @@ def run_ours(args):
     from engine.codec import CodecEngine
     import config
     config.init()
-    config.PARAM.update(device='cuda', data_name='CIFAR10', precision=args.precision, pack_mode='reference')
+    config.PARAM.update(device='cuda', data_name='CIFAR10', precision=args.precision, pack_mode='reference',
+                        grad_precision=args.grad_precision)
     config.PARAM['control'] = {'normalization': 'none', 'activation': 'tanh', 'num_iter': str(T_ITER),
                                'code_size': '8', 'num_node': str(M_NODES)}
     import utils
@@ -160,57 +178,72 @@ def run_ours(args):
     import models
     torch.manual_seed(0)
     model = models.dist_codec().to(dev)
-    model.train(False)
-    sd = {k: v for k, v in model.named_parameters()}
+    train = args.mode == 'train'
+    model.train(train)
     B = args.batch
     # each rank codes its own shard of the global batch (samples are independent: no data-path collective)
     img_h, label_h = synth_batch(B, 1000 + rank)
     img, label = img_h.to(dev), label_h.to(dev)
-    label_np = label_h.numpy()
-    eng = CodecEngine(CHANNELS, 8, M_NODES, precision=args.precision)
+    from engine.dist import allreduce_gradients
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True) if train else None    # train_model.py:161
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput
-    with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            eng.forward(sd, img, label, T_ITER, label_host=label_np)
-        barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            eng.forward(sd, img, label, T_ITER, label_host=label_np)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1) / args.steps
-        launches = eng.launches
-        clocks = sampler.stop() if sampler else None
+    def step(inp):
+        """one pass of the hot path through the public API"""
+        if train:
+            opt.zero_grad(set_to_none=True)
+            out = model(inp)                                          # train_model.py:113
+            out['loss'].backward()                                    # :115  (backward-through-time kernels)
+            allreduce_gradients(params, B, world * B)                 # replaces DataParallel's reduce (:60)
+            opt.step()                                                # :116
+        else:
+            with torch.no_grad():
+                out = model(inp)
+        return out
 
-        # ---- per-kernel timing on the launching stream (separate pass, events around every launch)
-        eng.profile = []
-        for _ in range(2):
-            eng.forward(sd, img, label, T_ITER, label_host=label_np)
-        torch.cuda.synchronize()
-        prof = eng.profile_summary()
-        eng.profile = None
+    resident = {'img': img, 'label': label}
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(resident)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    eng = model._engine
+    launches = eng.launches
+    clocks = sampler.stop() if sampler else None
 
-        # ---- end to end through the public API with host buffers
-        pin_img, pin_label = img_h.pin_memory(), label_h.pin_memory()
-        def e2e_step():
-            out = model({'img': pin_img.to(dev, non_blocking=True), 'label': pin_label.to(dev, non_blocking=True)})
-            return out['loss'].item(), out['code'][-1].nbytes       # D2H: loss scalar + all codes (inside forward)
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.steps
+    # ---- per-kernel timing on the launching stream (separate pass, CUDA events around every launch)
+    eng.profile = []
+    for _ in range(2):
+        step(resident)
+    torch.cuda.synchronize()
+    prof = eng.profile_summary()
+    eng.profile = None
+
+    # ---- end to end through the public API with host buffers (H2D of inputs, D2H of loss + codes)
+    pin_img, pin_label = img_h.pin_memory(), label_h.pin_memory()
+
+    def e2e_step():
+        out = step({'img': pin_img.to(dev, non_blocking=True), 'label': pin_label.to(dev, non_blocking=True)})
+        return out['loss'].item(), out['code'][-1].nbytes
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
 
     t_ms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
@@ -221,51 +254,66 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     sust, burst, hbm, how = measured_peaks()
-    gate = [(k, v) for k, v in prof.items() if k.startswith('gates_')]
+    gate = [(k, v) for k, v in prof.items() if k.split('_')[0] in ('gates', 'dgrad', 'wgrad')]
     g_n = sum(v[0] for _, v in gate)
     g_ms = sum(v[1] for _, v in gate)
     g_fl = sum(v[2] for _, v in gate)
     all_ms = sum(v[1] for v in prof.values())
     achieved = g_fl / (g_ms * 1e-3) / 1e12
     mma_per_mac = 3 if args.precision == 'parity' else 1
+    flop_per_img = FLOP_PER_IMG_FWD * (3 if train else 1)
+    sd = {k: v for k, v in model.named_parameters()}
     line = {
         'metric': METRIC, 'value': world * B / ms * 1e3, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None,
-        'dtype': 'f16x2-split (fp32-grade, fp32 accumulate)' if args.precision == 'parity' else 'f16 (fp32 accumulate)',
+        'dtype': ('f16x2-split forward (fp32-grade, fp32 accumulate)' if args.precision == 'parity' else 'f16 forward (fp32 accumulate)')
+                 + (', f16 backward GEMMs with exact per-tensor power-of-two scaling, fp32 gradients' if train else ''),
         'data': 'synthetic',
-        'config': {'workload': 'cifar10_32x32_m8_random_subsets_T16_eval_encode_decode', 'batch_per_gpu': B,
+        'config': {'workload': workload_name(args.mode), 'batch_per_gpu': B,
                    'global_batch': world * B, 'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8,
-                   'precision': args.precision, 'parallelism': 'batch-sharded replicas x{}'.format(world),
+                   'precision': args.precision,
+                   'parallelism': ('dp{}: batch sharded, one NCCL all-reduce of gradients per step'.format(world) if train
+                                   else 'batch-sharded replicas x{} (no collective)'.format(world)),
                    'l2': 'per-step working set (activations+state, ~1 MB/image) exceeds the 126 MB L2'},
         'e2e': {'value': world * B / e2e_ms * 1e3, 'unit': 'images/s',
                 'h2d_bytes_per_step': B * CHANNELS * 32 * 32 * 4 + B * 8,
-                'd2h_bytes_per_step': T_ITER * B * 128 * 4 + 4,
-                'api': 'models.dist_codec() Model.forward on pinned host img/label; loss.item() and packed codes read back'},
+                'd2h_bytes_per_step': T_ITER * B * 128 * 4 + 4 + B * 8,
+                'api': 'models.dist_codec() Model.forward (+ loss.backward(), Adam step when training) on pinned host '
+                       'img/label; loss.item() and the emitted codes read back'},
         'gpu_launches': launches * args.steps,
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'convlstm_gates_kernel (6 layers x 16 iterations)',
+        'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel<gates> + conv_gemm_kernel<dgrad> + wgrad_kernel (6 layers x 16 iterations)'
+                     if train else 'conv_gemm_kernel<gates> (6 layers x 16 iterations)',
                      'achieved': achieved, 'peak': sust, 'unit': 'TFLOP/s', 'frac': achieved / sust,
                      'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained ({}); burst {}'.format(how, burst),
                      'traffic': None, 'launches': g_n, 'avg_launch_ms': g_ms / max(g_n, 1),
                      'share_of_step': g_ms / all_ms, 'tensor_mma_per_algorithmic_mac': mma_per_mac,
-                     'tensor_issue_tflops': achieved * mma_per_mac, 'tensor_issue_frac': achieved * mma_per_mac / sust},
+                     'per_kind_tflops': {kk: sum(v[2] for k, v in gate if k.startswith(kk)) / max(1e-9, sum(v[1] for k, v in gate if k.startswith(kk))) / 1e9
+                                         for kk in ('gates', 'dgrad', 'wgrad') if any(k.startswith(kk) for k, _ in gate)},
+                     'forward_mma_per_algorithmic_mac': mma_per_mac},
         'kernels_ms_per_step': {k: v[1] / 2 for k, v in sorted(prof.items())},
-        'algorithmic_tflops': world * B / ms * 1e3 * FLOP_PER_IMG_FWD / 1e12,
+        'algorithmic_tflops': world * B / ms * 1e3 * flop_per_img / 1e12,
     }
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        sdc = {k: v.detach().cpu() for k, v in sd.items()}
-        ci, cl = synth_batch(256, 7)
+        nb = 32 if train else 256
+        sdc = {k: v.detach().cpu().clone().requires_grad_(train) for k, v in sd.items()}
+        ci, cl = synth_batch(nb, 7)
         with torch.no_grad():
             O.codec_forward(sdc, ci[:8], cl[:8], 2, M_NODES)
-            t0 = time.perf_counter()
-            O.codec_forward(sdc, ci, cl, T_ITER, M_NODES)
-            dt = time.perf_counter() - t0
-        line['cpu_baseline'] = {'value': 256 / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                'sample': 'oracle codec_forward eval, B=256 M=8 T=16, one pass ({:.1f} s)'.format(dt)}
+        t0 = time.perf_counter()
+        if train:
+            O.codec_forward(sdc, ci, cl, T_ITER, M_NODES, training=True)['loss'].backward()
+        else:
+            with torch.no_grad():
+                O.codec_forward(sdc, ci, cl, T_ITER, M_NODES)
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': nb / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                'sample': 'oracle codec_forward{} B={} M=8 T=16, one pass ({:.1f} s)'.format(
+                                    ' + backward (BPTT)' if train else ' eval', nb, dt)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -279,6 +327,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='images per GPU per step')
     ap.add_argument('--precision', default='parity', choices=['parity', 'fast'])
+    ap.add_argument('--mode', default='train', choices=['train', 'eval'],
+                    help='train: forward + backward-through-time + all-reduce + Adam step (BASELINE configs[1]); '
+                         'eval: encode+decode only')
+    ap.add_argument('--grad-precision', default='fp16', choices=['fp16', 'parity'])
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

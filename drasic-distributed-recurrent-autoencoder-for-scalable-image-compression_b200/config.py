@@ -16,4 +16,4 @@ def init():
         data_size=dict(train=0, test=0), device='cuda', num_epochs=200, save_mode=0, world_size=1,
         metric_names=dict(train=['Loss', 'BPP', 'PSNR'], test=['Loss', 'BPP', 'PSNR']),
         init_seed=0, num_Experiments=1, log_interval=0.25, log_overwrite=False, loss_fn='mae', resume_mode=0,
-        precision='parity', pack_mode='reference')
+        precision='parity', grad_precision='fp16', pack_mode='reference')

@@ -34,17 +34,24 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdParams p) {
     const size_t e0 = v * 8;
     const size_t pix = e0 / Co;
     const int ch = static_cast<int>(e0 - pix * Co);
-    const __half* gp = p.gates + pix * (4 * Co) + ch;
-    alignas(16) __half gi[8], gf[8], gg[8], go[8];
-    *reinterpret_cast<uint4*>(gi) = *reinterpret_cast<const uint4*>(gp);
-    *reinterpret_cast<uint4*>(gf) = *reinterpret_cast<const uint4*>(gp + Co);
-    *reinterpret_cast<uint4*>(gg) = *reinterpret_cast<const uint4*>(gp + 2 * Co);
-    *reinterpret_cast<uint4*>(go) = *reinterpret_cast<const uint4*>(gp + 3 * Co);
-    float ct[8], cp[8], dh[8], dcv[8];
     auto ld8 = [](const float* src, float (&dst)[8]) {
       const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
       dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
     };
+    float gi[8], gf[8], gg[8], go[8];
+    if (p.gates_f32) {
+      const float* gp = reinterpret_cast<const float*>(p.gates) + pix * (4 * Co) + ch;
+      ld8(gp, gi); ld8(gp + Co, gf); ld8(gp + 2 * Co, gg); ld8(gp + 3 * Co, go);
+    } else {
+      const __half* gp = reinterpret_cast<const __half*>(p.gates) + pix * (4 * Co) + ch;
+      auto ldh = [](const __half* src, float (&dst)[8]) {
+        alignas(16) __half t[8];
+        *reinterpret_cast<uint4*>(t) = *reinterpret_cast<const uint4*>(src);
+        for (int i = 0; i < 8; ++i) dst[i] = __half2float(t[i]);
+      };
+      ldh(gp, gi); ldh(gp + Co, gf); ldh(gp + 2 * Co, gg); ldh(gp + 3 * Co, go);
+    }
+    float ct[8], cp[8], dh[8], dcv[8];
     ld8(p.c_t + e0, ct);
     if (p.c_prev) ld8(p.c_prev + e0, cp);
     else for (int i = 0; i < 8; ++i) cp[i] = 0.0f;
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdParams p) {
     float di[8], df[8], dg[8], dob[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float ig = __half2float(gi[i]), fg = __half2float(gf[i]), cg = __half2float(gg[i]), og = __half2float(go[i]);
+      const float ig = gi[i], fg = gf[i], cg = gg[i], og = go[i];
       const float tc = tanhf(ct[i]);
       const float dct = fmaf(dh[i] * og, 1.0f - tc * tc, dcv[i]);
       dob[i] = dh[i] * tc * og * (1.0f - og);

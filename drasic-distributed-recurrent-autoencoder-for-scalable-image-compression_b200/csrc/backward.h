@@ -8,7 +8,8 @@ namespace drasic {
 
 // LSTM cell pointwise backward (modules/cell.py:133-139 differentiated), one launch per (layer, t)
 struct LstmBwdParams {
-  const __half* gates;     // [P, 4, Co] activated gates saved by the forward
+  const void* gates;       // [P, 4, Co] activated gates saved by the forward (fp16, or fp32 when gates_f32)
+  int gates_f32;
   const float* c_t;        // [P, Co]
   const float* c_prev;     // nullable (t == 0)
   const float* dh_above;   // [P, Co] gradient from the consumer of h_t

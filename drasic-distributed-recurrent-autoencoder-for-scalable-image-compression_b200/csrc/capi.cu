@@ -164,7 +164,8 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * 4 * Co, K, a->block_n))) return rc;
   p.c_state = a->c_state;
   p.c_prev = a->c_prev;
-  p.gates_out = static_cast<__half*>(a->gates_out);
+  p.gates_out = a->gates_out;
+  p.gates_f32 = a->gates_f32;
   p.w_group_rows = 4 * Co;
   p.h_out[0] = static_cast<__half*>(a->h_out_hi);
   p.h_out[1] = static_cast<__half*>(a->h_out_lo);
@@ -247,13 +248,13 @@ static int pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
   return 0;
 }
 
-int drasic_lstm_bwd_pointwise(const void* gates, const float* c_t, const float* c_prev,
+int drasic_lstm_bwd_pointwise(const void* gates, int gates_f32, const float* c_t, const float* c_prev,
                               const float* dh_above, const float* dh_rec, float* dc, int has_dc,
                               float* dgates, void* amax_bits, size_t n_pix, int Co, void* stream) {
   if (!gates || !c_t || !dh_above || !dc || !dgates || !amax_bits || Co % 8 || n_pix == 0)
     return fail(DRASIC_ERR_INVALID, "lstm_bwd_pointwise: bad argument");
   drasic::LstmBwdParams p;
-  p.gates = static_cast<const __half*>(gates); p.c_t = c_t; p.c_prev = c_prev; p.dh_above = dh_above;
+  p.gates = gates; p.gates_f32 = gates_f32; p.c_t = c_t; p.c_prev = c_prev; p.dh_above = dh_above;
   p.dh_rec = dh_rec; p.dc = dc; p.has_dc = has_dc; p.dgates = dgates;
   p.amax_bits = static_cast<unsigned int*>(amax_bits); p.n_pix = n_pix; p.Co = Co;
   return cuda_fail(drasic::launch_lstm_bwd(p, static_cast<cudaStream_t>(stream)), "lstm_bwd_pointwise launch");

@@ -163,11 +163,19 @@ __device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_r
     }
     store_f32x16(p.c_state + pix * Co + p0, cv);
     if (p.gates_out) {  // training: keep the activated gates for backward, [pix][gate][Co]
-      __half* gp = p.gates_out + pix * (4 * Co) + p0;
-      store_half16(gp, gi);
-      store_half16(gp + Co, gf);
-      store_half16(gp + 2 * Co, gg);
-      store_half16(gp + 3 * Co, go);
+      if (p.gates_f32) {
+        float* gp = reinterpret_cast<float*>(p.gates_out) + pix * (4 * Co) + p0;
+        store_f32x16(gp, gi);
+        store_f32x16(gp + Co, gf);
+        store_f32x16(gp + 2 * Co, gg);
+        store_f32x16(gp + 3 * Co, go);
+      } else {
+        __half* gp = reinterpret_cast<__half*>(p.gates_out) + pix * (4 * Co) + p0;
+        store_half16(gp, gi);
+        store_half16(gp + Co, gf);
+        store_half16(gp + 2 * Co, gg);
+        store_half16(gp + 3 * Co, go);
+      }
     }
     // consumer copy (fused PixelShuffleCell)
     size_t noff = 0;

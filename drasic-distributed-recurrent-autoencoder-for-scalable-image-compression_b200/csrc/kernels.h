@@ -41,7 +41,8 @@ struct GateParams {
   CUtensorMap tm_w[2];  // packed gate weights [groups*4Co, 9Cin+9Co] fp16 {hi, lo}
   float* c_state;       // [B,H,W,Co] fp32 new cell state (in place when c_prev == nullptr)
   const float* c_prev;  // nullable: previous cell state in a separate buffer (training keeps every c_t)
-  __half* gates_out;    // nullable: post-activation gates [B,H,W,4,Co] fp16, saved for backward
+  void* gates_out;      // nullable: post-activation gates [B,H,W,4,Co] (fp16, or fp32 when gates_f32), saved for backward
+  int gates_f32;
   __half* h_out[2];     // new hidden state (own layout), {hi, lo}
   void* next[2];        // consumer copy of h: fp16 {hi, lo} or fp32 (next[0])
   const float* w_inv_scale;  // [n_groups] power of two: 1 / (ACT_SCALE * weight scale)

@@ -20,7 +20,7 @@ class ConvLSTMArgs(C.Structure):
                                   'c_prev', 'gates_out', 'h_out_hi', 'h_out_lo', 'next_hi', 'next_lo',
                                   'group_mtile_end')] + \
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'has_state', 'next_mode',
-                                  'next_f32', 'split', 'precise', 'block_n')]
+                                  'next_f32', 'split', 'precise', 'block_n', 'gates_f32')]
 
 
 class BottleneckArgs(C.Structure):
@@ -108,7 +108,7 @@ def lib():
     L.drasic_quantize_fwd.restype = C.c_int
     L.drasic_quantize_fwd.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.drasic_lstm_bwd_pointwise.restype = C.c_int
-    L.drasic_lstm_bwd_pointwise.argtypes = [vp, vp, vp, vp, vp, vp, ip, vp, vp, C.c_size_t, ip, vp]
+    L.drasic_lstm_bwd_pointwise.argtypes = [vp, ip, vp, vp, vp, vp, vp, ip, vp, vp, C.c_size_t, ip, vp]
     L.drasic_convert_scale.restype = C.c_int
     L.drasic_convert_scale.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, vp]
     L.drasic_pack_dgrad_weights.restype = C.c_int

@@ -72,9 +72,15 @@ class CodecEngine(object):
     encoders and decoders).  `precision`: 'parity' = fp16 hi+lo operands with IEEE transcendental
     functions (fp32-grade, bit-exact codes); 'fast' = single fp16 operands with tanh.approx."""
 
-    def __init__(self, num_channel, code_size, num_node, separate=False, precision='parity'):
+    def __init__(self, num_channel, code_size, num_node, separate=False, precision='parity', grad_precision='fp16'):
+        """grad_precision: 'fp16' = backward GEMMs on single fp16 operands, gates saved in fp16 (gradients
+        within ~1e-3 relative of the fp32 reference); 'parity' = split-fp16 backward GEMMs and fp32 saved
+        gates (fp32-grade gradients; needs precision='parity')."""
         if precision not in ('parity', 'fast'):
             raise ValueError('Not valid precision')
+        if grad_precision not in ('fp16', 'parity') or (grad_precision == 'parity' and precision != 'parity'):
+            raise ValueError('Not valid grad_precision')
+        self.gsplit = 1 if grad_precision == 'parity' else 0
         self.C, self.code, self.M, self.separate = num_channel, code_size, num_node, separate
         self.split = 1 if precision == 'parity' else 0
         self.precise = self.split
@@ -141,7 +147,7 @@ class CodecEngine(object):
             L = {}
             L['h'] = planes(T if T else 2, B_pad, h, w, co)
             L['c'] = [torch.zeros((B_pad, h, w, co), **f32) for _ in range(n_t)]
-            L['gates'] = [torch.zeros((B_pad, h, w, 4, co), **f16) for _ in range(T)]
+            L['gates'] = [torch.zeros((B_pad, h, w, 4, co), **(f32 if self.gsplit else f16)) for _ in range(T)]
             if nmode == B.NEXT_DOWN:
                 nshape = (B_pad, h // 2, w // 2, 4 * co)
             elif nmode == B.NEXT_UP:
@@ -290,6 +296,7 @@ class CodecEngine(object):
                 a.c_state = P(Lb['c'][t])
                 a.c_prev = P(Lb['c'][t - 1]) if t > 0 else None
                 a.gates_out = P(Lb['gates'][t])
+                a.gates_f32 = self.gsplit
                 nxt = Lb['next'][t]
             else:
                 cur, prv = Lb['h'][t & 1], Lb['h'][(t & 1) ^ 1]
@@ -392,7 +399,7 @@ class CodecEngine(object):
             W_[ly.name] = dict(dh_above=torch.zeros(n, **f32), dh_rec=torch.zeros(n, **f32), dc=torch.zeros(n, **f32),
                                dgates=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f32),
                                dg_hi=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16),
-                               dg_lo=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16) if self.split else None,
+                               dg_lo=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16) if self.gsplit else None,
                                amax=torch.zeros((1,), dtype=torch.int32, device=dev),
                                inv=torch.ones((1,), **f32))
         W_['du1'] = torch.zeros((Bp, H // 2, W // 2, 128), **f32)
@@ -446,7 +453,7 @@ class CodecEngine(object):
             Lb, wb = A[ly.name], WB[ly.name]
             n_pix = Bp * ly.h * ly.w
             wb['amax'].zero_()
-            B.check(L.drasic_lstm_bwd_pointwise(P(Lb['gates'][t]), P(Lb['c'][t]), P(Lb['c'][t - 1]) if t > 0 else None,
+            B.check(L.drasic_lstm_bwd_pointwise(P(Lb['gates'][t]), self.gsplit, P(Lb['c'][t]), P(Lb['c'][t - 1]) if t > 0 else None,
                                                 P(wb['dh_above']), P(wb['dh_rec']) if t < T - 1 else None, P(wb['dc']),
                                                 1 if t < T - 1 else 0, P(wb['dgates']), P(wb['amax']), n_pix, ly.co,
                                                 stream), 'lstm_bwd_pointwise')
@@ -460,7 +467,7 @@ class CodecEngine(object):
             a.dhrec_out = P(wb['dh_rec']) if t > 0 else None
             a.group_mtile_end = P(ly.mtile_end)
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
-            a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.split
+            a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.gsplit
             fl = 2.0 * Bn * ly.h * ly.w * 36 * ly.co * (ly.cin + (ly.co if t > 0 else 0))
             self._timed('dgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_data(a, stream), 'convlstm_bwd_data'))
             w = B.WgradArgs()
@@ -471,7 +478,7 @@ class CodecEngine(object):
             w.gw, w.dg_inv_scale = P(gw[ly.name]), P(wb['inv'])
             w.group_kb_end = P(group_kb_end(ly)) if ly.groups > 1 else None
             w.B_pad, w.H, w.W, w.Cin, w.Co = Bp, ly.h, ly.w, ly.cin, ly.co
-            w.n_groups, w.has_h, w.split = ly.groups, 1 if t > 0 else 0, self.split
+            w.n_groups, w.has_h, w.split = ly.groups, 1 if t > 0 else 0, self.gsplit
             tiles = ly.groups * (4 * ly.co // 128) * ((9 * ly.cin // 64 + 3) // 4 + ((9 * ly.co // 64 + 3) // 4 if t > 0 else 0))
             kb_per_group = max(1, Bp * ly.h * ly.w // 64 // ly.groups)
             w.k_splits = int(max(1, min((3 * sms + tiles - 1) // tiles, kb_per_group // 16)))
@@ -523,7 +530,7 @@ class CodecEngine(object):
         for j, pref in enumerate(ctx['enc_pref']):
             grads[pref + '.0.cell.cell.main.weight'] = dw_e0[j].reshape(sd[pref + '.0.cell.cell.main.weight'].shape)
             if db_e0 is not None:
-                grads[pref + '.0.cell.cell.main.bias'] = db_e0[j]
+                grads[pref + '.0.cell.cell.main.bias'] = db_e0[j].reshape(sd[pref + '.0.cell.cell.main.bias'].shape)
             grads[pref + '.7.cell.cell.main.weight'] = dw_e4[j].reshape(sd[pref + '.7.cell.cell.main.weight'].shape)
         for j, pref in enumerate(ctx['dec_pref']):
             grads[pref + '.0.cell.cell.main.weight'] = dw_d0[j].reshape(sd[pref + '.0.cell.cell.main.weight'].shape)

@@ -119,10 +119,11 @@ class CodecModel(nn.Module):
 
     def _run_engine(self, img, label, noise, save_for_backward=False):
         key = (config.PARAM['num_channel'], config.PARAM['code_size'], config.PARAM['num_node'],
-               config.PARAM.get('precision', 'parity'))
+               config.PARAM.get('precision', 'parity'), config.PARAM.get('grad_precision', 'fp16'))
         if self._engine_key != key:
             self._check_architecture()
-            self._engine = CodecEngine(key[0], key[1], key[2], separate=self.separate, precision=key[3])
+            self._engine = CodecEngine(key[0], key[1], key[2], separate=self.separate, precision=key[3],
+                                       grad_precision=key[4])
             self._engine_key = key
         sd = {k: v for k, v in self.named_parameters()}
         return self._engine.forward(sd, img, label, config.PARAM['num_iter'], training=self.training,

@@ -72,7 +72,7 @@ typedef struct {
   const float* w_inv_scale;             /* [n_groups] from drasic_pack_lstm_weights */
   float* c_state;                       /* [B_pad,H,W,Co] fp32 new cell state (in place when c_prev is NULL) */
   const float* c_prev;                  /* nullable: previous cell state kept in its own buffer (training) */
-  void* gates_out;                      /* nullable: activated gates [B_pad,H,W,4,Co] fp16 saved for backward */
+  void* gates_out;                      /* nullable: activated gates [B_pad,H,W,4,Co] saved for backward (fp16; fp32 when gates_f32) */
   void* h_out_hi; void* h_out_lo;       /* new h (must not alias h_hi/h_lo) */
   void* next_hi; void* next_lo;         /* consumer copy; fp32 tensor in next_hi when next_f32 */
   const int* group_mtile_end;           /* device [n_groups]: exclusive end M-tile (128 pixels) per node */
@@ -83,6 +83,7 @@ typedef struct {
   int split;                            /* 1: fp16 hi+lo operands (fp32-grade), 0: fp16 only */
   int precise;                          /* 1: IEEE exp/div/tanh, 0: tanh.approx */
   int block_n;                          /* N tile: 256, 128 or 64 (must match the packing) */
+  int gates_f32;                        /* dtype of gates_out */
 } drasic_convlstm_args;
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream);
 
@@ -122,7 +123,7 @@ enum { DRASIC_DX_SAME = 0, DRASIC_DX_INV_DOWN = 1, DRASIC_DX_INV_UP = 2 };
 
 /* LSTM cell pointwise backward (modules/cell.py:133-139 differentiated): dgates fp32 [P,4,Co],
  * dc carry in/out, running max|dgates| (float bits, atomicMax; clear before the launch). */
-int drasic_lstm_bwd_pointwise(const void* gates, const float* c_t, const float* c_prev,
+int drasic_lstm_bwd_pointwise(const void* gates, int gates_f32, const float* c_t, const float* c_prev,
                               const float* dh_above, const float* dh_rec, float* dc, int has_dc,
                               float* dgates, void* amax_bits, size_t n_pix, int Co, void* stream);
 

@@ -1,0 +1,130 @@
+"""GPU parity of the training step (forward with the stochastic binarizer + backward-through-time)
+through the reference-facing API: `output = model(input); output['loss'].backward()`
+(train_model.py:113-115), against gradients the reference produced (golden fixture) and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_model
+from oracle import drasic_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# stated tolerances: relative L2 error of every parameter's gradient against the fp32 reference
+# (fp16 backward: fp16 operands / saved gates, errors compound over 6 layers x T iterations of BPTT and
+# do not average out for a node that saw only a handful of samples; median over tensors is ~6e-4)
+GRAD_TOL = {'fp16': 1e-2, 'parity': 5e-4}
+GRAD_TOL_MEDIAN = 2e-3
+
+
+def rel_err(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / max(b.norm().item(), 1e-30)).item()
+
+
+def train_step(model, img, label, noise):
+    model.train(True)
+    model.zero_grad()
+    out = model({'img': img.cuda(), 'label': label.cuda()}, noise=noise.cuda())
+    out['loss'].backward()
+    return out
+
+
+@pytest.mark.parametrize('precision,grad_precision', [('parity', 'fp16'), ('parity', 'parity'), ('fast', 'fp16')])
+def test_training_step_matches_reference_gradients(golden_dir, precision, grad_precision):
+    import config
+    g = np.load(os.path.join(golden_dir, 'loop_cifar_m2.npz'))
+    m = build_model('dist_codec', 'CIFAR10', 2, 4, seed=3, precision=precision)
+    config.PARAM['grad_precision'] = grad_precision
+    img, label = torch.from_numpy(g['img']), torch.from_numpy(g['label'])
+    out = train_step(m, img, label, torch.from_numpy(g['train_noise']))
+    assert out['loss'].requires_grad is False or out['loss'].grad_fn is not None
+    if precision == 'parity':
+        assert np.array_equal(out['code_pm1'].cpu().numpy().astype(np.int8), g['train_codes'])
+    assert abs(out['loss'].item() - float(g['train_loss'])) < 1e-5
+    tol = GRAD_TOL[grad_precision]
+    norms = {str(k): v for k, v in zip(g['grad_keys'], g['grad_norms'])}
+    named = dict(m.named_parameters())
+    assert set(named) == set(norms)
+    for k, p in named.items():
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        assert abs(p.grad.double().norm().item() - norms[k]) <= tol * norms[k], k
+    full = {'g_e0_w': 'model.encoder.0.0.cell.cell.main.weight', 'g_e0_b': 'model.encoder.1.0.cell.cell.main.bias',
+            'g_e4_w': 'model.encoder.1.7.cell.cell.main.weight', 'g_d0_w': 'model.decoder.0.cell.cell.main.weight',
+            'g_d4_w': 'model.decoder.7.cell.cell.main.weight'}
+    for short, k in full.items():
+        assert rel_err(named[k].grad.cpu(), torch.from_numpy(g[short])) < tol, k
+    assert rel_err(named['model.decoder.5.cell.cell.0.in.cell.cell.main.weight'].grad[:8, :8].cpu(),
+                   torch.from_numpy(g['g_d3_in_slice'])) < tol
+    assert rel_err(named['model.encoder.0.2.cell.cell.0.hidden.cell.cell.main.weight'].grad[:8, :8].cpu(),
+                   torch.from_numpy(g['g_e1_hidden_slice'])) < tol
+
+
+@pytest.mark.parametrize('name,M,B,T,separate', [('dist_codec', 8, 27, 5, False), ('sep_codec', 3, 13, 3, True),
+                                                  ('dist_codec', 1, 9, 16, False)])
+def test_training_step_vs_oracle_autograd(name, M, B, T, separate):
+    """ragged node groups (one node empty), per-source decoders (sep: detached residual), T=16 single source"""
+    data = 'MNIST' if M == 1 else 'CIFAR10'
+    C = 1 if M == 1 else 3
+    m = build_model(name, data, M, T, seed=11)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(12)
+    img = torch.rand(B, C, 32, 32, generator=g)
+    label = torch.randint(0, M, (B,), generator=g)
+    if M > 2:
+        label[label == 1] = 0                                       # node 1 sees no data in this batch
+    noise = torch.rand(T, B, 8, 4, 4, generator=g)
+    ref = O.codec_forward(sd, img, label, T, M, training=True, noise=[n for n in noise], separate=separate)
+    ref['loss'].backward()
+    out = train_step(m, img, label, noise)
+    assert np.array_equal(out['code_pm1'].cpu().numpy(), torch.stack(ref['code_pm1']).numpy())
+    assert abs(out['loss'].item() - ref['loss'].item()) < 1e-5
+    errs = []
+    for k, p in m.named_parameters():
+        if sd[k].grad is None:                                      # parameters of the empty node
+            assert p.grad is not None and float(p.grad.abs().max()) == 0.0, k
+        else:
+            errs.append(rel_err(p.grad.cpu(), sd[k].grad))
+            assert errs[-1] < GRAD_TOL['fp16'], k
+    assert sorted(errs)[len(errs) // 2] < GRAD_TOL_MEDIAN
+
+
+def test_optimizer_steps_reduce_loss_and_repack_weights():
+    """Adam updates the fp32 master parameters in place (train_model.py:116); the packed fp16 weight
+    planes are a cache keyed on the parameter version and must follow."""
+    m = build_model('dist_codec', 'CIFAR10', 2, 4, seed=5)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(6)
+    img = torch.rand(16, 3, 32, 32, generator=g)
+    label = torch.randint(0, 2, (16,), generator=g)
+    losses = []
+    for it in range(6):
+        m.train(True)
+        opt.zero_grad()
+        out = m({'img': img.cuda(), 'label': label.cuda()})
+        out['loss'].backward()
+        opt.step()
+        losses.append(out['loss'].item())
+    assert losses[-1] < losses[0] - 1e-3, losses
+    # eval after training equals the oracle on the *updated* weights (cache was refreshed)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.codec_forward(sd, img, label, 4, 2)
+    m.train(False)
+    with torch.no_grad():
+        out = m({'img': img.cuda(), 'label': label.cuda()})
+    assert abs(out['loss'].item() - ref['loss'].item()) < 1e-5
+    assert (out['code_pm1'].cpu() != torch.stack(ref['code_pm1'])).float().mean().item() < 1e-3
+
+
+def test_backward_requires_matching_forward():
+    m = build_model('dist_codec', 'MNIST', 1, 2, seed=0)
+    inp = {'img': torch.rand(4, 1, 32, 32).cuda(), 'label': torch.zeros(4, dtype=torch.long).cuda()}
+    m.train(True)
+    out1 = m(inp)
+    out2 = m(inp)                                                   # overwrites the saved per-iteration state
+    with pytest.raises(RuntimeError, match='must follow the forward'):
+        out1['loss'].backward()
+    out2['loss'].backward()

@@ -147,7 +147,7 @@ def stage_bench():
                   (prec, M, Bn, ms, wall * 1e3, Bn / ms * 1e3, 57.083e9 * Bn / ms / 1e9))
 
 
-def train_case(tag, num_channel, num_node, T, B_, seed, precision, separate=False, img=None, label=None, noise=None):
+def train_case(tag, num_channel, num_node, T, B_, seed, precision, separate=False, img=None, label=None, noise=None, gp='fp16'):
     sd = O.init_state_dict(num_channel=num_channel, code_size=8, num_node=num_node, separate=separate, seed=seed)
     if img is None:
         g = torch.Generator().manual_seed(seed + 100)
@@ -159,17 +159,18 @@ def train_case(tag, num_channel, num_node, T, B_, seed, precision, separate=Fals
     ref = O.codec_forward(sdg, img, label, T, num_node, training=True, noise=[n for n in noise], separate=separate)
     ref['loss'].backward()
     t_ref = time.time() - t0
-    eng = CodecEngine(num_channel, 8, num_node, separate=separate, precision=precision)
+    eng = CodecEngine(num_channel, 8, num_node, separate=separate, precision=precision, grad_precision=gp)
     sdc = {k: v.cuda() for k, v in sd.items()}
     out = eng.forward(sdc, img.cuda(), label.cuda(), T, training=True, noise=noise.cuda(), save_for_backward=True)
     grads = eng.backward(out)
     torch.cuda.synchronize()
     loss = CodecEngine.loss_from_acc(out['loss_acc'], img.numel()).item()
     mism = int((out['codes'].cpu() != torch.stack(ref['code_pm1'])).sum())
-    print(tag, precision, 'loss %.8f ref %.8f code mismatches %d  (oracle fwd+bwd %.1fs)' % (loss, ref['loss'].item(), mism, t_ref))
+    print(tag, precision, gp, 'loss %.8f ref %.8f code mismatches %d  (oracle fwd+bwd %.1fs)' % (loss, ref['loss'].item(), mism, t_ref))
     worst = []
     for k, v in sdg.items():
-        gr, gg = v.grad.double(), grads[k].cpu().double()
+        gr = v.grad.double() if v.grad is not None else torch.zeros_like(v).double()
+        gg = grads[k].cpu().double()
         rel = ((gg - gr).norm() / max(gr.norm().item(), 1e-30)).item()
         cos = (torch.dot(gg.flatten(), gr.flatten()) / max(gg.norm().item() * gr.norm().item(), 1e-30)).item()
         worst.append((rel, cos, k, gr.norm().item(), gg.norm().item()))
@@ -184,20 +185,22 @@ def stage_train_small():
     for prec in ('parity', 'fast'):
         train_case('cifar_m2 golden train', 3, 2, 4, 6, 3, prec, img=torch.from_numpy(g['img']),
                    label=torch.from_numpy(g['label']), noise=torch.from_numpy(g['train_noise']))
+    train_case('cifar_m2 golden train', 3, 2, 4, 6, 3, 'parity', img=torch.from_numpy(g['img']),
+               label=torch.from_numpy(g['label']), noise=torch.from_numpy(g['train_noise']), gp='parity')
     train_case('mnist_m1 T=3', 1, 1, 3, 8, 1, 'parity')
     train_case('sep_m2 T=3', 3, 2, 3, 10, 2, 'parity', separate=True)
 
 
 def stage_train_medium():
-    for prec in ('parity', 'fast'):
-        train_case('cifar_m8 B=32 T=8', 3, 8, 8, 32, 5, prec)
+    for prec, gp in (('parity', 'fp16'), ('parity', 'parity'), ('fast', 'fp16')):
+        train_case('cifar_m8 B=32 T=8', 3, 8, 8, 32, 5, prec, gp=gp)
 
 
 def stage_train_bench():
-    for prec in ('parity', 'fast'):
-        for (M, Bn) in [(8, 256), (8, 1024)]:
+    for prec, gp in (('parity', 'fp16'), ('parity', 'parity'), ('fast', 'fp16')):
+        for (M, Bn) in [(8, 1024)]:
             sd = {k: v.cuda() for k, v in O.init_state_dict(3, 8, M, seed=0).items()}
-            eng = CodecEngine(3, 8, M, precision=prec)
+            eng = CodecEngine(3, 8, M, precision=prec, grad_precision=gp)
             g = torch.Generator().manual_seed(1)
             img = torch.rand(Bn, 3, 32, 32, generator=g).cuda()
             lab_h = torch.randint(0, M, (Bn,), generator=g)
@@ -216,8 +219,8 @@ def stage_train_bench():
             ms = e0.elapsed_time(e1)
             prof = eng.profile_summary()
             eng.profile = None
-            print('train bench %s M=%d B=%d: %.1f ms/step -> %.0f img/s (%.1f algorithmic TFLOP/s) mem %.1f GB' %
-                  (prec, M, Bn, ms, Bn / ms * 1e3, 3 * 57.083e9 * Bn / ms / 1e9, torch.cuda.max_memory_allocated() / 2**30))
+            print('train bench %s/%s M=%d B=%d: %.1f ms/step -> %.0f img/s (%.1f algorithmic TFLOP/s) mem %.1f GB' %
+                  (prec, gp, M, Bn, ms, Bn / ms * 1e3, 3 * 57.083e9 * Bn / ms / 1e9, torch.cuda.max_memory_allocated() / 2**30))
             grp = {}
             for k, (n, t, fl) in prof.items():
                 kk = k.split('_')[0]

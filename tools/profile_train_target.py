@@ -1,0 +1,27 @@
+"""Short single-GPU training step for ncu (forward with saved state + backward-through-time).
+usage: python tools/profile_train_target.py [batch] [precision] [T]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'drasic-distributed-recurrent-autoencoder-for-scalable-image-compression_b200')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, PKG)
+from oracle import drasic_oracle as O      # seeded parameter construction only
+from engine.codec import CodecEngine
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+prec = sys.argv[2] if len(sys.argv) > 2 else 'parity'
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+sd = {k: v.cuda() for k, v in O.init_state_dict(3, 8, 8, seed=0).items()}
+g = torch.Generator().manual_seed(1)
+img = torch.rand(B, 3, 32, 32, generator=g).cuda()
+lab = torch.randint(0, 8, (B,), generator=g)
+eng = CodecEngine(3, 8, 8, precision=prec)
+for _ in range(2):
+    out = eng.forward(sd, img, lab.cuda(), T, training=True, label_host=lab.numpy(), save_for_backward=True)
+    grads = eng.backward(out)
+torch.cuda.synchronize()
+print('ok', float(out['loss_acc'].sum()), float(sum(v.abs().sum() for v in grads.values())))
