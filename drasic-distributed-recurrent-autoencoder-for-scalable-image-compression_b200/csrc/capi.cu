@@ -64,6 +64,28 @@ int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, i
   return 0;
 }
 
+// the same plane seen as [C/64 chunks][N,H,W][64 ch]: the chunk index is the outermost dimension so one
+// box = `nchunk` stacked (64 ch x pixel-box) tiles, each in the MN-major SWIZZLE_128B layout (wgrad.cu)
+int make_act_map_chunked(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn,
+                         int nchunk) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(DRASIC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  const cuuint64_t dims[5] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(C / 64)};
+  const cuuint64_t strides[4] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                                 static_cast<cuuint64_t>(H) * W * C * 2, 128};
+  const cuuint32_t box[5] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh),
+                             static_cast<cuuint32_t>(bn), static_cast<cuuint32_t>(nchunk)};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DRASIC_ERR_TENSORMAP, "chunked activation tensor map rejected (CUresult %d) N=%d H=%d W=%d C=%d box=%dx%dx%dx%d",
+                static_cast<int>(r), N, H, W, C, bw, bh, bn, nchunk);
+  return 0;
+}
+
 // packed weights [rows, K] fp16 K-major; box = (64, block_n)
 int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, int block_n) {
   EncodeTiledFn enc = encode_fn();
@@ -320,7 +342,7 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
 int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream) {
   if (!a) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: null args");
   const int H = a->H, W = a->W, Cin = a->Cin, Co = a->Co, B = a->B_pad;
-  if (Cin % 64 || Co % 128 || Cin <= 0 || Co <= 0) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: channels");
+  if (Cin % 128 || Co % 128 || Cin <= 0 || Co <= 0) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: channels must be multiples of 128 (Cin=%d Co=%d)", Cin, Co);
   int kbw, kbh, kbn;
   if (pixel_box(H, W, 64, &kbw, &kbh, &kbn)) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: H=%d W=%d unsupported", H, W);
   if (B <= 0 || B % kbn) return fail(DRASIC_ERR_INVALID, "convlstm_bwd_weight: B_pad=%d", B);
@@ -332,13 +354,13 @@ int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream) {
   drasic::WgradParams p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = make_act_map(&p.tm_g[0], a->dg_hi, B, H, W, 4 * Co, kbw, kbh, kbn))) return rc;
-  if (a->split && (rc = make_act_map(&p.tm_g[1], a->dg_lo, B, H, W, 4 * Co, kbw, kbh, kbn))) return rc;
-  if ((rc = make_act_map(&p.tm_x[0], a->x_hi, B, H, W, Cin, kbw, kbh, kbn))) return rc;
-  if (a->split && (rc = make_act_map(&p.tm_x[1], a->x_lo, B, H, W, Cin, kbw, kbh, kbn))) return rc;
+  if ((rc = make_act_map_chunked(&p.tm_g[0], a->dg_hi, B, H, W, 4 * Co, kbw, kbh, kbn, 2))) return rc;
+  if (a->split && (rc = make_act_map_chunked(&p.tm_g[1], a->dg_lo, B, H, W, 4 * Co, kbw, kbh, kbn, 2))) return rc;
+  if ((rc = make_act_map_chunked(&p.tm_x[0], a->x_hi, B, H, W, Cin, kbw, kbh, kbn, 2))) return rc;
+  if (a->split && (rc = make_act_map_chunked(&p.tm_x[1], a->x_lo, B, H, W, Cin, kbw, kbh, kbn, 2))) return rc;
   if (a->has_h) {
-    if ((rc = make_act_map(&p.tm_h[0], a->h_hi, B, H, W, Co, kbw, kbh, kbn))) return rc;
-    if (a->split && (rc = make_act_map(&p.tm_h[1], a->h_lo, B, H, W, Co, kbw, kbh, kbn))) return rc;
+    if ((rc = make_act_map_chunked(&p.tm_h[0], a->h_hi, B, H, W, Co, kbw, kbh, kbn, 2))) return rc;
+    if (a->split && (rc = make_act_map_chunked(&p.tm_h[1], a->h_lo, B, H, W, Co, kbw, kbh, kbn, 2))) return rc;
   }
   p.gw = a->gw; p.g_inv_scale = a->dg_inv_scale; p.group_kb_end = a->n_groups > 1 ? a->group_kb_end : nullptr;
   p.H = H; p.W = W; p.Cin = Cin; p.Co = Co; p.kbw = kbw; p.kbh = kbh; p.kbn = kbn;

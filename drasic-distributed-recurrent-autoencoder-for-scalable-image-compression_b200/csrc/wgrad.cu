@@ -8,7 +8,9 @@
 // Both operands are NHWC fp16 planes, i.e. MN-major with respect to K = pixels: a K block of 64
 // pixels is loaded as TMA boxes of (64 channels x 64 pixels) -- 2 boxes of dG for A, up to 4 boxes of
 // the tap-shifted activation plane for B (out-of-bounds pixels read as zero = conv padding) -- and fed
-// to tcgen05.mma through MN-major SWIZZLE_128B descriptors.  One launch covers one (layer, iteration);
+// to tcgen05.mma through MN-major SWIZZLE_128B descriptors.  The tensor maps are 5-D with the 64-channel
+// chunk index as the OUTERMOST dimension, so one TMA instruction brings two stacked boxes (3 TMA
+// instructions per K block; with one instruction per box the single producer thread could not keep up).  One launch covers one (layer, iteration);
 // tiles are (node, m-tile, n-tile, k-split) and accumulate into the fp32 packed-order gradient with
 // vector atomics, so iterations, k-splits and launches compose by addition.
 // Roles / pipeline are those of the gate kernel: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue.
@@ -147,13 +149,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
             uint8_t* sa = st + pl * C::A_BYTES;
             uint8_t* sb = st + (SPLIT ? 2 : 1) * C::A_BYTES + pl * C::B_BYTES;
-            ptx::tma_load_4d(sa, &p.tm_g[pl], &full_bar[stage], t.mt * 128, x0, y0, n0);
-            ptx::tma_load_4d(sa + BOX_BYTES, &p.tm_g[pl], &full_bar[stage], t.mt * 128 + 64, x0, y0, n0);
-            for (int u = 0; u < t.nunits; ++u) {
+            ptx::tma_load_5d(sa, &p.tm_g[pl], &full_bar[stage], 0, x0, y0, n0, t.mt * 2);
+            for (int u = 0; u < t.nunits; u += 2) {   // a pair of 64-channel chunks of the same tap
               const int unit = t.u0 + u;
               const int tap = unit / cpu, chunk = unit - tap * cpu;
-              ptx::tma_load_4d(sb + u * BOX_BYTES, &tb[pl], &full_bar[stage], chunk * 64, x0 + tap % 3 - 1,
-                               y0 + tap / 3 - 1, n0);
+              ptx::tma_load_5d(sb + u * BOX_BYTES, &tb[pl], &full_bar[stage], 0, x0 + tap % 3 - 1,
+                               y0 + tap / 3 - 1, n0, chunk);
             }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
