@@ -2,7 +2,8 @@
 caller scripts turn every key into a command-line flag, train_model.py:20-36).  Two optional keys are
 B200-specific: 'precision' ('parity' = fp32-grade split-fp16 tensor-core path with bit-exact codes,
 'fast' = single fp16) and 'pack_mode' ('reference' = the reference's np.packbits semantics, 'bits' =
-the real 1 bit/symbol stream)."""
+the real 1 bit/symbol stream), 'grad_precision' ('fp16' | 'parity') and 'cuda_graph' (capture the whole T-iteration
+loop, forward and backward, as one CUDA graph per batch shape)."""
 
 
 def init():
@@ -16,4 +17,4 @@ def init():
         data_size=dict(train=0, test=0), device='cuda', num_epochs=200, save_mode=0, world_size=1,
         metric_names=dict(train=['Loss', 'BPP', 'PSNR'], test=['Loss', 'BPP', 'PSNR']),
         init_seed=0, num_Experiments=1, log_interval=0.25, log_overwrite=False, loss_fn='mae', resume_mode=0,
-        precision='parity', grad_precision='fp16', pack_mode='reference')
+        precision='parity', grad_precision='fp16', pack_mode='reference', cuda_graph=False)

@@ -24,43 +24,80 @@ ENC_IDX = {'E1': 2, 'E2': 4, 'E3': 6}   # nn.Sequential indices, dist_codec.py:7
 DEC_IDX = {'D1': 1, 'D2': 3, 'D3': 5}   # dist_codec.py:88-104
 
 
-class BatchPlan(object):
-    """Node-sorted, padded slot layout of one batch."""
+def plan_arrays(label_host, num_node, pad_total=None):
+    """node-sort one batch: (perm [B_pad] slot -> original index or -1, exclusive end slot per node)"""
+    label_host = np.asarray(label_host).astype(np.int64).reshape(-1)
+    if label_host.size and (label_host.min() < 0 or label_host.max() >= num_node):
+        # the reference mis-indexes and raises IndexError for label >= num_node (dist_codec.py:52)
+        raise IndexError('label out of range for num_node={}'.format(num_node))
+    order = np.argsort(label_host, kind='stable')              # keeps the reference's within-node order
+    counts = np.bincount(label_host, minlength=num_node)
+    padded = (counts + PAD - 1) // PAD * PAD
+    ends = np.cumsum(padded)
+    B_pad = int(ends[-1]) if pad_total is None else int(pad_total)
+    if B_pad < int(ends[-1]) or B_pad % PAD:
+        raise ValueError('Not valid pad_total')
+    perm = np.full(B_pad, -1, dtype=np.int32)
+    starts = ends - padded
+    src = 0
+    for j in range(num_node):
+        n = int(counts[j])
+        perm[starts[j]:starts[j] + n] = order[src:src + n]
+        src += n
+    return perm, ends.astype(np.int32), counts
 
-    def __init__(self, label_host, num_node, device, pad_total=None):
-        label_host = np.asarray(label_host).astype(np.int64).reshape(-1)
-        if label_host.size and (label_host.min() < 0 or label_host.max() >= num_node):
-            # the reference mis-indexes and raises IndexError for label >= num_node (dist_codec.py:52)
-            raise IndexError('label out of range for num_node={}'.format(num_node))
-        self.B = int(label_host.size)
-        order = np.argsort(label_host, kind='stable')          # keeps the reference's within-node order
-        counts = np.bincount(label_host, minlength=num_node)
-        padded = (counts + PAD - 1) // PAD * PAD
-        ends = np.cumsum(padded)
-        self.B_pad = int(ends[-1]) if pad_total is None else int(pad_total)
-        if self.B_pad < int(ends[-1]) or self.B_pad % PAD:
-            raise ValueError('Not valid pad_total')
-        perm = np.full(self.B_pad, -1, dtype=np.int32)
-        starts = ends - padded
-        src = 0
-        for j in range(num_node):
-            n = int(counts[j])
-            perm[starts[j]:starts[j] + n] = order[src:src + n]
-            src += n
-        self.counts = counts
-        self.group_img_end_host = ends.astype(np.int32)
-        self.perm_host = perm
+
+def worst_case_pad(B, num_node):
+    """slot count that fits any assignment of B samples to num_node nodes"""
+    return (B + (PAD - 1) * min(num_node, B) + PAD - 1) // PAD * PAD
+
+
+class BatchPlan(object):
+    """Node-sorted, padded slot layout of one batch.  With `static_hw` the plan owns fixed device
+    buffers (worst-case slot count) that update() refreshes in place -- what a captured CUDA graph reads."""
+
+    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None):
+        self.num_node, self.device = num_node, device
+        self.pad_total = pad_total
+        perm, ends, counts = plan_arrays(label_host, num_node, pad_total)
+        self.B, self.B_pad = int(np.asarray(label_host).size), int(perm.size)
+        self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
         self.perm = torch.from_numpy(perm).to(device)
-        self.group_img_end = torch.from_numpy(self.group_img_end_host).to(device)
-        self._mtile_end = {}
-        self.device = device
+        self.group_img_end = torch.from_numpy(ends).to(device)
+        self._mtile_end, self._kb_end = {}, {}
+        self.static = static_hw is not None
+        for hw in static_hw or ():
+            self.mtile_end(hw)
+            self.kb_end(hw)
+
+    def _scaled(self, cache, hw, unit):
+        if hw not in cache:
+            if self.static and getattr(self, '_frozen', False):
+                raise RuntimeError('static batch plan has no buffer for hw={}'.format(hw))
+            e = (self.group_img_end_host.astype(np.int64) * hw) // unit
+            cache[hw] = torch.from_numpy(e.astype(np.int32)).to(self.device)
+        return cache[hw]
 
     def mtile_end(self, hw):
         """exclusive end M-tile (128 pixels) of each node at a layer with hw pixels per image"""
-        if hw not in self._mtile_end:
-            e = (self.group_img_end_host.astype(np.int64) * hw) // 128
-            self._mtile_end[hw] = torch.from_numpy(e.astype(np.int32)).to(self.device)
-        return self._mtile_end[hw]
+        return self._scaled(self._mtile_end, hw, 128)
+
+    def kb_end(self, hw):
+        """exclusive end K block (64 pixels) of each node, for the wgrad GEMM"""
+        return self._scaled(self._kb_end, hw, 64)
+
+    def update(self, label_host):
+        """refresh the device buffers in place for a new batch of the same size"""
+        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad)
+        if int(np.asarray(label_host).size) != self.B:
+            raise ValueError('Not valid batch size for this static plan')
+        self._frozen = True
+        self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
+        self.perm.copy_(torch.from_numpy(perm), non_blocking=False)
+        self.group_img_end.copy_(torch.from_numpy(ends))
+        for cache, unit in ((self._mtile_end, 128), (self._kb_end, 64)):
+            for hw, t in cache.items():
+                t.copy_(torch.from_numpy(((ends.astype(np.int64) * hw) // unit).astype(np.int32)))
 
 
 class _Layer(object):
@@ -90,6 +127,7 @@ class CodecEngine(object):
         self._wcache = {}
         self._sms = None
         self.launches = 0   # kernels launched by the last forward() (bench.py reports it)
+        self.force_pack = False  # True while capturing a CUDA graph: always re-pack into the same buffers
         self.profile = None  # set to [] to collect (label, flops, start_event, end_event) per launch
 
     # ------------------------------------------------------------------ helpers
@@ -163,16 +201,19 @@ class CodecEngine(object):
         """weights: list over groups of (w_in, w_h) fp32 tensors. Cached on tensor identity+version."""
         key = (name, block_n) + tuple((w.data_ptr(), w._version) for pair in weights for w in pair)
         hit = self._wcache.get(name)
-        if hit is not None and hit[0] == key:
+        if hit is not None and hit[0] == key and not self.force_pack:
             return hit[1]
         L = B.lib()
         G = len(weights)
         dev = weights[0][0].device
         K = 9 * (cin + co)
-        hi = torch.empty((G * 4 * co, K), dtype=torch.float16, device=dev)
-        lo = torch.empty((G * 4 * co, K), dtype=torch.float16, device=dev)
-        inv = torch.empty((G,), dtype=torch.float32, device=dev)
-        scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
+        if hit is not None and hit[0][:2] == key[:2] and hit[1][0].shape == (G * 4 * co, K):
+            hi, lo, inv, _, scratch = hit[1]                   # repack into the same (graph-static) buffers
+        else:
+            hi = torch.empty((G * 4 * co, K), dtype=torch.float16, device=dev)
+            lo = torch.empty((G * 4 * co, K), dtype=torch.float16, device=dev)
+            inv = torch.empty((G,), dtype=torch.float32, device=dev)
+            scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
         plane = 4 * co * K * 2
         for g, (w_in, w_h) in enumerate(weights):
             if tuple(w_in.shape) != (4 * co, cin, 3, 3) or tuple(w_h.shape) != (4 * co, co, 3, 3):
@@ -184,13 +225,13 @@ class CodecEngine(object):
                                                inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
                     'pack_lstm_weights')
             self.launches += 2
-        val = (hi, lo, inv, (w_in, w_h))
+        val = (hi, lo, inv, (w_in, w_h), scratch)
         self._wcache[name] = (key, val)
         return val
 
     # ------------------------------------------------------------------ the loop
     def forward(self, sd, img, label, num_iter, training=False, noise=None, loss_kind='mae',
-                label_host=None, want_z=False, save_for_backward=False):
+                label_host=None, want_z=False, save_for_backward=False, plan=None):
         """sd: mapping reference state_dict key -> fp32 CUDA tensor.  img [B,C,H,W] fp32 in [0,1],
         label [B] node ids.  noise: None (eval / deterministic sign) or [T,B,code,H/8,W/8] uniforms.
         Returns dict(recon [T,B,C,H,W], codes [T,B,code,H/8,W/8], bits [T,B,code*HW/64/8] uint8,
@@ -208,9 +249,10 @@ class CodecEngine(object):
         if H % 8 or W % 8 or (H * W) % 256:
             raise ValueError('Not valid image size {}x{} for the fused path'.format(H, W))
         T = int(num_iter)
-        if label_host is None:
-            label_host = label.detach().cpu().numpy()          # the one host sync per forward
-        plan = BatchPlan(label_host, self.M, dev)
+        if plan is None:
+            if label_host is None:
+                label_host = label.detach().cpu().numpy()      # the one host sync per forward
+            plan = BatchPlan(label_host, self.M, dev)
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
@@ -244,8 +286,8 @@ class CodecEngine(object):
             ly.in_order, ly.out_order, ly.is_enc, ly.idx, ly.prefs = io, oo, is_enc, idx, prefs
             ly.block_n = self._block_n(n_mtiles, co)
             ly.groups = len(prefs)
-            ly.hi, ly.lo, ly.inv, _ = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
-                                                   ly.block_n, stream)
+            ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
+                                                   ly.block_n, stream)[:3]
             ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
             layers.append(ly)
 
@@ -365,15 +407,18 @@ class CodecEngine(object):
         weights = [lstm_w(p, ly.idx) for p in ly.prefs]
         key = tuple((w.data_ptr(), w._version) for pair in weights for w in pair)
         hit = self._wcache.get('dgrad_' + ly.name)
-        if hit is not None and hit[0] == key:
-            return hit[1]
+        if hit is not None and hit[0] == key and not self.force_pack:
+            return hit[1][:3]
         L = B.lib()
         dev = weights[0][0].device
         G, n_out, K = len(weights), ly.cin + ly.co, 36 * ly.co
-        hi = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
-        lo = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
-        inv = torch.empty((G,), dtype=torch.float32, device=dev)
-        scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
+        if hit is not None:
+            hi, lo, inv, scratch = hit[1]
+        else:
+            hi = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
+            lo = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
+            inv = torch.empty((G,), dtype=torch.float32, device=dev)
+            scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
         plane = n_out * K * 2
         for g, (w_in, w_h) in enumerate(weights):
             w_in, w_h = w_in.detach().contiguous(), w_h.detach().contiguous()
@@ -382,9 +427,8 @@ class CodecEngine(object):
                                                 inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
                     'pack_dgrad_weights')
             self.launches += 2
-        val = (hi, lo, inv)
-        self._wcache['dgrad_' + ly.name] = (key, val)
-        return val
+        self._wcache['dgrad_' + ly.name] = (key, (hi, lo, inv, scratch))
+        return hi, lo, inv
 
     def _bwd_buffers(self, layers, Bp, H, W, dev):
         key = (Bp, H, W, str(dev))
@@ -433,14 +477,9 @@ class CodecEngine(object):
         dpk = {ly.name: self._packed_dgrad(ly, sd, stream) for ly in layers}
         by = {ly.name: ly for ly in layers}
         sms = self.sms()
-        kb_end = {}
 
         def group_kb_end(ly):
-            hw = ly.h * ly.w
-            if hw not in kb_end:
-                e = (plan.group_img_end_host.astype(np.int64) * hw) // 64
-                kb_end[hw] = torch.from_numpy(e.astype(np.int32)).to(dev)
-            return kb_end[hw]
+            return plan.kb_end(ly.h * ly.w)
 
         # where each layer's input lives / where its input gradient goes
         x_of = {'E1': lambda t: A['e1_in'][t], 'E2': lambda t: A['E1']['next'][t], 'E3': lambda t: A['E2']['next'][t],
@@ -544,3 +583,63 @@ class CodecEngine(object):
         """mean over T of the per-iteration mean loss (dist_codec.py:58,61)"""
         T = loss_acc.shape[0]
         return (loss_acc[:, 0].sum() / (float(numel) * T)).float()
+
+
+class GraphedCodec(object):
+    """The whole T-iteration loop -- and, for training, backward-through-time -- captured once as a CUDA
+    graph and replayed per batch.  Inputs live in static buffers (image batch, node-sort metadata of
+    worst-case size); weights are re-packed from the fp32 master parameters inside the graph, so
+    optimizer steps between replays are honoured; recurrent state never leaves the device.
+    Replay cost on the host: two small H2D copies and one cudaGraphLaunch."""
+
+    def __init__(self, engine, sd, batch, hw, num_iter, training=False, with_backward=False, loss_kind='mae',
+                 device=None):
+        self.eng, self.sd, self.T = engine, sd, int(num_iter)
+        self.training, self.with_backward, self.loss_kind = training, with_backward, loss_kind
+        H, W = hw
+        dev = device or next(iter(sd.values())).device
+        self.B = int(batch)
+        self.img = torch.zeros((self.B, engine.C, H, W), dtype=torch.float32, device=dev)
+        self.noise = torch.rand((self.T, self.B, engine.code, H // 8, W // 8), dtype=torch.float32, device=dev) \
+            if training else None
+        hws = sorted({(H // d) * (W // d) for d in (2, 4, 8)})
+        label0 = np.arange(self.B) % engine.M
+        self.plan = BatchPlan(label0, engine.M, dev, pad_total=worst_case_pad(self.B, engine.M), static_hw=hws)
+        self.graph = None
+        self.out = self.grads = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                          # warm-up: allocates arenas, sets attributes
+            for _ in range(2):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        engine.force_pack = True
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._run()
+        finally:
+            engine.force_pack = False
+        self.launches = engine.launches
+
+    def _run(self):
+        with torch.no_grad():
+            self.out = self.eng.forward(self.sd, self.img, None, self.T, training=self.training, noise=self.noise,
+                                        loss_kind=self.loss_kind, save_for_backward=self.with_backward,
+                                        plan=self.plan)
+            self.grads = self.eng.backward(self.out) if self.with_backward else None
+
+    def __call__(self, img, label_host, noise=None):
+        """img: [B,C,H,W] tensor (host or device); label_host: host array of node ids; noise: optional
+        uniforms for the stochastic binarizer (drawn with torch's generator otherwise)"""
+        self.img.copy_(img, non_blocking=True)
+        if self.noise is not None:
+            if noise is not None:
+                self.noise.copy_(noise, non_blocking=True)
+            else:
+                self.noise.uniform_()
+        self.plan.update(label_host)
+        self.graph.replay()
+        self.eng.launches = self.launches
+        return self.out, self.grads

@@ -7,7 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 import config
-from engine.codec import CodecEngine
+from engine.codec import CodecEngine, GraphedCodec
 from modules.cell import ConvCell, ConvLSTMCell, PixelShuffleCell
 from utils import apply_fn
 from .utils import make_model
@@ -55,9 +55,14 @@ class _LoopFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, img, label, noise, *params):
-        out = model._run_engine(img, label, noise, save_for_backward=True)
         ctx.model = model
         ctx.names = [k for k, _ in model.named_parameters()]
+        if config.PARAM.get('cuda_graph', False):
+            # one graph holds forward AND backward-through-time; backward() only hands the gradients out
+            out, ctx.grads = model._run_graphed(img, label, noise, with_backward=True)
+        else:
+            out = model._run_engine(img, label, noise, save_for_backward=True)
+            ctx.grads = None
         ctx.saved = out
         ctx.mark_non_differentiable(out['recon'], out['codes'], out['bits'])
         loss = CodecEngine.loss_from_acc(out['loss_acc'], img.numel())
@@ -65,7 +70,10 @@ class _LoopFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, g_recon, g_codes, g_bits):
-        grads = ctx.model._engine.backward(ctx.saved, g_loss)
+        if ctx.grads is not None:
+            grads = {k: v * g_loss for k, v in ctx.grads.items()}
+        else:
+            grads = ctx.model._engine.backward(ctx.saved, g_loss)
         return (None, None, None, None) + tuple(grads[k] for k in ctx.names)
 
 
@@ -117,7 +125,7 @@ class CodecModel(nn.Module):
         if config.PARAM.get('normalization', 'none') != 'none':
             raise ValueError('Not valid normalization for the B200 path (only none)')
 
-    def _run_engine(self, img, label, noise, save_for_backward=False):
+    def _ensure_engine(self):
         key = (config.PARAM['num_channel'], config.PARAM['code_size'], config.PARAM['num_node'],
                config.PARAM.get('precision', 'parity'), config.PARAM.get('grad_precision', 'fp16'))
         if self._engine_key != key:
@@ -125,6 +133,24 @@ class CodecModel(nn.Module):
             self._engine = CodecEngine(key[0], key[1], key[2], separate=self.separate, precision=key[3],
                                        grad_precision=key[4])
             self._engine_key = key
+            self._graphs = {}
+
+    def _run_graphed(self, img, label, noise, with_backward=False):
+        self._ensure_engine()
+        if not img.is_cuda:
+            from engine.binding import DrasicError
+            raise DrasicError('DRASIC B200 engine needs CUDA tensors; there is no CPU path')
+        key = (tuple(img.shape), config.PARAM['num_iter'], self.training, with_backward, config.PARAM['loss_fn'])
+        g = self._graphs.get(key)
+        if g is None:
+            sd = {k: v for k, v in self.named_parameters()}
+            g = GraphedCodec(self._engine, sd, img.shape[0], tuple(img.shape[2:]), config.PARAM['num_iter'],
+                             training=self.training, with_backward=with_backward, loss_kind=config.PARAM['loss_fn'])
+            self._graphs[key] = g
+        return g(img.detach(), label.detach().cpu().numpy(), noise)
+
+    def _run_engine(self, img, label, noise, save_for_backward=False):
+        self._ensure_engine()
         sd = {k: v for k, v in self.named_parameters()}
         return self._engine.forward(sd, img, label, config.PARAM['num_iter'], training=self.training,
                                     noise=noise, loss_kind=config.PARAM['loss_fn'],
@@ -143,7 +169,10 @@ class CodecModel(nn.Module):
         if need_grad:
             loss, recon, codes, bits = _LoopFunction.apply(self, img, label, noise, *params)
         else:
-            res = self._run_engine(img, label, noise)
+            if config.PARAM.get('cuda_graph', False):
+                res, _ = self._run_graphed(img, label, noise)
+            else:
+                res = self._run_engine(img, label, noise)
             loss = CodecEngine.loss_from_acc(res['loss_acc'], img.numel())
             recon, codes, bits = res['recon'], res['codes'], res['bits']
         T = recon.shape[0]

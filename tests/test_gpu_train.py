@@ -91,32 +91,41 @@ def test_training_step_vs_oracle_autograd(name, M, B, T, separate):
     assert sorted(errs)[len(errs) // 2] < GRAD_TOL_MEDIAN
 
 
-def test_optimizer_steps_reduce_loss_and_repack_weights():
-    """Adam updates the fp32 master parameters in place (train_model.py:116); the packed fp16 weight
-    planes are a cache keyed on the parameter version and must follow."""
-    m = build_model('dist_codec', 'CIFAR10', 2, 4, seed=5)
-    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+def test_optimizer_trajectory_follows_oracle_and_weights_are_repacked():
+    """SGD updates the fp32 master parameters in place (train_model.py:116); the packed fp16 weight planes
+    are a cache keyed on the parameter version and must follow.  Three training steps with given binarizer
+    noise must track the same three steps done by the CPU oracle."""
+    m = build_model('dist_codec', 'CIFAR10', 2, 3, seed=5)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    opt_ref = torch.optim.SGD(list(sd.values()), lr=0.5)
     g = torch.Generator().manual_seed(6)
-    img = torch.rand(16, 3, 32, 32, generator=g)
-    label = torch.randint(0, 2, (16,), generator=g)
-    losses = []
-    for it in range(6):
+    img = torch.rand(8, 3, 32, 32, generator=g)
+    label = torch.randint(0, 2, (8,), generator=g)
+    for it in range(3):
+        noise = torch.rand(3, 8, 8, 4, 4, generator=g)
+        opt_ref.zero_grad()
+        ref = O.codec_forward(sd, img, label, 3, 2, training=True, noise=[n for n in noise])
+        ref['loss'].backward()
+        opt_ref.step()
         m.train(True)
         opt.zero_grad()
-        out = m({'img': img.cuda(), 'label': label.cuda()})
+        out = m({'img': img.cuda(), 'label': label.cuda()}, noise=noise.cuda())
         out['loss'].backward()
         opt.step()
-        losses.append(out['loss'].item())
-    assert losses[-1] < losses[0] - 1e-3, losses
+        assert abs(out['loss'].item() - ref['loss'].item()) < 2e-5, it
+        assert (out['code_pm1'].cpu() != torch.stack(ref['code_pm1'])).float().mean().item() < 2e-3
+    for k, p in m.named_parameters():
+        assert rel_err(p.detach().cpu(), sd[k].detach()) < 1e-4, k
     # eval after training equals the oracle on the *updated* weights (cache was refreshed)
-    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    sdn = {k: v.detach() for k, v in sd.items()}
     with torch.no_grad():
-        ref = O.codec_forward(sd, img, label, 4, 2)
+        ref = O.codec_forward(sdn, img, label, 3, 2)
     m.train(False)
     with torch.no_grad():
         out = m({'img': img.cuda(), 'label': label.cuda()})
-    assert abs(out['loss'].item() - ref['loss'].item()) < 1e-5
-    assert (out['code_pm1'].cpu() != torch.stack(ref['code_pm1'])).float().mean().item() < 1e-3
+    assert abs(out['loss'].item() - ref['loss'].item()) < 1e-4
+    assert (out['code_pm1'].cpu() != torch.stack(ref['code_pm1'])).float().mean().item() < 5e-3
 
 
 def test_backward_requires_matching_forward():
@@ -128,3 +137,48 @@ def test_backward_requires_matching_forward():
     with pytest.raises(RuntimeError, match='must follow the forward'):
         out1['loss'].backward()
     out2['loss'].backward()
+
+
+def test_cuda_graph_matches_eager_eval_and_train():
+    """config.PARAM['cuda_graph']: the whole loop (and backward-through-time) replayed as one CUDA graph
+    must reproduce the eager launches bit for bit, across batches with different node assignments and
+    across optimizer updates of the weights."""
+    import config
+    m = build_model('dist_codec', 'CIFAR10', 3, 4, seed=7)
+    g = torch.Generator().manual_seed(8)
+    batches = [(torch.rand(24, 3, 32, 32, generator=g), torch.randint(0, 3, (24,), generator=g)) for _ in range(3)]
+    batches[2] = (batches[2][0], torch.zeros(24, dtype=torch.long))          # all samples on one node
+    noise = torch.rand(4, 24, 8, 4, 4, generator=g)
+    # ---- eval
+    eager = []
+    m.train(False)
+    for img, label in batches:
+        with torch.no_grad():
+            eager.append(m({'img': img.cuda(), 'label': label.cuda()}))
+    config.PARAM['cuda_graph'] = True
+    for (img, label), ref in zip(batches, eager):
+        with torch.no_grad():
+            out = m({'img': img.cuda(), 'label': label.cuda()})
+        assert torch.equal(out['code_pm1'], ref['code_pm1'])
+        assert torch.equal(torch.stack(out['img']), torch.stack(ref['img']))
+        assert out['loss'].item() == ref['loss'].item()
+    # ---- train: gradients from the graph == eager gradients; then an optimizer step and again
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    for step in range(2):
+        grads = {}
+        for mode in (False, True):
+            config.PARAM['cuda_graph'] = mode
+            m.train(True)
+            m.zero_grad()
+            img, label = batches[step]
+            out = m({'img': img.cuda(), 'label': label.cuda()}, noise=noise.cuda())
+            out['loss'].backward()
+            grads[mode] = ({k: p.grad.clone() for k, p in m.named_parameters()}, out['loss'].item(), out['code_pm1'].clone())
+        assert grads[True][1] == grads[False][1]
+        assert torch.equal(grads[True][2], grads[False][2])
+        for k in grads[True][0]:
+            # fp32 atomics in the weight-gradient accumulation make the sums order dependent at the 1e-6 level
+            a, b = grads[True][0][k], grads[False][0][k]
+            assert (a - b).norm().item() <= 1e-4 * max(b.norm().item(), 1e-30), k
+        opt.step()
+    config.PARAM['cuda_graph'] = False
