@@ -206,6 +206,7 @@ def run_ours(args):
                 out = model(inp)
         return out
 
+    config.PARAM['cuda_graph'] = args.graph
     resident = {'img': img, 'label': label}
     for _ in range(max(args.warmup, 3)):
         step(resident)
@@ -222,13 +223,15 @@ def run_ours(args):
     launches = eng.launches
     clocks = sampler.stop() if sampler else None
 
-    # ---- per-kernel timing on the launching stream (separate pass, CUDA events around every launch)
+    # ---- per-kernel timing on the launching stream (separate eager pass, CUDA events around every launch)
+    config.PARAM['cuda_graph'] = False
     eng.profile = []
     for _ in range(2):
         step(resident)
     torch.cuda.synchronize()
     prof = eng.profile_summary()
     eng.profile = None
+    config.PARAM['cuda_graph'] = args.graph
 
     # ---- end to end through the public API with host buffers (H2D of inputs, D2H of loss + codes)
     pin_img, pin_label = img_h.pin_memory(), label_h.pin_memory()
@@ -272,7 +275,7 @@ def run_ours(args):
         'data': 'synthetic',
         'config': {'workload': workload_name(args.mode), 'batch_per_gpu': B,
                    'global_batch': world * B, 'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8,
-                   'precision': args.precision,
+                   'precision': args.precision, 'cuda_graph': args.graph,
                    'parallelism': ('dp{}: batch sharded, one NCCL all-reduce of gradients per step'.format(world) if train
                                    else 'batch-sharded replicas x{} (no collective)'.format(world)),
                    'l2': 'per-step working set (activations+state, ~1 MB/image) exceeds the 126 MB L2'},
@@ -331,6 +334,9 @@ def main():
                     help='train: forward + backward-through-time + all-reduce + Adam step (BASELINE configs[1]); '
                          'eval: encode+decode only')
     ap.add_argument('--grad-precision', default='fp16', choices=['fp16', 'parity'])
+    ap.add_argument('--graph', action='store_true',
+                    help='replay one captured CUDA graph per step instead of launching eagerly (measured slower: the '
+                         'loop is GPU-bound at >100 us per launch and a static graph needs worst-case node padding)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

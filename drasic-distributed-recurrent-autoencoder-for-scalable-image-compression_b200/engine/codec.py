@@ -231,7 +231,7 @@ class CodecEngine(object):
 
     # ------------------------------------------------------------------ the loop
     def forward(self, sd, img, label, num_iter, training=False, noise=None, loss_kind='mae',
-                label_host=None, want_z=False, save_for_backward=False, plan=None):
+                label_host=None, want_z=False, save_for_backward=False, plan=None, pack_only=False):
         """sd: mapping reference state_dict key -> fp32 CUDA tensor.  img [B,C,H,W] fp32 in [0,1],
         label [B] node ids.  noise: None (eval / deterministic sign) or [T,B,code,H/8,W/8] uniforms.
         Returns dict(recon [T,B,C,H,W], codes [T,B,code,H/8,W/8], bits [T,B,code*HW/64/8] uint8,
@@ -290,6 +290,9 @@ class CodecEngine(object):
                                                    ly.block_n, stream)[:3]
             ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
             layers.append(ly)
+
+        if pack_only:
+            return None
 
         def stack(keys):
             return torch.stack([sd[k].detach().float().reshape(sd[k].shape[0], -1) for k in keys]).contiguous()
@@ -614,7 +617,9 @@ class GraphedCodec(object):
                 self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        engine.force_pack = True
+        # training re-packs the weights inside the graph (they change every step); inference keeps the
+        # packed planes outside and refreshes them eagerly only when a parameter version changes
+        engine.force_pack = bool(with_backward)
         try:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
@@ -623,7 +628,23 @@ class GraphedCodec(object):
             engine.force_pack = False
         self.launches = engine.launches
 
+    def _versions(self):
+        return tuple(v._version for v in self.sd.values())
+
+    def _refresh_weights(self):
+        if self._versions() == self._seen:
+            return
+        # a parameter changed since capture: re-pack eagerly into the buffers the graph reads
+        self.eng.force_pack = True
+        try:
+            with torch.no_grad():
+                self.eng.forward(self.sd, self.img, None, 0, training=False, plan=self.plan, pack_only=True)
+        finally:
+            self.eng.force_pack = False
+        self._seen = self._versions()
+
     def _run(self):
+        self._seen = self._versions()
         with torch.no_grad():
             self.out = self.eng.forward(self.sd, self.img, None, self.T, training=self.training, noise=self.noise,
                                         loss_kind=self.loss_kind, save_for_backward=self.with_backward,
@@ -640,6 +661,8 @@ class GraphedCodec(object):
             else:
                 self.noise.uniform_()
         self.plan.update(label_host)
+        if not self.with_backward:
+            self._refresh_weights()
         self.graph.replay()
         self.eng.launches = self.launches
         return self.out, self.grads
