@@ -262,150 +262,272 @@ __global__ void __launch_bounds__(128) bottleneck_bwd_kernel(const BottleneckBwd
 }
 
 // ------------------------------------------------------------------ tail / head backward
+// Same thread mapping as the forward tail/head kernel (pointwise.cu): four lanes per pixel, eight of the
+// 32 feature channels per lane, pixels enumerated quad-major so the feature-side tensors (D3's h, dh_d3,
+// du1) are contiguous per warp.  Weight gradients accumulate in registers over all passes of the block
+// and are reduced once per block (shuffles over the lanes that own the same channel slice -> shared
+// atomics -> one global atomic per weight).
 constexpr int TB_THREADS = 256;
+constexpr int TB_PIX = TB_THREADS / 4;
 constexpr int MAXC = 4;
 constexpr int FEATB = 32;
 
+__device__ __forceinline__ int slice_channel(int sub, int j) { return j < 4 ? 4 * sub + j : 16 + 4 * sub + (j - 4); }
+
+struct QuadMapB {  // quad-major pixel index -> raster pixel offset
+  int W, qw, shift;
+  __device__ __forceinline__ explicit QuadMapB(int W_) : W(W_), qw(W_ >> 1) {
+    shift = (qw & (qw - 1)) == 0 ? 31 - __clz(qw) : -1;
+  }
+  __device__ __forceinline__ int raster(int i) const {
+    const int quad = i >> 2, qd = i & 3;
+    const int qy = shift >= 0 ? quad >> shift : quad / qw;
+    const int qx = quad - qy * qw;
+    return (2 * qy + (qd >> 1)) * W + 2 * qx + (qd & 1);
+  }
+};
+
 // iteration t: G = (has_acc ? G : 0) + dLoss_t/dRecon_t ; d = tanh(W4 v4) ; backward through it
-__global__ void __launch_bounds__(TB_THREADS) tail_bwd_kernel(const TailBwdParams p) {
-  __shared__ float s_w4[MAXC * FEATB];
+template <int NC>
+__global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdParams p) {
   __shared__ float s_acc[MAXC * FEATB];
+  __shared__ alignas(16) float s_w4[MAXC][4][8];   // [c][sub][j]
   const int HW = p.H * p.W;
-  const int blocks_per_img = HW / TB_THREADS;
-  const int slot = blockIdx.x / blocks_per_img;
-  const int pix = (blockIdx.x - slot * blocks_per_img) * TB_THREADS + threadIdx.x;
+  const int bpi = gridDim.x / p.B_pad;
+  const int slot = blockIdx.x / bpi;
+  const int part = blockIdx.x - slot * bpi;
+  const int ppb = HW / bpi;
   const int orig = p.perm[slot];
-  const int Y = pix / p.W, X = pix - Y * p.W;
-  const int qd = (Y & 1) * 2 + (X & 1);
-  const size_t ppix = (static_cast<size_t>(slot) * (p.H >> 1) + (Y >> 1)) * (p.W >> 1) + (X >> 1);
-  float4* dst = reinterpret_cast<float4*>(p.dh_d3 + ppix * (4 * FEATB) + qd * FEATB);
+  float* dh_img = p.dh_d3 + static_cast<size_t>(slot) * HW * FEATB;
   if (orig < 0) {  // padding slot: zero gradient
-#pragma unroll
-    for (int v = 0; v < FEATB / 4; ++v) dst[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* z = reinterpret_cast<float4*>(dh_img + static_cast<size_t>(part) * ppb * FEATB);
+    for (int v = threadIdx.x; v < ppb * FEATB / 4; v += TB_THREADS) z[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
-  const int C = p.C;
+  constexpr int C = NC;
   const int gd = p.n_dec_groups > 1 ? find_group_b(p.group_img_end, p.n_dec_groups, slot) : 0;
-  if (threadIdx.x < C * FEATB) s_w4[threadIdx.x] = p.w_d4[static_cast<size_t>(gd) * C * FEATB + threadIdx.x];
-  __syncthreads();
-  float f[FEATB];
-  const float4* src = reinterpret_cast<const float4*>(p.d3_next + (static_cast<size_t>(slot) * HW + pix) * FEATB);
-#pragma unroll
-  for (int v = 0; v < FEATB / 4; ++v) {
-    const float4 t = src[v];
-    f[4 * v + 0] = t.x; f[4 * v + 1] = t.y; f[4 * v + 2] = t.z; f[4 * v + 3] = t.w;
+  const int sub = threadIdx.x & 3;
+  const int lane = threadIdx.x & 31;
+  const int lane_base = lane & ~3;
+  const bool mine = sub < C;
+  const QuadMapB qm(p.W);
+  for (int t = threadIdx.x; t < MAXC * FEATB; t += TB_THREADS) {
+    const int c = t >> 5, sb = (t >> 3) & 3, j = t & 7;
+    s_w4[c][sb][j] = c < C ? p.w_d4[(static_cast<size_t>(gd) * C + c) * FEATB + slice_channel(sb, j)] : 0.0f;
+    s_acc[t] = 0.0f;
   }
-  float dv[FEATB];
-#pragma unroll
-  for (int k = 0; k < FEATB; ++k) dv[k] = 0.0f;
-  float dpre[MAXC] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
-    if (c < C) {
-      const size_t gi = (static_cast<size_t>(orig) * C + c) * HW + pix;
-      const float r = p.recon_t[gi], im = p.img[gi];
-      float direct;
-      if (p.loss_kind == LOSS_MAE) direct = (r > im) ? 1.0f : ((r < im) ? -1.0f : 0.0f);
-      else if (p.loss_kind == LOSS_MSE) direct = 2.0f * (r - im);
-      else direct = (r - im) / fmaxf(r * (1.0f - r), 1e-12f);
-      const float G = (p.has_acc ? p.gacc[gi] : 0.0f) + direct * p.loss_scale;
-      p.gacc[gi] = G;
-      float acc = 0.0f;
-#pragma unroll
-      for (int k = 0; k < FEATB; ++k) acc = fmaf(s_w4[c * FEATB + k], f[k], acc);
-      const float d = tanhf(acc);
-      dpre[c] = G * (p.first ? 0.5f : 1.0f) * (1.0f - d * d);
-#pragma unroll
-      for (int k = 0; k < FEATB; ++k) dv[k] = fmaf(s_w4[c * FEATB + k], dpre[c], dv[k]);
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < FEATB / 4; ++v) dst[v] = make_float4(dv[4 * v], dv[4 * v + 1], dv[4 * v + 2], dv[4 * v + 3]);
-  // dW_d4[c,k] += sum_pixels dpre[c] * v4[k]: warp shuffle -> shared atomics -> one global atomic per block
-  for (int i = threadIdx.x; i < MAXC * FEATB; i += blockDim.x) s_acc[i] = 0.0f;
   __syncthreads();
+  float wacc[NC][8];
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
-    if (c < C) {
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int k = 0; k < FEATB; ++k) {
-        float v = dpre[c] * f[k];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[c * FEATB + k], v);
+    for (int j = 0; j < 8; ++j) wacc[c][j] = 0.0f;
+  const float gain = p.first ? 0.5f : 1.0f;
+  const size_t img_base = (static_cast<size_t>(orig) * C + (mine ? sub : 0)) * HW;
+  const float4* d3 = reinterpret_cast<const float4*>(p.d3_next) + static_cast<size_t>(slot) * HW * (FEATB / 4);
+
+  int i = part * ppb + (threadIdx.x >> 2);
+  const int i_end = (part + 1) * ppb;
+  int rpix = qm.raster(i);
+  float4 fa = d3[i * (FEATB / 4) + sub], fb = d3[i * (FEATB / 4) + sub + 4];
+  float r = 0.0f, im = 0.0f, ga = 0.0f;
+  if (mine) {
+    r = p.recon_t[img_base + rpix];
+    im = p.img[img_base + rpix];
+    if (p.has_acc) ga = p.gacc[img_base + rpix];
+  }
+  for (; i < i_end; i += TB_PIX) {
+    const float f[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+    const float r_c = r, im_c = im, ga_c = ga;
+    const size_t gi = img_base + rpix;
+    const int in = i + TB_PIX;
+    if (in < i_end) {  // next pass's loads (uniform branch)
+      rpix = qm.raster(in);
+      fa = d3[in * (FEATB / 4) + sub];
+      fb = d3[in * (FEATB / 4) + sub + 4];
+      if (mine) {
+        r = p.recon_t[img_base + rpix];
+        im = p.img[img_base + rpix];
+        if (p.has_acc) ga = p.gacc[img_base + rpix];
       }
     }
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float a = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a = fmaf(s_w4[c][sub][j], f[j], a);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      acc[c] = a;
+    }
+    float dpre_mine = 0.0f;
+    if (mine) {
+      float direct;
+      if (p.loss_kind == LOSS_MAE) direct = (r_c > im_c) ? 1.0f : ((r_c < im_c) ? -1.0f : 0.0f);
+      else if (p.loss_kind == LOSS_MSE) direct = 2.0f * (r_c - im_c);
+      else direct = (r_c - im_c) / fmaxf(r_c * (1.0f - r_c), 1e-12f);
+      const float G = ga_c + direct * p.loss_scale;
+      p.gacc[gi] = G;
+      float pre = acc[0];
+#pragma unroll
+      for (int c = 1; c < NC; ++c) pre = sub == c ? acc[c] : pre;
+      const float d = tanhf(pre);
+      dpre_mine = G * gain * (1.0f - d * d);
+    }
+    float dpre[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dpre[c] = __shfl_sync(0xffffffffu, dpre_mine, lane_base + c);
+    float dv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.0f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        a = fmaf(s_w4[c][sub][j], dpre[c], a);
+        wacc[c][j] = fmaf(dpre[c], f[j], wacc[c][j]);
+      }
+      dv[j] = a;
+    }
+    float4* dst = reinterpret_cast<float4*>(dh_img + static_cast<size_t>(i) * FEATB);
+    dst[sub] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    dst[sub + 4] = make_float4(dv[4], dv[5], dv[6], dv[7]);
   }
+  // dW_d4[c,k] += sum_pixels dpre[c] * v4[k]
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = wacc[c][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) atomicAdd(&s_acc[c * FEATB + slice_channel(sub, j)], v);
+    }
   __syncthreads();
   if (threadIdx.x < C * FEATB)
     atomicAdd(p.dw_d4 + static_cast<size_t>(gd) * C * FEATB + threadIdx.x, s_acc[threadIdx.x]);
 }
 
 // iteration t: e0 = tanh(W0 x + b) recomputed; backward to W0, b and (dist codec, t > 0) to recon_{t-1}
-__global__ void __launch_bounds__(TB_THREADS) head_bwd_kernel(const HeadBwdParams p) {
-  __shared__ float s_w0[FEATB * MAXC];
-  __shared__ float s_b0[FEATB];
+template <int NC>
+__global__ void __launch_bounds__(TB_THREADS, 3) head_bwd_kernel(const HeadBwdParams p) {
   __shared__ float s_acc[FEATB * MAXC + FEATB];
+  __shared__ alignas(16) float s_w0[4][8][MAXC];   // [sub][j][c]
+  __shared__ alignas(16) float s_b0[4][8];
   const int HW = p.H * p.W;
-  const int blocks_per_img = HW / TB_THREADS;
-  const int slot = blockIdx.x / blocks_per_img;
-  const int pix = (blockIdx.x - slot * blocks_per_img) * TB_THREADS + threadIdx.x;
+  const int bpi = gridDim.x / p.B_pad;
+  const int slot = blockIdx.x / bpi;
+  const int part = blockIdx.x - slot * bpi;
+  const int ppb = HW / bpi;
   const int orig = p.perm[slot];
   if (orig < 0) return;
-  const int C = p.C;
+  constexpr int C = NC;
   const int ge = p.n_enc_groups > 1 ? find_group_b(p.group_img_end, p.n_enc_groups, slot) : 0;
-  if (threadIdx.x < C * FEATB) s_w0[threadIdx.x] = p.w_e0[static_cast<size_t>(ge) * FEATB * C + threadIdx.x];
-  if (threadIdx.x < FEATB) s_b0[threadIdx.x] = p.b_e0 ? p.b_e0[static_cast<size_t>(ge) * FEATB + threadIdx.x] : 0.0f;
+  const int sub = threadIdx.x & 3;
+  const int lane = threadIdx.x & 31;
+  const int lane_base = lane & ~3;
+  const bool mine = sub < C;
+  const QuadMapB qm(p.W);
+  for (int t = threadIdx.x; t < FEATB * MAXC + FEATB; t += TB_THREADS) s_acc[t] = 0.0f;
+  for (int t = threadIdx.x; t < MAXC * FEATB; t += TB_THREADS) {
+    const int c = t >> 5, sb = (t >> 3) & 3, j = t & 7;
+    const int k = slice_channel(sb, j);
+    s_w0[sb][j][c] = c < C ? p.w_e0[(static_cast<size_t>(ge) * FEATB + k) * C + c] : 0.0f;
+    if (c == 0) s_b0[sb][j] = p.b_e0 ? p.b_e0[static_cast<size_t>(ge) * FEATB + k] : 0.0f;
+  }
   __syncthreads();
-  const int Y = pix / p.W, X = pix - Y * p.W;
-  const int qd = (Y & 1) * 2 + (X & 1);
-  const size_t ppix = (static_cast<size_t>(slot) * (p.H >> 1) + (Y >> 1)) * (p.W >> 1) + (X >> 1);
-  const float4* src = reinterpret_cast<const float4*>(p.du1 + ppix * (4 * FEATB) + qd * FEATB);
-  float du[FEATB];
+  float wacc[8][NC], bacc[8];
 #pragma unroll
-  for (int v = 0; v < FEATB / 4; ++v) {
-    const float4 t = src[v];
-    du[4 * v + 0] = t.x; du[4 * v + 1] = t.y; du[4 * v + 2] = t.z; du[4 * v + 3] = t.w;
-  }
-  float x[MAXC];
-  for (int c = 0; c < C; ++c) {
-    const size_t gi = (static_cast<size_t>(orig) * C + c) * HW + pix;
-    const float im = p.img[gi];
-    x[c] = p.first ? __fsub_rn(__fmul_rn(im, 2.0f), 1.0f) : __fsub_rn(im, p.recon_prev[gi]);
-  }
-  float dpre[FEATB];
-  float dx[MAXC] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < 8; ++j) {
+    bacc[j] = 0.0f;
 #pragma unroll
-  for (int k = 0; k < FEATB; ++k) {
-    float a = s_b0[k];
-    for (int c = 0; c < C; ++c) a = fmaf(s_w0[k * C + c], x[c], a);
-    const float e = tanhf(a);
-    dpre[k] = du[k] * (1.0f - e * e);
-    for (int c = 0; c < C; ++c) dx[c] = fmaf(s_w0[k * C + c], dpre[k], dx[c]);
+    for (int c = 0; c < NC; ++c) wacc[j][c] = 0.0f;
   }
-  if (p.propagate) {
-    for (int c = 0; c < C; ++c) {
-      const size_t gi = (static_cast<size_t>(orig) * C + c) * HW + pix;
-      p.gacc[gi] -= dx[c];   // x_t = img - recon_{t-1}  (dist_codec.py:59)
+  const size_t img_base = (static_cast<size_t>(orig) * C + (mine ? sub : 0)) * HW;
+  const float4* du1 = reinterpret_cast<const float4*>(p.du1) + static_cast<size_t>(slot) * HW * (FEATB / 4);
+
+  int i = part * ppb + (threadIdx.x >> 2);
+  const int i_end = (part + 1) * ppb;
+  int rpix = qm.raster(i);
+  float4 da = du1[i * (FEATB / 4) + sub], db = du1[i * (FEATB / 4) + sub + 4];
+  float im = 0.0f, rp = 0.0f, ga = 0.0f;
+  if (mine) {
+    im = p.img[img_base + rpix];
+    if (!p.first) rp = p.recon_prev[img_base + rpix];
+    if (p.propagate) ga = p.gacc[img_base + rpix];
+  }
+  for (; i < i_end; i += TB_PIX) {
+    const float du[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+    const float im_c = im, rp_c = rp, ga_c = ga;
+    const size_t gi = img_base + rpix;
+    const int in = i + TB_PIX;
+    if (in < i_end) {  // next pass's loads (uniform branch)
+      rpix = qm.raster(in);
+      da = du1[in * (FEATB / 4) + sub];
+      db = du1[in * (FEATB / 4) + sub + 4];
+      if (mine) {
+        im = p.img[img_base + rpix];
+        if (!p.first) rp = p.recon_prev[img_base + rpix];
+        if (p.propagate) ga = p.gacc[img_base + rpix];
+      }
     }
-  }
-  // dW_e0[k,c] += sum_pixels dpre[k]*x[c], db[k] += sum dpre[k]
-  for (int i = threadIdx.x; i < FEATB * MAXC + FEATB; i += blockDim.x) s_acc[i] = 0.0f;
-  __syncthreads();
+    float xv = 0.0f;
+    if (mine) xv = p.first ? __fsub_rn(__fmul_rn(im_c, 2.0f), 1.0f) : __fsub_rn(im_c, rp_c);
+    float x[NC], dx[NC];
 #pragma unroll
-  for (int k = 0; k < FEATB; ++k) {
+    for (int c = 0; c < NC; ++c) {
+      x[c] = __shfl_sync(0xffffffffu, xv, lane_base + c);
+      dx[c] = 0.0f;
+    }
 #pragma unroll
-    for (int c = 0; c <= MAXC; ++c) {
-      if (c < C || c == MAXC) {
-        float v = c == MAXC ? dpre[k] : dpre[k] * x[c];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[c == MAXC ? FEATB * MAXC + k : k * MAXC + c], v);
+    for (int j = 0; j < 8; ++j) {
+      float w[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) w[c] = s_w0[sub][j][c];
+      float a = s_b0[sub][j];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) a = fmaf(w[c], x[c], a);
+      const float e = tanhf(a);
+      const float dpre = du[j] * (1.0f - e * e);
+      bacc[j] += dpre;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        dx[c] = fmaf(w[c], dpre, dx[c]);
+        wacc[j][c] = fmaf(dpre, x[c], wacc[j][c]);
+      }
+    }
+    if (p.propagate) {  // uniform
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        dx[c] += __shfl_xor_sync(0xffffffffu, dx[c], 1);
+        dx[c] += __shfl_xor_sync(0xffffffffu, dx[c], 2);
+      }
+      if (mine) {
+        float dxm = dx[0];
+#pragma unroll
+        for (int c = 1; c < NC; ++c) dxm = sub == c ? dx[c] : dxm;
+        p.gacc[gi] = ga_c - dxm;   // x_t = img - recon_{t-1}  (dist_codec.py:59)
       }
     }
   }
+  // dW_e0[k,c] += sum_pixels dpre[k]*x[c], db[k] += sum dpre[k]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = slice_channel(sub, j);
+#pragma unroll
+    for (int c = 0; c <= NC; ++c) {
+      float v = c == NC ? bacc[j] : wacc[j][c < NC ? c : 0];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) atomicAdd(&s_acc[c == NC ? FEATB * MAXC + k : k * MAXC + c], v);
+    }
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < FEATB * C; i += blockDim.x) {
-    const int k = i / C, c = i - k * C;
-    atomicAdd(p.dw_e0 + static_cast<size_t>(ge) * FEATB * C + i, s_acc[k * MAXC + c]);
+  for (int t = threadIdx.x; t < FEATB * C; t += blockDim.x) {
+    const int k = t / C, c = t - k * C;
+    atomicAdd(p.dw_e0 + static_cast<size_t>(ge) * FEATB * C + t, s_acc[k * MAXC + c]);
   }
   if (p.db_e0 && threadIdx.x < FEATB) atomicAdd(p.db_e0 + static_cast<size_t>(ge) * FEATB + threadIdx.x, s_acc[FEATB * MAXC + threadIdx.x]);
 }
@@ -448,14 +570,26 @@ int launch_bottleneck_bwd(const BottleneckBwdParams& p, cudaStream_t stream) {
 }
 int launch_tail_bwd(const TailBwdParams& p, cudaStream_t stream) {
   const int HW = p.H * p.W;
-  if (HW % TB_THREADS != 0 || p.C > MAXC) return static_cast<int>(cudaErrorInvalidValue);
-  tail_bwd_kernel<<<p.B_pad * (HW / TB_THREADS), TB_THREADS, 0, stream>>>(p);
+  if (HW % TB_THREADS != 0 || p.C > MAXC || p.C < 1) return static_cast<int>(cudaErrorInvalidValue);
+  const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TB_PIX, 148 * 6);
+  switch (p.C) {
+    case 1: tail_bwd_kernel<1><<<grid, TB_THREADS, 0, stream>>>(p); break;
+    case 2: tail_bwd_kernel<2><<<grid, TB_THREADS, 0, stream>>>(p); break;
+    case 3: tail_bwd_kernel<3><<<grid, TB_THREADS, 0, stream>>>(p); break;
+    default: tail_bwd_kernel<4><<<grid, TB_THREADS, 0, stream>>>(p); break;
+  }
   return static_cast<int>(cudaGetLastError());
 }
 int launch_head_bwd(const HeadBwdParams& p, cudaStream_t stream) {
   const int HW = p.H * p.W;
-  if (HW % TB_THREADS != 0 || p.C > MAXC) return static_cast<int>(cudaErrorInvalidValue);
-  head_bwd_kernel<<<p.B_pad * (HW / TB_THREADS), TB_THREADS, 0, stream>>>(p);
+  if (HW % TB_THREADS != 0 || p.C > MAXC || p.C < 1) return static_cast<int>(cudaErrorInvalidValue);
+  const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TB_PIX, 148 * 6);
+  switch (p.C) {
+    case 1: head_bwd_kernel<1><<<grid, TB_THREADS, 0, stream>>>(p); break;
+    case 2: head_bwd_kernel<2><<<grid, TB_THREADS, 0, stream>>>(p); break;
+    case 3: head_bwd_kernel<3><<<grid, TB_THREADS, 0, stream>>>(p); break;
+    default: head_bwd_kernel<4><<<grid, TB_THREADS, 0, stream>>>(p); break;
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -44,6 +44,7 @@ struct WgradParams {
   int n_kb;                 // total K blocks = B_pad*H*W/64
   int has_h;                // 0 at t == 0
   int n_groups, m_tiles, n_tiles_x, n_tiles_h, k_splits;
+  int dbg;                  // diagnostics only (env DRASIC_WGRAD_DBG): 1 = skip the TMA loads, 2 = skip the MMAs
 };
 
 struct BottleneckBwdParams {
@@ -62,7 +63,7 @@ struct BottleneckBwdParams {
 };
 
 struct TailBwdParams {
-  const float* d3_next;    // [B_pad,H,W,32] saved shuffled decoder ConvLSTM output of iteration t
+  const float* d3_next;    // [B_pad,H/2,W/2,128] saved decoder ConvLSTM output of iteration t (own quad-major order)
   const float* w_d4;       // [n_dec_groups][C,32]
   const float* img;        // [B,C,H,W]
   const float* recon_t;    // [B,C,H,W] reconstruction after iteration t

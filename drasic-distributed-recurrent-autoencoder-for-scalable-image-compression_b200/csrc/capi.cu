@@ -2,6 +2,7 @@
 // construction, launches.  No torch types, no allocation, no synchronisation.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/drasic_b200.h"
@@ -367,6 +368,10 @@ int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream) {
   p.n_kb = static_cast<int>(static_cast<long long>(B) * H * W / 64);
   p.has_h = a->has_h ? 1 : 0; p.n_groups = a->n_groups; p.m_tiles = 4 * Co / 128;
   p.n_tiles_x = (9 * (Cin / 64) + 3) / 4; p.n_tiles_h = (9 * (Co / 64) + 3) / 4; p.k_splits = a->k_splits;
+  {
+    static const int dbg = getenv("DRASIC_WGRAD_DBG") ? atoi(getenv("DRASIC_WGRAD_DBG")) : 0;
+    p.dbg = dbg;
+  }
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
   return cuda_fail(drasic::launch_wgrad(p, a->split != 0, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_weight launch");

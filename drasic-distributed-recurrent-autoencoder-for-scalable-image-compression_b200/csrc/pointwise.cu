@@ -126,82 +126,158 @@ __global__ void __launch_bounds__(128) bottleneck_kernel(const BottleneckParams 
 }
 
 // ------------------------------------------------------------------ K-C
+// Four lanes per pixel, eight of the 32 feature channels per lane.  Pixels are enumerated quad-major
+// (i = quad*4 + (dy*2+dx), quads row-major over H/2 x W/2), which is exactly the physical order of D3's
+// hidden state (ORDER_QUAD) and of E1's input (pixel_unshuffle): both feature tensors are addressed as
+// [(slot*HW + i)*32 + channel], so every warp-wide load / store of them is one contiguous run.
+// The two 1x1 convolutions are fp32 FMA chains (8 terms per lane, then a two-level tree over the four
+// lanes of the pixel): their rounding error is below that of the reference's own fp32 convolution.
+// The next pass's global loads are issued before the current pass is computed (software prefetch).
 constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_PIX = TAIL_THREADS / 4;  // pixels per pass
 constexpr int MAX_C = 4;
 constexpr int FEAT = 32;  // channels of the 32x32 feature map on both sides (dist_codec.py:71,101)
 
-__global__ void __launch_bounds__(TAIL_THREADS) tail_head_kernel(const TailParams p) {
-  __shared__ float s_w4[MAX_C * FEAT];
-  __shared__ float s_w0[FEAT * MAX_C];
-  __shared__ float s_b0[FEAT];
+struct QuadMap {  // quad-major pixel index -> raster pixel offset
+  int W, qw, shift;
+  __device__ __forceinline__ explicit QuadMap(int W_) : W(W_), qw(W_ >> 1) {
+    shift = (qw & (qw - 1)) == 0 ? 31 - __clz(qw) : -1;
+  }
+  __device__ __forceinline__ int raster(int i) const {
+    const int quad = i >> 2, qd = i & 3;
+    const int qy = shift >= 0 ? quad >> shift : quad / qw;
+    const int qx = quad - qy * qw;
+    return (2 * qy + (qd >> 1)) * W + 2 * qx + (qd & 1);
+  }
+};
+
+template <bool PRECISE, int NC>
+__global__ void __launch_bounds__(TAIL_THREADS, 3) tail_head_kernel(const TailParams p) {
   __shared__ double s_red[2][TAIL_THREADS / 32];
   const int HW = p.H * p.W;
-  const int blocks_per_img = HW / TAIL_THREADS;
-  const int slot = blockIdx.x / blocks_per_img;
-  const int pix = (blockIdx.x - slot * blocks_per_img) * TAIL_THREADS + threadIdx.x;
+  const int bpi = gridDim.x / p.B_pad;  // blocks per image
+  const int slot = blockIdx.x / bpi;
+  const int part = blockIdx.x - slot * bpi;
+  const int ppb = HW / bpi;             // pixels of this block (multiple of TAIL_PIX)
   const int orig = p.perm[slot];
   if (orig < 0) return;  // padding slot (uniform per block)
-  const int C = p.C;
+  constexpr int C = NC;
   const int ge = p.n_enc_groups > 1 ? find_group(p.group_img_end, p.n_enc_groups, slot) : 0;
   const int gd = p.n_dec_groups > 1 ? find_group(p.group_img_end, p.n_dec_groups, slot) : 0;
-  if (threadIdx.x < C * FEAT) {
-    if (p.mode != TAIL_INIT) s_w4[threadIdx.x] = p.w_d4[static_cast<size_t>(gd) * C * FEAT + threadIdx.x];
-    s_w0[threadIdx.x] = p.w_e0[static_cast<size_t>(ge) * FEAT * C + threadIdx.x];
+  const int sub = threadIdx.x & 3;                 // which channel slice of the pixel
+  const int lane_base = (threadIdx.x & 31) & ~3;
+  const bool has_tail = p.mode != TAIL_INIT;
+  const bool has_head = p.e1_in[0] != nullptr;
+  const bool mine = sub < C;                       // this lane owns image channel `sub` of its pixel
+  const QuadMap qm(p.W);
+
+  // weights laid out per channel slice so a lane reads its eight channels with vector loads:
+  // tail channels {4sub..4sub+3, 16+4sub..16+4sub+3}; head channels 8sub..8sub+7
+  __shared__ alignas(16) float s_w4[MAX_C][4][8];   // [c][sub][j]
+  __shared__ alignas(16) float s_w0[4][8][MAX_C];   // [sub][j][c]
+  __shared__ alignas(16) float s_b0[4][8];
+  for (int t = threadIdx.x; t < MAX_C * FEAT; t += TAIL_THREADS) {
+    const int c = t >> 5, sb = (t >> 3) & 3, j = t & 7;
+    const int kt = j < 4 ? 4 * sb + j : 16 + 4 * sb + (j - 4);
+    s_w4[c][sb][j] = (has_tail && c < C) ? p.w_d4[(static_cast<size_t>(gd) * C + c) * FEAT + kt] : 0.0f;
+    s_w0[sb][j][c] = (c < C) ? p.w_e0[(static_cast<size_t>(ge) * FEAT + 8 * sb + j) * C + c] : 0.0f;
+    if (c == 0) s_b0[sb][j] = p.b_e0 ? p.b_e0[static_cast<size_t>(ge) * FEAT + 8 * sb + j] : 0.0f;
   }
-  if (threadIdx.x < FEAT) s_b0[threadIdx.x] = p.b_e0 ? p.b_e0[static_cast<size_t>(ge) * FEAT + threadIdx.x] : 0.0f;
   __syncthreads();
 
-  const int Y = pix / p.W, X = pix - Y * p.W;
-  float x[MAX_C];
+  const size_t img_base = (static_cast<size_t>(orig) * C + (mine ? sub : 0)) * HW;
+  const float4* d3 = reinterpret_cast<const float4*>(p.d3_next) + static_cast<size_t>(slot) * HW * (FEAT / 4);
+  const bool step_mode = p.mode == TAIL_STEP;
+
+  int i = part * ppb + (threadIdx.x >> 2);
+  const int i_end = (part + 1) * ppb;
+  // prefetch registers
+  float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
+  float im = 0.0f, rp = 0.0f;
+  int rpix = qm.raster(i);
+  if (has_tail) { fa = d3[i * (FEAT / 4) + sub]; fb = d3[i * (FEAT / 4) + sub + 4]; }
+  if (mine) {
+    im = p.img[img_base + rpix];
+    if (step_mode) rp = p.recon_prev[img_base + rpix];
+  }
+
   double l_abs = 0.0, l_sq = 0.0;
-  if (p.mode == TAIL_INIT) {
-    // x = img * 2 - 1   (dist_codec.py:38)
-    for (int c = 0; c < C; ++c) {
-      const float im = p.img[(static_cast<size_t>(orig) * C + c) * HW + pix];
-      x[c] = __fsub_rn(__fmul_rn(im, 2.0f), 1.0f);
-    }
-  } else {
-    float f[FEAT];
-    const float4* src = reinterpret_cast<const float4*>(p.d3_next + (static_cast<size_t>(slot) * HW + pix) * FEAT);
-#pragma unroll
-    for (int v = 0; v < FEAT / 4; ++v) {
-      const float4 t = src[v];
-      f[4 * v + 0] = t.x; f[4 * v + 1] = t.y; f[4 * v + 2] = t.z; f[4 * v + 3] = t.w;
-    }
-    for (int c = 0; c < C; ++c) {
-      float d;
-      if (p.precise) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < FEAT; ++k) acc = fma(static_cast<double>(s_w4[c * FEAT + k]), static_cast<double>(f[k]), acc);
-        d = tanhf(static_cast<float>(acc));
-      } else {
-        float acc = 0.0f;
-#pragma unroll
-        for (int k = 0; k < FEAT; ++k) acc = fmaf(s_w4[c * FEAT + k], f[k], acc);
-        d = tanh_fast_pw(acc);
+  for (; i < i_end; i += TAIL_PIX) {
+    const float f[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+    const float im_c = im, rp_c = rp;
+    const size_t gi = img_base + rpix;
+    const int in = i + TAIL_PIX;
+    if (in < i_end) {  // issue the next pass's loads now (uniform branch)
+      rpix = qm.raster(in);
+      if (has_tail) { fa = d3[in * (FEAT / 4) + sub]; fb = d3[in * (FEAT / 4) + sub + 4]; }
+      if (mine) {
+        im = p.img[img_base + rpix];
+        if (step_mode) rp = p.recon_prev[img_base + rpix];
       }
-      const size_t gi = (static_cast<size_t>(orig) * C + c) * HW + pix;
-      if (p.dec_out) p.dec_out[gi] = d;  // raw decoder output (saved for backward)
-      float r;
-      if (p.mode == TAIL_FIRST) {
-        d = __fadd_rn(d, 1.0f) / 2.0f;   // (decoded + 1) / 2   (dist_codec.py:56)
-        r = __fadd_rn(0.0f, d);          // reconstructed = 0 + decoded (dist_codec.py:39,57)
-      } else {
-        r = __fadd_rn(p.recon_prev[gi], d);
-      }
-      p.recon_out[gi] = r;
-      const float im = p.img[gi];
-      const float e = __fsub_rn(r, im);
-      if (p.loss_kind == LOSS_MAE) l_abs += static_cast<double>(fabsf(e));
-      else if (p.loss_kind == LOSS_MSE) l_abs += static_cast<double>(e) * e;
-      else {  // bce with torch's log clamp at -100
-        const float lr = fmaxf(logf(r), -100.0f), l1r = fmaxf(logf(1.0f - r), -100.0f);
-        l_abs += -static_cast<double>(im * lr + (1.0f - im) * l1r);
-      }
-      l_sq += static_cast<double>(e) * e;
-      x[c] = __fsub_rn(im, r);  // x = img - reconstructed   (dist_codec.py:59)
     }
+    float xv = 0.0f;
+    if (!has_tail) {
+      // x = img * 2 - 1   (dist_codec.py:38)
+      if (mine) xv = __fsub_rn(__fmul_rn(im_c, 2.0f), 1.0f);
+    } else {
+      float acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(s_w4[c][sub][j], f[j], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        acc[c] = a;
+      }
+      if (mine) {
+        float pre = acc[0];
+#pragma unroll
+        for (int c = 1; c < NC; ++c) pre = sub == c ? acc[c] : pre;
+        float d = PRECISE ? tanhf(pre) : tanh_fast_pw(pre);
+        if (p.dec_out) p.dec_out[gi] = d;  // raw decoder output (saved for backward)
+        float r;
+        if (!step_mode) {
+          d = __fadd_rn(d, 1.0f) / 2.0f;   // (decoded + 1) / 2   (dist_codec.py:56)
+          r = __fadd_rn(0.0f, d);          // reconstructed = 0 + decoded (dist_codec.py:39,57)
+        } else {
+          r = __fadd_rn(rp_c, d);
+        }
+        p.recon_out[gi] = r;
+        const float e = __fsub_rn(r, im_c);
+        if (p.loss_kind == LOSS_MAE) l_abs += static_cast<double>(fabsf(e));
+        else if (p.loss_kind == LOSS_MSE) l_abs += static_cast<double>(e) * e;
+        else {  // bce with torch's log clamp at -100
+          const float lr = fmaxf(logf(r), -100.0f), l1r = fmaxf(logf(1.0f - r), -100.0f);
+          l_abs += -static_cast<double>(im_c * lr + (1.0f - im_c) * l1r);
+        }
+        l_sq += static_cast<double>(e) * e;
+        xv = __fsub_rn(im_c, r);  // x = img - reconstructed   (dist_codec.py:59)
+      }
+    }
+    if (!has_head) continue;  // last iteration: no next encoder pass (uniform)
+    // encoder head + pixel_unshuffle(2): E1 input [(slot*HW + i)*32 + k]
+    float x[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) x[c] = __shfl_sync(0xffffffffu, xv, lane_base + c);
+    alignas(16) __half hi[8];
+    alignas(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = s_b0[sub][j];
+#pragma unroll
+      for (int c = NC - 1; c >= 0; --c) a = fmaf(s_w0[sub][j][c], x[c], a);
+      float e = PRECISE ? tanhf(a) : tanh_fast_pw(a);
+      e *= ACT_SCALE;
+      hi[j] = __float2half_rn(e);
+      lo[j] = __float2half_rn(e - __half2float(hi[j]));
+    }
+    const size_t off = (static_cast<size_t>(slot) * HW + i) * FEAT + 8 * sub;
+    *reinterpret_cast<uint4*>(p.e1_in[0] + off) = *reinterpret_cast<const uint4*>(hi);
+    if (p.split) *reinterpret_cast<uint4*>(p.e1_in[1] + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+
+  if (has_tail) {
     // block reduction of the loss terms -> one fp64 atomic pair per block
     for (int o = 16; o > 0; o >>= 1) {
       l_abs += __shfl_xor_sync(0xffffffffu, l_abs, o);
@@ -218,38 +294,6 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_head_kernel(const TailParam
       atomicAdd(&p.loss_acc[0], a);
       atomicAdd(&p.loss_acc[1], b);
     }
-  }
-
-  if (p.e1_in[0] == nullptr) return;  // last iteration: no next encoder pass
-  // encoder head + pixel_unshuffle(2): E1 input [B,H/2,W/2,4*FEAT], physical channel q*FEAT + k
-  alignas(16) __half hi[FEAT];
-  alignas(16) __half lo[FEAT];
-#pragma unroll
-  for (int k = 0; k < FEAT; ++k) {
-    float e;
-    if (p.precise) {
-      double acc = 0.0;
-      for (int c = 0; c < C; ++c) acc = fma(static_cast<double>(s_w0[k * C + c]), static_cast<double>(x[c]), acc);
-      e = tanhf(static_cast<float>(acc + static_cast<double>(s_b0[k])));
-    } else {
-      float acc = s_b0[k];
-      for (int c = 0; c < C; ++c) acc = fmaf(s_w0[k * C + c], x[c], acc);
-      e = tanh_fast_pw(acc);
-    }
-    e *= ACT_SCALE;
-    hi[k] = __float2half_rn(e);
-    lo[k] = __float2half_rn(e - __half2float(hi[k]));
-  }
-  const int qd = (Y & 1) * 2 + (X & 1);
-  const size_t npix = (static_cast<size_t>(slot) * (p.H >> 1) + (Y >> 1)) * (p.W >> 1) + (X >> 1);
-  const size_t off = npix * (4 * FEAT) + qd * FEAT;
-  uint4* dh = reinterpret_cast<uint4*>(p.e1_in[0] + off);
-#pragma unroll
-  for (int v = 0; v < FEAT / 8; ++v) dh[v] = reinterpret_cast<const uint4*>(hi)[v];
-  if (p.split) {
-    uint4* dl = reinterpret_cast<uint4*>(p.e1_in[1] + off);
-#pragma unroll
-    for (int v = 0; v < FEAT / 8; ++v) dl[v] = reinterpret_cast<const uint4*>(lo)[v];
   }
 }
 
@@ -314,10 +358,29 @@ int launch_bottleneck(const BottleneckParams& p, cudaStream_t stream) {
   return static_cast<int>(cudaGetLastError());
 }
 
+// blocks per image: enough blocks to fill the machine a few times over, each a whole number of passes
+int pixel_blocks_per_image(int B_pad, int HW, int pix_per_pass, int min_blocks) {
+  const int max_bpi = HW / pix_per_pass;
+  int bpi = 1;
+  while (bpi < max_bpi && static_cast<long long>(B_pad) * bpi < min_blocks) bpi *= 2;
+  while (max_bpi % bpi) bpi /= 2;
+  return bpi;
+}
+
 int launch_tail_head(const TailParams& p, cudaStream_t stream) {
   const int HW = p.H * p.W;
-  if (HW % TAIL_THREADS != 0 || p.C > MAX_C) return static_cast<int>(cudaErrorInvalidValue);
-  tail_head_kernel<<<p.B_pad * (HW / TAIL_THREADS), TAIL_THREADS, 0, stream>>>(p);
+  if (HW % TAIL_THREADS != 0 || p.C > MAX_C || p.C < 1 || ((p.H | p.W) & 1)) return static_cast<int>(cudaErrorInvalidValue);
+  const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TAIL_PIX, 148 * 12);
+#define DRASIC_TAIL_LAUNCH(NC)                                                            \
+  if (p.precise) tail_head_kernel<true, NC><<<grid, TAIL_THREADS, 0, stream>>>(p);        \
+  else tail_head_kernel<false, NC><<<grid, TAIL_THREADS, 0, stream>>>(p)
+  switch (p.C) {
+    case 1: DRASIC_TAIL_LAUNCH(1); break;
+    case 2: DRASIC_TAIL_LAUNCH(2); break;
+    case 3: DRASIC_TAIL_LAUNCH(3); break;
+    default: DRASIC_TAIL_LAUNCH(4); break;
+  }
+#undef DRASIC_TAIL_LAUNCH
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -30,7 +30,7 @@ struct BottleneckParams {
 };
 
 struct TailParams {
-  const float* d3_next;     // [B_pad, H, W, 32] fp32: shuffled last decoder ConvLSTM h
+  const float* d3_next;     // [B_pad, H/2, W/2, 4*32] fp32: last decoder ConvLSTM h in its own (quad-major) order
   const float* w_d4;        // [n_dec_groups][C, 32]
   const float* w_e0;        // [n_enc_groups][32, C]
   const float* b_e0;        // nullable: [n_enc_groups][32]
@@ -50,6 +50,7 @@ struct TailParams {
 
 int launch_bottleneck(const BottleneckParams& p, cudaStream_t stream);
 int launch_tail_head(const TailParams& p, cudaStream_t stream);
+int pixel_blocks_per_image(int B_pad, int HW, int pix_per_pass, int min_blocks);
 int launch_conv1x1(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout,
                    int HW, int act, cudaStream_t stream);
 int launch_quantize(const float* x, const float* u, float* y, size_t n, cudaStream_t stream);

@@ -144,6 +144,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             n0 = kb * p.kbn; y0 = 0; x0 = 0;
           }
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg == 1) {
+            ptx::mbar_arrive(&full_bar[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           ptx::mbar_expect_tx(&full_bar[stage], bytes);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           const uint32_t a_lo = a_hi + C::A_BYTES;
           const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * C::A_BYTES;
           const uint32_t b_lo = b_hi + C::B_BYTES;
+          if (p.dbg != 2)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {            // 4 x UMMA_K(16 pixels) per 64-pixel K block
             const uint32_t koff = k * 16 * 128;    // 16 K rows of 128 bytes

@@ -19,7 +19,7 @@ ENC_LAYERS = (('E1', 128, 128, 2, B.ORDER_QUAD, B.ORDER_IDENT, B.NEXT_DOWN, 0),
               ('E3', 512, 128, 8, B.ORDER_QUAD, B.ORDER_IDENT, B.NEXT_SAME, 1))
 DEC_LAYERS = (('D1', 128, 512, 8, B.ORDER_IDENT, B.ORDER_QUAD, B.NEXT_UP, 0),
               ('D2', 128, 512, 4, B.ORDER_IDENT, B.ORDER_QUAD, B.NEXT_UP, 0),
-              ('D3', 128, 128, 2, B.ORDER_IDENT, B.ORDER_QUAD, B.NEXT_UP, 1))
+              ('D3', 128, 128, 2, B.ORDER_IDENT, B.ORDER_QUAD, B.NEXT_SAME, 1))  # fp32 copy in D3's own quad-major order for the tail
 ENC_IDX = {'E1': 2, 'E2': 4, 'E3': 6}   # nn.Sequential indices, dist_codec.py:70-86
 DEC_IDX = {'D1': 1, 'D2': 3, 'D3': 5}   # dist_codec.py:88-104
 
@@ -495,12 +495,13 @@ class CodecEngine(object):
             Lb, wb = A[ly.name], WB[ly.name]
             n_pix = Bp * ly.h * ly.w
             wb['amax'].zero_()
-            B.check(L.drasic_lstm_bwd_pointwise(P(Lb['gates'][t]), self.gsplit, P(Lb['c'][t]), P(Lb['c'][t - 1]) if t > 0 else None,
-                                                P(wb['dh_above']), P(wb['dh_rec']) if t < T - 1 else None, P(wb['dc']),
-                                                1 if t < T - 1 else 0, P(wb['dgates']), P(wb['amax']), n_pix, ly.co,
-                                                stream), 'lstm_bwd_pointwise')
-            B.check(L.drasic_convert_scale(P(wb['dgates']), P(wb['dg_hi']), P(wb['dg_lo']), P(wb['amax']), P(wb['inv']),
-                                           n_pix * 4 * ly.co, stream), 'convert_scale')
+            self._timed('lstm_bwd', 0.0, lambda: B.check(L.drasic_lstm_bwd_pointwise(
+                P(Lb['gates'][t]), self.gsplit, P(Lb['c'][t]), P(Lb['c'][t - 1]) if t > 0 else None,
+                P(wb['dh_above']), P(wb['dh_rec']) if t < T - 1 else None, P(wb['dc']),
+                1 if t < T - 1 else 0, P(wb['dgates']), P(wb['amax']), n_pix, ly.co, stream), 'lstm_bwd_pointwise'))
+            self._timed('convert_scale', 0.0, lambda: B.check(L.drasic_convert_scale(
+                P(wb['dgates']), P(wb['dg_hi']), P(wb['dg_lo']), P(wb['amax']), P(wb['inv']),
+                n_pix * 4 * ly.co, stream), 'convert_scale'))
             hi, lo, inv = dpk[ly.name]
             a = B.DgradArgs()
             a.dg_hi, a.dg_lo, a.w_hi, a.w_lo = P(wb['dg_hi']), P(wb['dg_lo']), P(hi), P(lo)
