@@ -3,6 +3,7 @@
 // fp16 operand conversion for the tensor-core dgrad / wgrad GEMMs, weight (un)packing for those GEMMs
 // and the backward of the fused bottleneck and tail/head kernels (pointwise.cu).
 #include "backward.h"
+#include "pixel_stream.cuh"
 #include "pointwise.h"
 
 namespace drasic {
@@ -324,27 +325,36 @@ __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdPa
     for (int j = 0; j < 8; ++j) wacc[c][j] = 0.0f;
   const float gain = p.first ? 0.5f : 1.0f;
   const size_t img_base = (static_cast<size_t>(orig) * C + (mine ? sub : 0)) * HW;
-  const float4* d3 = reinterpret_cast<const float4*>(p.d3_next) + static_cast<size_t>(slot) * HW * (FEATB / 4);
+  __shared__ alignas(128) float4 s_feat[TB_THREADS / 32][4][64];
+  __shared__ uint64_t s_bar[TB_THREADS / 32][4];
+  const int warp = threadIdx.x >> 5;
+  const int n_pass = ppb / TB_PIX;
+  const int i_warp = part * ppb + warp * (ppb / (TB_THREADS / 32));
+  WarpStream<1, 4> ws;
+  ws.buf = &s_feat[warp][0][0];
+  ws.bar = &s_bar[warp][0];
+  ws.src = reinterpret_cast<const char*>(p.d3_next) + (static_cast<size_t>(slot) * HW + i_warp) * FEATB * sizeof(float);
+  ws.n = n_pass;
+  ws.start(lane);
 
-  int i = part * ppb + (threadIdx.x >> 2);
-  const int i_end = (part + 1) * ppb;
+  int i = i_warp + (lane >> 2);
   int rpix = qm.raster(i);
-  float4 fa = d3[i * (FEATB / 4) + sub], fb = d3[i * (FEATB / 4) + sub + 4];
   float r = 0.0f, im = 0.0f, ga = 0.0f;
   if (mine) {
     r = p.recon_t[img_base + rpix];
     im = p.img[img_base + rpix];
     if (p.has_acc) ga = p.gacc[img_base + rpix];
   }
-  for (; i < i_end; i += TB_PIX) {
+  for (int pass = 0; pass < n_pass; ++pass, i += 8) {
+    float4 fa, fb;
+    ws.wait(pass);
+    ws.read(pass, 0, lane, fa, fb);
+    ws.release(pass, lane);
     const float f[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
     const float r_c = r, im_c = im, ga_c = ga;
     const size_t gi = img_base + rpix;
-    const int in = i + TB_PIX;
-    if (in < i_end) {  // next pass's loads (uniform branch)
-      rpix = qm.raster(in);
-      fa = d3[in * (FEATB / 4) + sub];
-      fb = d3[in * (FEATB / 4) + sub + 4];
+    if (pass + 1 < n_pass) {  // next pass's small loads (uniform branch)
+      rpix = qm.raster(i + 8);
       if (mine) {
         r = p.recon_t[img_base + rpix];
         im = p.img[img_base + rpix];
@@ -445,27 +455,36 @@ __global__ void __launch_bounds__(TB_THREADS, 3) head_bwd_kernel(const HeadBwdPa
     for (int c = 0; c < NC; ++c) wacc[j][c] = 0.0f;
   }
   const size_t img_base = (static_cast<size_t>(orig) * C + (mine ? sub : 0)) * HW;
-  const float4* du1 = reinterpret_cast<const float4*>(p.du1) + static_cast<size_t>(slot) * HW * (FEATB / 4);
+  __shared__ alignas(128) float4 s_feat[TB_THREADS / 32][4][64];
+  __shared__ uint64_t s_bar[TB_THREADS / 32][4];
+  const int warp = threadIdx.x >> 5;
+  const int n_pass = ppb / TB_PIX;
+  const int i_warp = part * ppb + warp * (ppb / (TB_THREADS / 32));
+  WarpStream<1, 4> ws;
+  ws.buf = &s_feat[warp][0][0];
+  ws.bar = &s_bar[warp][0];
+  ws.src = reinterpret_cast<const char*>(p.du1) + (static_cast<size_t>(slot) * HW + i_warp) * FEATB * sizeof(float);
+  ws.n = n_pass;
+  ws.start(lane);
 
-  int i = part * ppb + (threadIdx.x >> 2);
-  const int i_end = (part + 1) * ppb;
+  int i = i_warp + (lane >> 2);
   int rpix = qm.raster(i);
-  float4 da = du1[i * (FEATB / 4) + sub], db = du1[i * (FEATB / 4) + sub + 4];
   float im = 0.0f, rp = 0.0f, ga = 0.0f;
   if (mine) {
     im = p.img[img_base + rpix];
     if (!p.first) rp = p.recon_prev[img_base + rpix];
     if (p.propagate) ga = p.gacc[img_base + rpix];
   }
-  for (; i < i_end; i += TB_PIX) {
+  for (int pass = 0; pass < n_pass; ++pass, i += 8) {
+    float4 da, db;
+    ws.wait(pass);
+    ws.read(pass, 0, lane, da, db);
+    ws.release(pass, lane);
     const float du[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
     const float im_c = im, rp_c = rp, ga_c = ga;
     const size_t gi = img_base + rpix;
-    const int in = i + TB_PIX;
-    if (in < i_end) {  // next pass's loads (uniform branch)
-      rpix = qm.raster(in);
-      da = du1[in * (FEATB / 4) + sub];
-      db = du1[in * (FEATB / 4) + sub + 4];
+    if (pass + 1 < n_pass) {  // next pass's small loads (uniform branch)
+      rpix = qm.raster(i + 8);
       if (mine) {
         im = p.img[img_base + rpix];
         if (!p.first) rp = p.recon_prev[img_base + rpix];

@@ -10,6 +10,7 @@
 // The 1x1 convolutions here are a few hundred MACs per pixel: CUDA-core work. In precise mode their
 // dot products accumulate in fp64 so this side adds at most one rounding to the reference result.
 #include "kernels.h"
+#include "pixel_stream.cuh"
 #include "pointwise.h"
 
 namespace drasic {
@@ -151,24 +152,31 @@ struct QuadMap {  // quad-major pixel index -> raster pixel offset
   }
 };
 
+constexpr int TAIL_U = 2;        // pixels per lane per pass (independent chains interleave)
+constexpr int TAIL_STAGES = 2;   // chunks of 16 pixels (2 KB) in flight per warp
+
 template <bool PRECISE, int NC>
-__global__ void __launch_bounds__(TAIL_THREADS, 3) tail_head_kernel(const TailParams p) {
+__global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailParams p) {
+  constexpr int U = TAIL_U;
+  using Stream = WarpStream<U, TAIL_STAGES>;
   __shared__ double s_red[2][TAIL_THREADS / 32];
   const int HW = p.H * p.W;
   const int bpi = gridDim.x / p.B_pad;  // blocks per image
   const int slot = blockIdx.x / bpi;
   const int part = blockIdx.x - slot * bpi;
-  const int ppb = HW / bpi;             // pixels of this block (multiple of TAIL_PIX)
+  const int ppb = HW / bpi;             // pixels of this block (multiple of TAIL_PIX * U)
   const int orig = p.perm[slot];
   if (orig < 0) return;  // padding slot (uniform per block)
   constexpr int C = NC;
   const int ge = p.n_enc_groups > 1 ? find_group(p.group_img_end, p.n_enc_groups, slot) : 0;
   const int gd = p.n_dec_groups > 1 ? find_group(p.group_img_end, p.n_dec_groups, slot) : 0;
   const int sub = threadIdx.x & 3;                 // which channel slice of the pixel
-  const int lane_base = (threadIdx.x & 31) & ~3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane_base = lane & ~3;
   const bool has_tail = p.mode != TAIL_INIT;
   const bool has_head = p.e1_in[0] != nullptr;
   const bool mine = sub < C;                       // this lane owns image channel `sub` of its pixel
+  const bool step_mode = p.mode == TAIL_STEP;
   const QuadMap qm(p.W);
 
   // weights laid out per channel slice so a lane reads its eight channels with vector loads:
@@ -185,96 +193,146 @@ __global__ void __launch_bounds__(TAIL_THREADS, 3) tail_head_kernel(const TailPa
   }
   __syncthreads();
 
-  const size_t img_base = (static_cast<size_t>(orig) * C + (mine ? sub : 0)) * HW;
-  const float4* d3 = reinterpret_cast<const float4*>(p.d3_next) + static_cast<size_t>(slot) * HW * (FEAT / 4);
-  const bool step_mode = p.mode == TAIL_STEP;
+  // each warp walks its own contiguous run of pixels, 8*U per pass; D3's h streams through shared memory
+  __shared__ alignas(128) float4 s_feat[TAIL_THREADS / 32][TAIL_STAGES][Stream::CHUNK_F4];
+  __shared__ uint64_t s_bar[TAIL_THREADS / 32][TAIL_STAGES];
+  const int n_pass = ppb / (TAIL_PIX * U);
+  const int i_warp = part * ppb + warp * (ppb / (TAIL_THREADS / 32));
+  Stream ws;
+  ws.buf = &s_feat[warp][0][0];
+  ws.bar = &s_bar[warp][0];
+  ws.src = reinterpret_cast<const char*>(p.d3_next) + (static_cast<size_t>(slot) * HW + i_warp) * FEAT * sizeof(float);
+  ws.n = has_tail ? n_pass : 0;
+  ws.start(lane);
 
-  int i = part * ppb + (threadIdx.x >> 2);
-  const int i_end = (part + 1) * ppb;
-  // prefetch registers
-  float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
-  float im = 0.0f, rp = 0.0f;
-  int rpix = qm.raster(i);
-  if (has_tail) { fa = d3[i * (FEAT / 4) + sub]; fb = d3[i * (FEAT / 4) + sub + 4]; }
-  if (mine) {
-    im = p.img[img_base + rpix];
-    if (step_mode) rp = p.recon_prev[img_base + rpix];
+  const size_t img_base = (static_cast<size_t>(orig) * C + (mine ? sub : 0)) * HW;
+  // register prefetch of the small per-channel loads
+  int i0 = i_warp + (lane >> 2);
+  int rpix[U];
+  float im[U], rp[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    rpix[u] = qm.raster(i0 + 8 * u);
+    im[u] = rp[u] = 0.0f;
+    if (mine) {
+      im[u] = p.img[img_base + rpix[u]];
+      if (step_mode) rp[u] = p.recon_prev[img_base + rpix[u]];
+    }
   }
 
   double l_abs = 0.0, l_sq = 0.0;
-  for (; i < i_end; i += TAIL_PIX) {
-    const float f[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
-    const float im_c = im, rp_c = rp;
-    const size_t gi = img_base + rpix;
-    const int in = i + TAIL_PIX;
-    if (in < i_end) {  // issue the next pass's loads now (uniform branch)
-      rpix = qm.raster(in);
-      if (has_tail) { fa = d3[in * (FEAT / 4) + sub]; fb = d3[in * (FEAT / 4) + sub + 4]; }
-      if (mine) {
-        im = p.img[img_base + rpix];
-        if (step_mode) rp = p.recon_prev[img_base + rpix];
+  for (int pass = 0; pass < n_pass; ++pass, i0 += 8 * U) {
+    float f[U][8];
+    if (has_tail) {
+      ws.wait(pass);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float4 fa, fb;
+        ws.read(pass, u, lane, fa, fb);
+        f[u][0] = fa.x; f[u][1] = fa.y; f[u][2] = fa.z; f[u][3] = fa.w;
+        f[u][4] = fb.x; f[u][5] = fb.y; f[u][6] = fb.z; f[u][7] = fb.w;
+      }
+      ws.release(pass, lane);
+    }
+    float im_c[U], rp_c[U];
+    size_t gi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      im_c[u] = im[u]; rp_c[u] = rp[u];
+      gi[u] = img_base + rpix[u];
+    }
+    if (pass + 1 < n_pass) {  // issue the next pass's loads now (uniform branch)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rpix[u] = qm.raster(i0 + 8 * U + 8 * u);
+        if (mine) {
+          im[u] = p.img[img_base + rpix[u]];
+          if (step_mode) rp[u] = p.recon_prev[img_base + rpix[u]];
+        }
       }
     }
-    float xv = 0.0f;
+    float xv[U];
     if (!has_tail) {
       // x = img * 2 - 1   (dist_codec.py:38)
-      if (mine) xv = __fsub_rn(__fmul_rn(im_c, 2.0f), 1.0f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) xv[u] = mine ? __fsub_rn(__fmul_rn(im_c[u], 2.0f), 1.0f) : 0.0f;
     } else {
-      float acc[NC];
+      float pre[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) pre[u] = 0.0f;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        float a = 0.0f;
+        float w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a = fmaf(s_w4[c][sub][j], f[j], a);
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        acc[c] = a;
+        for (int j = 0; j < 8; ++j) w[j] = s_w4[c][sub][j];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float a = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a = fmaf(w[j], f[u][j], a);
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          pre[u] = sub == c ? a : pre[u];
+        }
       }
-      if (mine) {
-        float pre = acc[0];
 #pragma unroll
-        for (int c = 1; c < NC; ++c) pre = sub == c ? acc[c] : pre;
-        float d = PRECISE ? tanhf(pre) : tanh_fast_pw(pre);
-        if (p.dec_out) p.dec_out[gi] = d;  // raw decoder output (saved for backward)
-        float r;
-        if (!step_mode) {
-          d = __fadd_rn(d, 1.0f) / 2.0f;   // (decoded + 1) / 2   (dist_codec.py:56)
-          r = __fadd_rn(0.0f, d);          // reconstructed = 0 + decoded (dist_codec.py:39,57)
-        } else {
-          r = __fadd_rn(rp_c, d);
+      for (int u = 0; u < U; ++u) {
+        xv[u] = 0.0f;
+        if (mine) {
+          float d = PRECISE ? tanhf(pre[u]) : tanh_fast_pw(pre[u]);
+          if (p.dec_out) p.dec_out[gi[u]] = d;  // raw decoder output (saved for backward)
+          float r;
+          if (!step_mode) {
+            d = __fadd_rn(d, 1.0f) / 2.0f;   // (decoded + 1) / 2   (dist_codec.py:56)
+            r = __fadd_rn(0.0f, d);          // reconstructed = 0 + decoded (dist_codec.py:39,57)
+          } else {
+            r = __fadd_rn(rp_c[u], d);
+          }
+          p.recon_out[gi[u]] = r;
+          const float e = __fsub_rn(r, im_c[u]);
+          if (p.loss_kind == LOSS_MAE) l_abs += static_cast<double>(fabsf(e));
+          else if (p.loss_kind == LOSS_MSE) l_abs += static_cast<double>(e) * e;
+          else {  // bce with torch's log clamp at -100
+            const float lr = fmaxf(logf(r), -100.0f), l1r = fmaxf(logf(1.0f - r), -100.0f);
+            l_abs += -static_cast<double>(im_c[u] * lr + (1.0f - im_c[u]) * l1r);
+          }
+          l_sq += static_cast<double>(e) * e;
+          xv[u] = __fsub_rn(im_c[u], r);  // x = img - reconstructed   (dist_codec.py:59)
         }
-        p.recon_out[gi] = r;
-        const float e = __fsub_rn(r, im_c);
-        if (p.loss_kind == LOSS_MAE) l_abs += static_cast<double>(fabsf(e));
-        else if (p.loss_kind == LOSS_MSE) l_abs += static_cast<double>(e) * e;
-        else {  // bce with torch's log clamp at -100
-          const float lr = fmaxf(logf(r), -100.0f), l1r = fmaxf(logf(1.0f - r), -100.0f);
-          l_abs += -static_cast<double>(im_c * lr + (1.0f - im_c) * l1r);
-        }
-        l_sq += static_cast<double>(e) * e;
-        xv = __fsub_rn(im_c, r);  // x = img - reconstructed   (dist_codec.py:59)
       }
     }
     if (!has_head) continue;  // last iteration: no next encoder pass (uniform)
     // encoder head + pixel_unshuffle(2): E1 input [(slot*HW + i)*32 + k]
-    float x[NC];
+    float x[U][NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) x[c] = __shfl_sync(0xffffffffu, xv, lane_base + c);
-    alignas(16) __half hi[8];
-    alignas(16) __half lo[8];
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) x[u][c] = __shfl_sync(0xffffffffu, xv[u], lane_base + c);
+    alignas(16) __half hi[U][8];
+    alignas(16) __half lo[U][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float a = s_b0[sub][j];
+      float w[NC];
 #pragma unroll
-      for (int c = NC - 1; c >= 0; --c) a = fmaf(s_w0[sub][j][c], x[c], a);
-      float e = PRECISE ? tanhf(a) : tanh_fast_pw(a);
-      e *= ACT_SCALE;
-      hi[j] = __float2half_rn(e);
-      lo[j] = __float2half_rn(e - __half2float(hi[j]));
+      for (int c = 0; c < NC; ++c) w[c] = s_w0[sub][j][c];
+      const float b = s_b0[sub][j];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float a = b;
+#pragma unroll
+        for (int c = NC - 1; c >= 0; --c) a = fmaf(w[c], x[u][c], a);
+        float e = PRECISE ? tanhf(a) : tanh_fast_pw(a);
+        e *= ACT_SCALE;
+        hi[u][j] = __float2half_rn(e);
+        lo[u][j] = __float2half_rn(e - __half2float(hi[u][j]));
+      }
     }
-    const size_t off = (static_cast<size_t>(slot) * HW + i) * FEAT + 8 * sub;
-    *reinterpret_cast<uint4*>(p.e1_in[0] + off) = *reinterpret_cast<const uint4*>(hi);
-    if (p.split) *reinterpret_cast<uint4*>(p.e1_in[1] + off) = *reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t off = (static_cast<size_t>(slot) * HW + i0 + 8 * u) * FEAT + 8 * sub;
+      *reinterpret_cast<uint4*>(p.e1_in[0] + off) = *reinterpret_cast<const uint4*>(hi[u]);
+      if (p.split) *reinterpret_cast<uint4*>(p.e1_in[1] + off) = *reinterpret_cast<const uint4*>(lo[u]);
+    }
   }
 
   if (has_tail) {
@@ -370,7 +428,7 @@ int pixel_blocks_per_image(int B_pad, int HW, int pix_per_pass, int min_blocks) 
 int launch_tail_head(const TailParams& p, cudaStream_t stream) {
   const int HW = p.H * p.W;
   if (HW % TAIL_THREADS != 0 || p.C > MAX_C || p.C < 1 || ((p.H | p.W) & 1)) return static_cast<int>(cudaErrorInvalidValue);
-  const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TAIL_PIX, 148 * 12);
+  const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TAIL_PIX * TAIL_U, 148 * 8);
 #define DRASIC_TAIL_LAUNCH(NC)                                                            \
   if (p.precise) tail_head_kernel<true, NC><<<grid, TAIL_THREADS, 0, stream>>>(p);        \
   else tail_head_kernel<false, NC><<<grid, TAIL_THREADS, 0, stream>>>(p)
