@@ -97,7 +97,7 @@ int launch_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int 
                               unsigned int* scratch_amax, cudaStream_t stream);
 int launch_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,
                         float* dw_h, cudaStream_t stream);
-int launch_wgrad(const WgradParams& p, bool split, int num_sms, cudaStream_t stream);
+int launch_wgrad(const WgradParams& p, bool split, bool pair, int num_sms, cudaStream_t stream);
 int launch_bottleneck_bwd(const BottleneckBwdParams& p, cudaStream_t stream);
 int launch_tail_bwd(const TailBwdParams& p, cudaStream_t stream);
 int launch_head_bwd(const HeadBwdParams& p, cudaStream_t stream);

@@ -183,8 +183,12 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
     if (a->split && (rc = make_act_map(&p.tm_h[1], a->h_lo, B, H, W, Co, bw, bh, bn))) return rc;
   }
   const int K = 9 * (Cin + Co);
-  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * 4 * Co, K, a->block_n))) return rc;
-  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * 4 * Co, K, a->block_n))) return rc;
+  const bool pair = a->cta_pair != 0;
+  if (pair && (a->block_n != 256 || (static_cast<long long>(B) * H * W / 128) % 2))
+    return fail(DRASIC_ERR_INVALID, "convlstm_fwd: cta_pair needs block_n == 256 and an even number of M tiles");
+  const int w_box_rows = pair ? a->block_n / 2 : a->block_n;   // each CTA of a pair stages half of the N tile
+  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * 4 * Co, K, w_box_rows))) return rc;
+  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * 4 * Co, K, w_box_rows))) return rc;
   p.c_state = a->c_state;
   p.c_prev = a->c_prev;
   p.gates_out = a->gates_out;
@@ -208,7 +212,7 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   p.group_mtile_end = a->group_mtile_end;
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
-  return cuda_fail(drasic::launch_convlstm_gates(p, a->split != 0, a->block_n, sms, static_cast<cudaStream_t>(stream)),
+  return cuda_fail(drasic::launch_convlstm_gates(p, a->split != 0, a->block_n, pair, sms, static_cast<cudaStream_t>(stream)),
                    "convlstm_fwd launch");
 }
 
@@ -325,8 +329,11 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   const int Cg = 4 * Co, Nout = Cin + Co, K = 9 * Cg;
   if ((rc = make_act_map(&p.tm_x[0], a->dg_hi, B, H, W, Cg, bw, bh, bn))) return rc;
   if (a->split && (rc = make_act_map(&p.tm_x[1], a->dg_lo, B, H, W, Cg, bw, bh, bn))) return rc;
-  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * Nout, K, 256))) return rc;
-  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * Nout, K, 256))) return rc;
+  const bool pair = a->cta_pair != 0;
+  if (pair && (static_cast<long long>(B) * H * W / 128) % 2)
+    return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: cta_pair needs an even number of M tiles");
+  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * Nout, K, pair ? 128 : 256))) return rc;
+  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * Nout, K, pair ? 128 : 256))) return rc;
   p.w_inv_scale = a->w_inv_scale; p.a_inv_scale = a->dg_inv_scale;
   p.H = H; p.W = W; p.Cin = Cg; p.Co = Co;
   p.bw = bw; p.bh = bh; p.bn = bn;
@@ -337,7 +344,7 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   p.dx_out = a->dx_out; p.dhrec_out = a->dhrec_out;
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
-  return cuda_fail(drasic::launch_convlstm_dgrad(p, a->split != 0, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_data launch");
+  return cuda_fail(drasic::launch_convlstm_dgrad(p, a->split != 0, pair, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_data launch");
 }
 
 int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream) {
@@ -374,7 +381,7 @@ int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream) {
   }
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
-  return cuda_fail(drasic::launch_wgrad(p, a->split != 0, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_weight launch");
+  return cuda_fail(drasic::launch_wgrad(p, a->split != 0, a->cta_pair != 0, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_weight launch");
 }
 
 int drasic_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,

@@ -31,9 +31,13 @@ constexpr int A_TILE_BYTES = TILE_M * BLOCK_K * 2;  // 16 KB
 constexpr int SMEM_DATA_BUDGET = 196608;            // 192 KB of operand stages
 constexpr int NUM_THREADS = 192;
 
-template <bool SPLIT, int BLOCK_N>
+// PAIR: two CTAs of a cluster (cta_group::2) share one 256-pixel x BLOCK_N tile: each CTA stages its own
+// 128 pixels of A and half of the B rows, the leader issues M=256 MMAs that read both CTAs' shared memory.
+// Per CTA and K block that is 32 KB instead of 48 KB of L2 -> SMEM traffic for the same MMA work.
+template <bool SPLIT, int BLOCK_N, bool PAIR = false>
 struct Cfg {
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;   // weight rows staged by one CTA
+  static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int STAGES_RAW = SMEM_DATA_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -240,10 +244,12 @@ __device__ __forceinline__ void epilogue_dgrad(const GateParams& p, uint32_t t_r
   }
 }
 
-template <bool SPLIT, int BLOCK_N, int EPI>
+template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ GateParams p) {
-  using C = Cfg<SPLIT, BLOCK_N>;
+  using C = Cfg<SPLIT, BLOCK_N, PAIR>;
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -265,7 +271,7 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[a], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&p.tm_x[0]);
@@ -280,15 +286,23 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     }
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.n_mtiles * p.n_ntiles;
+  // tile walk: a work unit is one M tile (1 CTA) or one pair of adjacent M tiles (CTA pair) x one N tile
+  const int unit_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
+  const int unit_first = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const int total_tiles = (PAIR ? p.n_mtiles >> 1 : p.n_mtiles) * p.n_ntiles;
   const int cx_chunks = p.Cin / BLOCK_K;
   const int ch_chunks = p.Co / BLOCK_K;
   const int nkb = 9 * cx_chunks + (p.has_hidden ? 9 * ch_chunks : 0);
@@ -300,11 +314,19 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      uint32_t full_remote[C::STAGES];  // the leader's full barriers (shared::cluster addresses)
+      if (PAIR)
+        for (int s = 0; s < C::STAGES; ++s) full_remote[s] = ptx::mapa_u32(&full_bar[s], 0);
+      for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
         const int nt = tile % p.n_ntiles;
-        const int mt = tile / p.n_ntiles;
+        const int mt = PAIR ? 2 * (tile / p.n_ntiles) + static_cast<int>(cta_rank) : tile / p.n_ntiles;
         const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
-        const int wrow = group_of(p, mt) * p.w_group_rows + nt * BLOCK_N;
+        int wrow = group_of(p, mt) * p.w_group_rows + nt * BLOCK_N;
+        if (PAIR) {  // this CTA stages its half of the (possibly narrower, dgrad) N tile
+          int width = BLOCK_N;
+          if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
+          wrow += static_cast<int>(cta_rank) * (width >> 1);
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           const bool is_h = kb >= 9 * cx_chunks;
           const int kk = is_h ? kb - 9 * cx_chunks : kb;
@@ -314,32 +336,43 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
           const int kcol = (is_h ? 9 * p.Cin : 0) + kk * BLOCK_K;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           const CUtensorMap* ta = is_h ? p.tm_h : p.tm_x;
-          ptx::tma_load_4d(st, &ta[0], &full_bar[stage], cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
-          if (SPLIT)
-            ptx::tma_load_4d(st + A_TILE_BYTES, &ta[1], &full_bar[stage], cc * BLOCK_K, tc.x0 + dx,
-                             tc.y0 + dy, tc.n0);
           uint8_t* sb = st + (SPLIT ? 2 : 1) * A_TILE_BYTES;
-          ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], kcol, wrow);
-          if (SPLIT)
-            ptx::tma_load_2d(sb + C::B_TILE_BYTES, &p.tm_w[1], &full_bar[stage], kcol, wrow);
+          if (PAIR) {
+            // both CTAs' bytes are accounted on the leader's barrier (its MMA thread consumes both halves)
+            if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            const uint32_t fb = full_remote[stage];
+            ptx::tma_load_4d_pair(st, &ta[0], fb, cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
+            if (SPLIT)
+              ptx::tma_load_4d_pair(st + A_TILE_BYTES, &ta[1], fb, cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
+            ptx::tma_load_2d_pair(sb, &p.tm_w[0], fb, kcol, wrow);
+            if (SPLIT) ptx::tma_load_2d_pair(sb + C::B_TILE_BYTES, &p.tm_w[1], fb, kcol, wrow);
+          } else {
+            ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            ptx::tma_load_4d(st, &ta[0], &full_bar[stage], cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
+            if (SPLIT)
+              ptx::tma_load_4d(st + A_TILE_BYTES, &ta[1], &full_bar[stage], cc * BLOCK_K, tc.x0 + dx,
+                               tc.y0 + dy, tc.n0);
+            ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], kcol, wrow);
+            if (SPLIT)
+              ptx::tma_load_2d(sb + C::B_TILE_BYTES, &p.tm_w[1], &full_bar[stage], kcol, wrow);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
         // dgrad: the last N tile of a row may be narrower than BLOCK_N (UMMA N is a runtime field)
         int width = BLOCK_N;
         if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - (tile % p.n_ntiles) * BLOCK_N);
-        const uint32_t idesc = ptx::umma_idesc_f16(TILE_M, width);
+        const uint32_t idesc = ptx::umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, width);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -361,17 +394,27 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
               const uint64_t da_lo = ptx::umma_desc_sw128(a_lo + koff);
               const uint64_t db_lo = ptx::umma_desc_sw128(b_lo + koff);
               // small terms first, then the dominant one
-              ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
-              ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
-              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+              if (PAIR) {
+                ptx::umma_f16_pair(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
+                ptx::umma_f16_pair(d_tmem, da_hi, db_lo, idesc, 1);
+                ptx::umma_f16_pair(d_tmem, da_hi, db_hi, idesc, 1);
+              } else {
+                ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);
+                ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+                ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+              }
+            } else if (PAIR) {
+              ptx::umma_f16_pair(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
             } else {
               ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+          if (PAIR) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
+        // accumulator complete (each CTA of a pair holds its own 128 rows)
+        if (PAIR) ptx::umma_commit_pair(&tmem_full[acc]); else ptx::umma_commit(&tmem_full[acc]);
       }
     }
   } else {
@@ -382,9 +425,12 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     const int yl = (row / p.bw) % p.bh;
     const int nl = row / (p.bw * p.bh);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    uint32_t tmem_empty_leader[2];
+    if (PAIR)
+      for (int a = 0; a < 2; ++a) tmem_empty_leader[a] = ptx::mapa_u32(&tmem_empty[a], 0);
+    for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
       const int nt = tile % p.n_ntiles;
-      const int mt = tile / p.n_ntiles;
+      const int mt = PAIR ? 2 * (tile / p.n_ntiles) + static_cast<int>(cta_rank) : tile / p.n_ntiles;
       const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
       const int g = group_of(p, mt);
       const int acc = it & 1;
@@ -399,22 +445,24 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       // release the accumulator to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(tmem_empty_leader[acc]); else ptx::mbar_arrive(&tmem_empty[acc]);
+      }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <bool SPLIT, int BLOCK_N, int EPI>
+template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
 int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<SPLIT, BLOCK_N>;
-  auto kern = conv_gemm_kernel<SPLIT, BLOCK_N, EPI>;
+  using C = Cfg<SPLIT, BLOCK_N, PAIR>;
+  auto kern = conv_gemm_kernel<SPLIT, BLOCK_N, EPI, PAIR>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e =
@@ -422,10 +470,26 @@ int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  const int total = p.n_mtiles * p.n_ntiles;
-  const int grid = total < num_sms ? total : num_sms;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
-  return static_cast<int>(cudaGetLastError());
+  const int total = (PAIR ? p.n_mtiles / 2 : p.n_mtiles) * p.n_ntiles;
+  if (!PAIR) {
+    const int grid = total < num_sms ? total : num_sms;
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  const int pairs = num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (total < pairs ? total : pairs));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, p));
 }
 
 }  // namespace
@@ -441,27 +505,37 @@ size_t convlstm_gates_smem_bytes(bool split, int block_n) {
   return Cfg<false, 64>::SMEM_BYTES;
 }
 
-int launch_convlstm_gates(const GateParams& p, bool split, int block_n, int num_sms,
+int launch_convlstm_gates(const GateParams& p, bool split, int block_n, bool pair, int num_sms,
                           cudaStream_t stream) {
+  if (pair) {  // CTA pairs: 256-pixel x 256-column tiles only
+    if (block_n != 256 || (p.n_mtiles & 1)) return static_cast<int>(cudaErrorInvalidValue);
+    return split ? launch_t<true, 256, EPI_GATES, true>(p, num_sms, stream)
+                 : launch_t<false, 256, EPI_GATES, true>(p, num_sms, stream);
+  }
   if (split) {
     switch (block_n) {
-      case 256: return launch_t<true, 256, EPI_GATES>(p, num_sms, stream);
-      case 128: return launch_t<true, 128, EPI_GATES>(p, num_sms, stream);
-      case 64: return launch_t<true, 64, EPI_GATES>(p, num_sms, stream);
+      case 256: return launch_t<true, 256, EPI_GATES, false>(p, num_sms, stream);
+      case 128: return launch_t<true, 128, EPI_GATES, false>(p, num_sms, stream);
+      case 64: return launch_t<true, 64, EPI_GATES, false>(p, num_sms, stream);
     }
   } else {
     switch (block_n) {
-      case 256: return launch_t<false, 256, EPI_GATES>(p, num_sms, stream);
-      case 128: return launch_t<false, 128, EPI_GATES>(p, num_sms, stream);
-      case 64: return launch_t<false, 64, EPI_GATES>(p, num_sms, stream);
+      case 256: return launch_t<false, 256, EPI_GATES, false>(p, num_sms, stream);
+      case 128: return launch_t<false, 128, EPI_GATES, false>(p, num_sms, stream);
+      case 64: return launch_t<false, 64, EPI_GATES, false>(p, num_sms, stream);
     }
   }
   return static_cast<int>(cudaErrorInvalidValue);
 }
 
-int launch_convlstm_dgrad(const GateParams& p, bool split, int num_sms, cudaStream_t stream) {
-  return split ? launch_t<true, 256, EPI_DGRAD>(p, num_sms, stream)
-               : launch_t<false, 256, EPI_DGRAD>(p, num_sms, stream);
+int launch_convlstm_dgrad(const GateParams& p, bool split, bool pair, int num_sms, cudaStream_t stream) {
+  if (pair) {
+    if (p.n_mtiles & 1) return static_cast<int>(cudaErrorInvalidValue);
+    return split ? launch_t<true, 256, EPI_DGRAD, true>(p, num_sms, stream)
+                 : launch_t<false, 256, EPI_DGRAD, true>(p, num_sms, stream);
+  }
+  return split ? launch_t<true, 256, EPI_DGRAD, false>(p, num_sms, stream)
+               : launch_t<false, 256, EPI_DGRAD, false>(p, num_sms, stream);
 }
 
 }  // namespace drasic

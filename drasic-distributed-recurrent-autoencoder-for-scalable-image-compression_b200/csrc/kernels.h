@@ -67,9 +67,9 @@ struct GateParams {
 enum EpiKind : int { EPI_GATES = 0, EPI_DGRAD = 1 };
 
 // launches the persistent tcgen05 gate kernel; returns a cudaError_t as int
-int launch_convlstm_gates(const GateParams& p, bool split, int block_n, int num_sms,
+int launch_convlstm_gates(const GateParams& p, bool split, int block_n, bool pair, int num_sms,
                           cudaStream_t stream);
-int launch_convlstm_dgrad(const GateParams& p, bool split, int num_sms, cudaStream_t stream);
+int launch_convlstm_dgrad(const GateParams& p, bool split, bool pair, int num_sms, cudaStream_t stream);
 size_t convlstm_gates_smem_bytes(bool split, int block_n);
 
 }  // namespace drasic

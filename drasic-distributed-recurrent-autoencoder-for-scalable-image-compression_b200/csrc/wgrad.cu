@@ -26,10 +26,12 @@ constexpr int BOX_BYTES = 64 * 64 * 2;       // one (64 ch x 64 pixel) fp16 box 
 constexpr int WG_BLOCK_N = 256;
 constexpr int WG_DATA_BUDGET = 196608;
 
-template <bool SPLIT>
+// PAIR: two CTAs of a cluster (cta_group::2) own 256 gate channels x up to 256 columns: each stages its own
+// 128 gate channels of dG and half of the activation columns (32 KB instead of 48 KB per K block and CTA).
+template <bool SPLIT, bool PAIR = false>
 struct WCfg {
-  static constexpr int A_BYTES = 2 * BOX_BYTES;   // 128 gate channels
-  static constexpr int B_BYTES = 4 * BOX_BYTES;   // 256 columns
+  static constexpr int A_BYTES = 2 * BOX_BYTES;                 // 128 gate channels
+  static constexpr int B_BYTES = (PAIR ? 2 : 4) * BOX_BYTES;    // columns staged by one CTA
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int STAGES = WG_DATA_BUDGET / STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * WG_BLOCK_N;
@@ -56,15 +58,15 @@ struct WTile {
   int g, mt, is_h, u0, nunits, kb_lo, kb_hi;
 };
 
-__device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile) {
+__device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile, int m_units) {
   const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
   WTile t;
   const int ks = tile % p.k_splits;
   int r = tile / p.k_splits;
   const int nt = r % nt_total;
   r /= nt_total;
-  t.mt = r % p.m_tiles;
-  t.g = r / p.m_tiles;
+  t.mt = r % m_units;      // M tile (single CTA) or pair of M tiles (CTA pair)
+  t.g = r / m_units;
   t.is_h = nt >= p.n_tiles_x;
   const int ntl = t.is_h ? nt - p.n_tiles_x : nt;
   const int units = 9 * ((t.is_h ? p.Co : p.Cin) / 64);
@@ -79,9 +81,11 @@ __device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile) {
   return t;
 }
 
-template <bool SPLIT>
+template <bool SPLIT, bool PAIR>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using C = WCfg<SPLIT>;
+  using C = WCfg<SPLIT, PAIR>;
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);
+      ptx::mbar_init(&tmem_empty[a], PAIR ? 8 : 4);
     }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&p.tm_g[0]);
@@ -109,16 +113,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     if (p.has_h) ptx::prefetch_tmap(&p.tm_h[0]);
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
-  const int total_tiles = p.n_groups * p.m_tiles * nt_total * p.k_splits;
+  const int m_units = PAIR ? p.m_tiles >> 1 : p.m_tiles;
+  const int total_tiles = p.n_groups * m_units * nt_total * p.k_splits;
+  const int unit_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
+  const int unit_first = PAIR ? blockIdx.x >> 1 : blockIdx.x;
   const int HW = p.H * p.W;
   const int kb_per_img = HW >= 64 ? HW / 64 : 1;   // HW < 64: one K block spans kbn images
   const int kbx = p.W / p.kbw;
@@ -128,11 +140,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const WTile t = decode_tile(p, tile);
+      uint32_t full_remote[C::STAGES];  // the leader's full barriers (shared::cluster addresses)
+      if (PAIR)
+        for (int s = 0; s < C::STAGES; ++s) full_remote[s] = ptx::mapa_u32(&full_bar[s], 0);
+      for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
+        const WTile t = decode_tile(p, tile, m_units);
         const CUtensorMap* tb = t.is_h ? p.tm_h : p.tm_x;
         const int cpu = (t.is_h ? p.Co : p.Cin) / 64;
-        const uint32_t bytes = (SPLIT ? 2 : 1) * (C::A_BYTES + t.nunits * BOX_BYTES);
+        // a pair: this CTA stages gate channels of M tile 2*mt + rank and columns [rank*nunits/2, ...) --
+        // always one 2-box TMA (with nunits == 2 its second box is unused filler)
+        const int mt = PAIR ? 2 * t.mt + static_cast<int>(cta_rank) : t.mt;
+        const int my_u0 = PAIR ? t.u0 + static_cast<int>(cta_rank) * (t.nunits >> 1) : t.u0;
+        const int my_units = PAIR ? 2 : t.nunits;
+        const uint32_t bytes = (SPLIT ? 2 : 1) * (C::A_BYTES + my_units * BOX_BYTES);
         for (int kb = t.kb_lo; kb < t.kb_hi; ++kb) {
           int n0, y0, x0;
           if (HW >= 64) {
@@ -149,17 +169,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          ptx::mbar_expect_tx(&full_bar[stage], bytes);
+          if (!PAIR) ptx::mbar_expect_tx(&full_bar[stage], bytes);
+          else if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * bytes);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
             uint8_t* sa = st + pl * C::A_BYTES;
             uint8_t* sb = st + (SPLIT ? 2 : 1) * C::A_BYTES + pl * C::B_BYTES;
-            ptx::tma_load_5d(sa, &p.tm_g[pl], &full_bar[stage], 0, x0, y0, n0, t.mt * 2);
-            for (int u = 0; u < t.nunits; u += 2) {   // a pair of 64-channel chunks of the same tap
-              const int unit = t.u0 + u;
+            if (PAIR) ptx::tma_load_5d_pair(sa, &p.tm_g[pl], full_remote[stage], 0, x0, y0, n0, mt * 2);
+            else ptx::tma_load_5d(sa, &p.tm_g[pl], &full_bar[stage], 0, x0, y0, n0, mt * 2);
+            for (int u = 0; u < my_units; u += 2) {   // a pair of 64-channel chunks of the same tap
+              const int unit = my_u0 + u;
               const int tap = unit / cpu, chunk = unit - tap * cpu;
-              ptx::tma_load_5d(sb + u * BOX_BYTES, &tb[pl], &full_bar[stage], 0, x0 + tap % 3 - 1,
-                               y0 + tap / 3 - 1, n0, chunk);
+              if (PAIR)
+                ptx::tma_load_5d_pair(sb + u * BOX_BYTES, &tb[pl], full_remote[stage], 0, x0 + tap % 3 - 1,
+                                      y0 + tap / 3 - 1, n0, chunk);
+              else
+                ptx::tma_load_5d(sb + u * BOX_BYTES, &tb[pl], &full_bar[stage], 0, x0 + tap % 3 - 1,
+                                 y0 + tap / 3 - 1, n0, chunk);
             }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -168,14 +194,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const WTile t = decode_tile(p, tile);
+      for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
+        const WTile t = decode_tile(p, tile, m_units);
         if (t.kb_hi <= t.kb_lo) continue;  // empty node / empty k-split: nothing to add
-        const uint32_t idesc = idesc_mn(128, t.nunits * 64);
+        const uint32_t idesc = idesc_mn(PAIR ? 256 : 128, t.nunits * 64);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ++it;
@@ -199,17 +225,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             if (SPLIT) {
               const uint64_t da_lo = umma_desc_mn_sw128(a_lo + koff);
               const uint64_t db_lo = umma_desc_mn_sw128(b_lo + koff);
-              ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, first);
-              ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
-              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+              if (PAIR) {
+                ptx::umma_f16_pair(d_tmem, da_lo, db_hi, idesc, first);
+                ptx::umma_f16_pair(d_tmem, da_hi, db_lo, idesc, 1);
+                ptx::umma_f16_pair(d_tmem, da_hi, db_hi, idesc, 1);
+              } else {
+                ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, first);
+                ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+                ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+              }
+            } else if (PAIR) {
+              ptx::umma_f16_pair(d_tmem, da_hi, db_hi, idesc, first);
             } else {
               ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, first);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          if (PAIR) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full[acc]);
+        if (PAIR) ptx::umma_commit_pair(&tmem_full[acc]); else ptx::umma_commit(&tmem_full[acc]);
       }
     }
   } else {
@@ -218,9 +252,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     const int row = q * 32 + lane;
     const int Kw = 9 * (p.Cin + p.Co);
     const float scale = __ldg(p.g_inv_scale) * ACT_INV_SCALE;
+    uint32_t tmem_empty_leader[2];
+    if (PAIR)
+      for (int a = 0; a < 2; ++a) tmem_empty_leader[a] = ptx::mapa_u32(&tmem_empty[a], 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const WTile t = decode_tile(p, tile);
+    for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
+      const WTile t = decode_tile(p, tile, m_units);
       if (t.kb_hi <= t.kb_lo) continue;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -228,7 +265,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * WG_BLOCK_N;
-      float* dst = p.gw + (static_cast<size_t>(t.g) * 4 * p.Co + t.mt * 128 + row) * Kw +
+      const int mt = PAIR ? 2 * t.mt + static_cast<int>(cta_rank) : t.mt;
+      float* dst = p.gw + (static_cast<size_t>(t.g) * 4 * p.Co + mt * 128 + row) * Kw +
                    (t.is_h ? 9 * p.Cin : 0) + t.u0 * 64;
 #pragma unroll 1
       for (int j = 0; j < t.nunits * 4; ++j) {
@@ -242,22 +280,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(tmem_empty_leader[acc]); else ptx::mbar_arrive(&tmem_empty[acc]);
+      }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <bool SPLIT>
+template <bool SPLIT, bool PAIR>
 int launch_w(const WgradParams& p, int num_sms, cudaStream_t stream) {
-  using C = WCfg<SPLIT>;
-  auto kern = wgrad_kernel<SPLIT>;
+  using C = WCfg<SPLIT, PAIR>;
+  auto kern = wgrad_kernel<SPLIT, PAIR>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -265,16 +305,36 @@ int launch_w(const WgradParams& p, int num_sms, cudaStream_t stream) {
     configured = true;
   }
   const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
-  const int total = p.n_groups * p.m_tiles * nt_total * p.k_splits;
-  const int grid = total < num_sms ? total : num_sms;
-  kern<<<grid, WG_THREADS, C::SMEM_BYTES, stream>>>(p);
-  return static_cast<int>(cudaGetLastError());
+  const int total = p.n_groups * (PAIR ? p.m_tiles / 2 : p.m_tiles) * nt_total * p.k_splits;
+  if (!PAIR) {
+    const int grid = total < num_sms ? total : num_sms;
+    kern<<<grid, WG_THREADS, C::SMEM_BYTES, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  const int pairs = num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (total < pairs ? total : pairs));
+  cfg.blockDim = dim3(WG_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, p));
 }
 
 }  // namespace
 
-int launch_wgrad(const WgradParams& p, bool split, int num_sms, cudaStream_t stream) {
-  return split ? launch_w<true>(p, num_sms, stream) : launch_w<false>(p, num_sms, stream);
+int launch_wgrad(const WgradParams& p, bool split, bool pair, int num_sms, cudaStream_t stream) {
+  if (pair) {
+    if (p.m_tiles & 1) return static_cast<int>(cudaErrorInvalidValue);
+    return split ? launch_w<true, true>(p, num_sms, stream) : launch_w<false, true>(p, num_sms, stream);
+  }
+  return split ? launch_w<true, false>(p, num_sms, stream) : launch_w<false, false>(p, num_sms, stream);
 }
 
 }  // namespace drasic

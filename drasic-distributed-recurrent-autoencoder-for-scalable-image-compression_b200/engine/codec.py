@@ -104,12 +104,26 @@ class _Layer(object):
     pass
 
 
+def _pick_k_splits(tiles, units, k_max):
+    """K splits of the wgrad GEMM: the persistent grid walks tiles*k work items in waves of `units`;
+    pick the split count (at least ~3 waves of work when K allows) whose last wave is fullest."""
+    best_k, best_eff = 1, 0.0
+    k_lo = max(1, min(k_max, (3 * units + tiles - 1) // tiles))
+    for k in range(k_lo, max(k_lo, min(k_max, 4 * k_lo)) + 1):
+        n = tiles * k
+        eff = n / float(-(-n // units) * units)
+        if eff > best_eff + 1e-3:
+            best_k, best_eff = k, eff
+    return int(best_k)
+
+
 class CodecEngine(object):
     """Runs the T-iteration loop for one codec (dist: per-node encoders + shared decoder; sep: per-node
     encoders and decoders).  `precision`: 'parity' = fp16 hi+lo operands with IEEE transcendental
     functions (fp32-grade, bit-exact codes); 'fast' = single fp16 operands with tanh.approx."""
 
-    def __init__(self, num_channel, code_size, num_node, separate=False, precision='parity', grad_precision='fp16'):
+    def __init__(self, num_channel, code_size, num_node, separate=False, precision='parity', grad_precision='fp16',
+                 cta_pair='auto'):
         """grad_precision: 'fp16' = backward GEMMs on single fp16 operands, gates saved in fp16 (gradients
         within ~1e-3 relative of the fp32 reference); 'parity' = split-fp16 backward GEMMs and fp32 saved
         gates (fp32-grade gradients; needs precision='parity')."""
@@ -117,6 +131,9 @@ class CodecEngine(object):
             raise ValueError('Not valid precision')
         if grad_precision not in ('fp16', 'parity') or (grad_precision == 'parity' and precision != 'parity'):
             raise ValueError('Not valid grad_precision')
+        if cta_pair not in ('auto', 'on', 'off'):
+            raise ValueError('Not valid cta_pair')
+        self.cta_pair = cta_pair  # CTA pairs (cta_group::2) for the gate / dgrad / wgrad GEMMs
         self.gsplit = 1 if grad_precision == 'parity' else 0
         self.C, self.code, self.M, self.separate = num_channel, code_size, num_node, separate
         self.split = 1 if precision == 'parity' else 0
@@ -162,6 +179,15 @@ class CodecEngine(object):
             if n_mtiles * (4 * co // bn) >= self.sms():
                 return bn
         return 64
+
+    def _use_pair(self, n_mtiles, hw, co):
+        """CTA pairs need 256-column N tiles and node boundaries on even M tiles: a node's slots are a
+        multiple of 8 images, i.e. hw/16 M tiles -- even once an image has at least 32 pixels."""
+        if self.cta_pair == 'off' or (8 * hw // 128) % 2 or n_mtiles % 2:
+            return False
+        if self.cta_pair == 'on':
+            return True
+        return n_mtiles // 2 * (4 * co // 256) >= self.sms() // 2
 
     def _get_arena(self, B_pad, H, W, device, T=0):
         """T == 0: inference arena (h ping-pongs, c in place, one buffer per edge).  T > 0: training
@@ -284,7 +310,8 @@ class CodecEngine(object):
             ly.name, ly.cin, ly.co, ly.h, ly.w = name, cin, co, h, w
             ly.next_mode, ly.next_f32 = nmode, nf32
             ly.in_order, ly.out_order, ly.is_enc, ly.idx, ly.prefs = io, oo, is_enc, idx, prefs
-            ly.block_n = self._block_n(n_mtiles, co)
+            ly.pair = self._use_pair(n_mtiles, h * w, co)
+            ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.groups = len(prefs)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
@@ -359,6 +386,7 @@ class CodecEngine(object):
             a.has_state = 1 if t > 0 else 0
             a.next_mode, a.next_f32 = ly.next_mode, ly.next_f32
             a.split, a.precise, a.block_n = self.split, self.precise, ly.block_n
+            a.cta_pair = int(ly.pair)
             # algorithmic FLOPs of this launch: real images only, hidden conv skipped on zero state
             k = 9 * (ly.cin + (ly.co if t > 0 else 0))
             flops = 2.0 * Bn * ly.h * ly.w * 4 * ly.co * k
@@ -511,6 +539,7 @@ class CodecEngine(object):
             a.group_mtile_end = P(ly.mtile_end)
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.gsplit
+            a.cta_pair = int(ly.pair)
             fl = 2.0 * Bn * ly.h * ly.w * 36 * ly.co * (ly.cin + (ly.co if t > 0 else 0))
             self._timed('dgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_data(a, stream), 'convlstm_bwd_data'))
             w = B.WgradArgs()
@@ -522,9 +551,13 @@ class CodecEngine(object):
             w.group_kb_end = P(group_kb_end(ly)) if ly.groups > 1 else None
             w.B_pad, w.H, w.W, w.Cin, w.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             w.n_groups, w.has_h, w.split = ly.groups, 1 if t > 0 else 0, self.gsplit
+            w.cta_pair = 0 if self.cta_pair == 'off' else 1      # 4Co/128 M tiles: always even
             tiles = ly.groups * (4 * ly.co // 128) * ((9 * ly.cin // 64 + 3) // 4 + ((9 * ly.co // 64 + 3) // 4 if t > 0 else 0))
+            units = sms
+            if w.cta_pair:
+                tiles, units = tiles // 2, sms // 2
             kb_per_group = max(1, Bp * ly.h * ly.w // 64 // ly.groups)
-            w.k_splits = int(max(1, min((3 * sms + tiles - 1) // tiles, kb_per_group // 16)))
+            w.k_splits = _pick_k_splits(tiles, units, max(1, kb_per_group // 16))
             self._timed('wgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_weight(w, stream), 'convlstm_bwd_weight'))
             self.launches += 5
 

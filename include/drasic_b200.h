@@ -84,6 +84,8 @@ typedef struct {
   int precise;                          /* 1: IEEE exp/div/tanh, 0: tanh.approx */
   int block_n;                          /* N tile: 256, 128 or 64 (must match the packing) */
   int gates_f32;                        /* dtype of gates_out */
+  int cta_pair;                         /* 1: CTA pairs (cta_group::2) on 256-pixel x 256-column tiles; needs block_n == 256, an even
+                                           number of M tiles and node boundaries on even M tiles */
 } drasic_convlstm_args;
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream);
 
@@ -148,6 +150,7 @@ typedef struct {
   float* dhrec_out;                       /* nullable: fp32 [B_pad,H,W,Co] gradient w.r.t. h_{t-1} */
   const int* group_mtile_end;
   int B_pad, H, W, Cin, Co, n_groups, dx_mode, split;
+  int cta_pair;                           /* as in drasic_convlstm_args */
 } drasic_dgrad_args;
 int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream);
 
@@ -161,6 +164,7 @@ typedef struct {
   const float* dg_inv_scale;
   const int* group_kb_end;                /* device [n_groups]: exclusive end 64-pixel block per node */
   int B_pad, H, W, Cin, Co, n_groups, has_h, split, k_splits;
+  int cta_pair;                           /* 1: CTA pairs, each pair owns 256 gate channels x 256 columns */
 } drasic_wgrad_args;
 int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream);
 int drasic_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,

@@ -94,11 +94,13 @@ def first_mismatch_margins(codes, ref_codes, ref_z):
     return margins, clean
 
 
-@pytest.mark.parametrize('M,B,seed,ragged', [(8, 64, 0, False), (8, 61, 1, True), (3, 20, 2, True)])
-def test_config2_3_multi_source_vs_oracle(M, B, seed, ragged):
+@pytest.mark.parametrize('M,B,seed,ragged,cta_pair', [(8, 64, 0, False, 'off'), (8, 61, 1, True, 'off'), (3, 20, 2, True, 'off'),
+                                                       (8, 64, 0, False, 'on'), (8, 61, 1, True, 'on')])
+def test_config2_3_multi_source_vs_oracle(M, B, seed, ragged, cta_pair):
     """CIFAR-like, M sources (random-subset ids, or ragged class-label-like groups incl. an empty node),
-    T=16, eval: codes equal the oracle's except where the oracle's own margin is ~0."""
-    m = build_model('dist_codec', 'CIFAR10', M, 16, seed=seed)
+    T=16, eval: codes equal the oracle's except where the oracle's own margin is ~0.  cta_pair='on' forces
+    the CTA-pair (cta_group::2) gate kernels that large batches select on their own."""
+    m = build_model('dist_codec', 'CIFAR10', M, 16, seed=seed, cta_pair=cta_pair)
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     g = torch.Generator().manual_seed(100 + seed)
     img = torch.rand(B, 3, 32, 32, generator=g)

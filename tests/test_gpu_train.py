@@ -62,13 +62,14 @@ def test_training_step_matches_reference_gradients(golden_dir, precision, grad_p
                    torch.from_numpy(g['g_e1_hidden_slice'])) < tol
 
 
-@pytest.mark.parametrize('name,M,B,T,separate', [('dist_codec', 8, 27, 5, False), ('sep_codec', 3, 13, 3, True),
-                                                  ('dist_codec', 1, 9, 16, False)])
-def test_training_step_vs_oracle_autograd(name, M, B, T, separate):
+@pytest.mark.parametrize('name,M,B,T,separate,cta_pair', [('dist_codec', 8, 27, 5, False, 'off'), ('sep_codec', 3, 13, 3, True, 'off'),
+                                                           ('dist_codec', 1, 9, 16, False, 'off'), ('dist_codec', 8, 27, 5, False, 'on'),
+                                                           ('sep_codec', 3, 13, 3, True, 'on')])
+def test_training_step_vs_oracle_autograd(name, M, B, T, separate, cta_pair):
     """ragged node groups (one node empty), per-source decoders (sep: detached residual), T=16 single source"""
     data = 'MNIST' if M == 1 else 'CIFAR10'
     C = 1 if M == 1 else 3
-    m = build_model(name, data, M, T, seed=11)
+    m = build_model(name, data, M, T, seed=11, cta_pair=cta_pair)
     sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
     g = torch.Generator().manual_seed(12)
     img = torch.rand(B, C, 32, 32, generator=g)
