@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdPa
   const int lane_base = lane & ~3;
   const bool mine = sub < C;
   const QuadMapB qm(p.W);
+  // heterogeneous rates: a frozen node's decoded refinement is the constant 0 -> no gradient into the decoder
+  const bool frozen = p.group_iters != nullptr &&
+                      p.iter >= p.group_iters[p.n_enc_groups > 1 ? find_group_b(p.group_img_end, p.n_enc_groups, slot) : 0];
   for (int t = threadIdx.x; t < MAXC * FEATB; t += TB_THREADS) {
     const int c = t >> 5, sb = (t >> 3) & 3, j = t & 7;
     s_w4[c][sb][j] = c < C ? p.w_d4[(static_cast<size_t>(gd) * C + c) * FEATB + slice_channel(sb, j)] : 0.0f;
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdPa
 #pragma unroll
       for (int c = 1; c < NC; ++c) pre = sub == c ? acc[c] : pre;
       const float d = tanhf(pre);
-      dpre_mine = G * gain * (1.0f - d * d);
+      dpre_mine = frozen ? 0.0f : G * gain * (1.0f - d * d);
     }
     float dpre[NC];
 #pragma unroll

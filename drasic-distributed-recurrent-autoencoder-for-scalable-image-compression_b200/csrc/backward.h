@@ -74,6 +74,8 @@ struct TailBwdParams {
   const int* group_img_end;
   float loss_scale;        // 1 / (T * B*C*H*W)
   int B_pad, C, H, W, first, loss_kind, n_dec_groups, has_acc;
+  const int* group_iters;  // nullable: per-node iteration budget (heterogeneous rates)
+  int iter, n_enc_groups;
 };
 
 struct HeadBwdParams {

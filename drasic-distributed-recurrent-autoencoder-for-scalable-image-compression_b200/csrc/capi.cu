@@ -218,7 +218,8 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
 
 int drasic_bottleneck_fwd(const drasic_bottleneck_args* a, void* stream) {
   if (!a) return fail(DRASIC_ERR_INVALID, "bottleneck_fwd: null args");
-  if (!a->h_e3 || !a->w_e4 || !a->w_d0 || !a->perm || !a->code_out || !a->d1_in_hi || (a->split && !a->d1_in_lo))
+  if (!a->w_d0 || !a->perm || !a->code_out || !a->d1_in_hi || (a->split && !a->d1_in_lo) ||
+      (!a->bits_in && (!a->h_e3 || !a->w_e4)))
     return fail(DRASIC_ERR_INVALID, "bottleneck_fwd: null pointer");
   if (a->B_pad <= 0 || a->HW <= 0 || a->Ch % 4 || a->code <= 0 || (a->code * a->HW) % 32)
     return fail(DRASIC_ERR_INVALID, "bottleneck_fwd: shape B_pad=%d HW=%d Ch=%d code=%d", a->B_pad, a->HW, a->Ch, a->code);
@@ -236,13 +237,17 @@ int drasic_bottleneck_fwd(const drasic_bottleneck_args* a, void* stream) {
   p.n_enc_groups = a->n_enc_groups; p.n_dec_groups = a->n_dec_groups;
   p.precise = a->precise; p.split = a->split;
   p.group_img_end = a->group_img_end;
+  p.bits_in = a->bits_in;
   return cuda_fail(drasic::launch_bottleneck(p, static_cast<cudaStream_t>(stream)), "bottleneck_fwd launch");
 }
 
 int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream) {
   if (!a) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: null args");
-  if (!a->w_e0 || !a->img || !a->perm) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: null pointer");
-  if (a->mode != DRASIC_TAIL_INIT && (!a->d3_next || !a->w_d4 || !a->recon_out || !a->loss_acc))
+  if (!a->perm) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: null pointer");
+  const bool decode_only = !a->img;
+  if (decode_only ? (a->mode == DRASIC_TAIL_INIT || a->e1_in_hi) : !a->w_e0)
+    return fail(DRASIC_ERR_INVALID, "tail_head_fwd: img is required unless decoding only (mode != INIT, no e1_in)");
+  if (a->mode != DRASIC_TAIL_INIT && (!a->d3_next || !a->w_d4 || !a->recon_out || (!decode_only && !a->loss_acc)))
     return fail(DRASIC_ERR_INVALID, "tail_head_fwd: step mode needs decoder buffers");
   if (a->mode == DRASIC_TAIL_STEP && !a->recon_prev) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: recon_prev");
   if (a->mode < 0 || a->mode > 2 || a->loss_kind < 0 || a->loss_kind > 2) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: mode/loss");
@@ -261,6 +266,8 @@ int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream) {
   p.n_dec_groups = a->n_dec_groups < 1 ? 1 : a->n_dec_groups;
   p.precise = a->precise; p.split = a->split;
   p.group_img_end = a->group_img_end;
+  p.group_iters = a->group_iters; p.iter = a->iter;
+  if (a->group_iters && p.n_enc_groups > 1 && !a->group_img_end) return fail(DRASIC_ERR_INVALID, "tail_head_fwd: group_iters needs group_img_end");
   return cuda_fail(drasic::launch_tail_head(p, static_cast<cudaStream_t>(stream)), "tail_head_fwd launch");
 }
 
@@ -414,6 +421,8 @@ int drasic_tail_bwd(const drasic_tail_bwd_args* a, void* stream) {
   p.dh_d3 = a->dh_d3; p.dw_d4 = a->dw_d4; p.perm = a->perm; p.group_img_end = a->group_img_end;
   p.loss_scale = a->loss_scale; p.B_pad = a->B_pad; p.C = a->C; p.H = a->H; p.W = a->W; p.first = a->first;
   p.loss_kind = a->loss_kind; p.n_dec_groups = a->n_dec_groups < 1 ? 1 : a->n_dec_groups; p.has_acc = a->has_acc;
+  p.group_iters = a->group_iters; p.iter = a->iter; p.n_enc_groups = a->n_enc_groups < 1 ? 1 : a->n_enc_groups;
+  if (a->group_iters && p.n_enc_groups > 1 && !a->group_img_end) return fail(DRASIC_ERR_INVALID, "tail_bwd: group_iters needs group_img_end");
   return cuda_fail(drasic::launch_tail_bwd(p, static_cast<cudaStream_t>(stream)), "tail_bwd launch");
 }
 

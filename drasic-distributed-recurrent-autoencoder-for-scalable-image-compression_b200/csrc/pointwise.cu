@@ -50,14 +50,24 @@ __global__ void __launch_bounds__(128) bottleneck_kernel(const BottleneckParams 
   const int gd = p.n_dec_groups > 1 ? find_group(p.group_img_end, p.n_dec_groups, slot) : 0;
   const float* w4 = p.w_e4 + static_cast<size_t>(ge) * code * CH;
   const float* w0 = p.w_d0 + static_cast<size_t>(gd) * CH * code;
+  const int n_out = code * HW;
 
+  if (p.bits_in) {
+    // decode-only: the symbols of this image come from the packed stream (MSB first over [code][HW])
+    const uint8_t* bsrc = p.bits_in + static_cast<size_t>(orig) * (n_out >> 3);
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+      const int k = o / HW, pix = o - k * HW;
+      const float q = ((bsrc[o >> 3] >> (7 - (o & 7))) & 1) ? 1.0f : -1.0f;
+      p.code_out[static_cast<size_t>(orig) * n_out + o] = q;
+      scode[pix * code + k] = q;
+    }
+  } else {
   const float4* src = reinterpret_cast<const float4*>(p.h_e3 + static_cast<size_t>(slot) * HW * CH);
   for (int i = threadIdx.x; i < HW * CH / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sh)[i] = src[i];
   __syncthreads();
 
   // encoder tail + quantizer; o enumerates the NCHW code tensor [code][HW] of this image
-  const int n_out = code * HW;
   for (int base = 0; base < n_out; base += blockDim.x) {
     const int o = base + threadIdx.x;
     float q = 0.0f;
@@ -101,6 +111,7 @@ __global__ void __launch_bounds__(128) bottleneck_kernel(const BottleneckParams 
       const int nbytes = min(4, (n_out >> 3) - byte0);
       for (int b = 0; b < nbytes; ++b) dst[b] = static_cast<uint8_t>(rev >> (24 - 8 * b));
     }
+  }
   }
   __syncthreads();
 
@@ -177,6 +188,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
   const bool has_head = p.e1_in[0] != nullptr;
   const bool mine = sub < C;                       // this lane owns image channel `sub` of its pixel
   const bool step_mode = p.mode == TAIL_STEP;
+  const bool has_img = p.img != nullptr;            // false = decode-only: no loss, no residual
+  // heterogeneous rates: a node whose iteration budget is spent receives no further refinement
+  const bool frozen = p.group_iters != nullptr && p.iter >= p.group_iters[ge];
   const QuadMap qm(p.W);
 
   // weights laid out per channel slice so a lane reads its eight channels with vector loads:
@@ -188,8 +202,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
     const int c = t >> 5, sb = (t >> 3) & 3, j = t & 7;
     const int kt = j < 4 ? 4 * sb + j : 16 + 4 * sb + (j - 4);
     s_w4[c][sb][j] = (has_tail && c < C) ? p.w_d4[(static_cast<size_t>(gd) * C + c) * FEAT + kt] : 0.0f;
-    s_w0[sb][j][c] = (c < C) ? p.w_e0[(static_cast<size_t>(ge) * FEAT + 8 * sb + j) * C + c] : 0.0f;
-    if (c == 0) s_b0[sb][j] = p.b_e0 ? p.b_e0[static_cast<size_t>(ge) * FEAT + 8 * sb + j] : 0.0f;
+    s_w0[sb][j][c] = (has_head && c < C) ? p.w_e0[(static_cast<size_t>(ge) * FEAT + 8 * sb + j) * C + c] : 0.0f;
+    if (c == 0) s_b0[sb][j] = (has_head && p.b_e0) ? p.b_e0[static_cast<size_t>(ge) * FEAT + 8 * sb + j] : 0.0f;
   }
   __syncthreads();
 
@@ -215,7 +229,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
     rpix[u] = qm.raster(i0 + 8 * u);
     im[u] = rp[u] = 0.0f;
     if (mine) {
-      im[u] = p.img[img_base + rpix[u]];
+      if (has_img) im[u] = p.img[img_base + rpix[u]];
       if (step_mode) rp[u] = p.recon_prev[img_base + rpix[u]];
     }
   }
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
       for (int u = 0; u < U; ++u) {
         rpix[u] = qm.raster(i0 + 8 * U + 8 * u);
         if (mine) {
-          im[u] = p.img[img_base + rpix[u]];
+          if (has_img) im[u] = p.img[img_base + rpix[u]];
           if (step_mode) rp[u] = p.recon_prev[img_base + rpix[u]];
         }
       }
@@ -284,11 +298,14 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
           float r;
           if (!step_mode) {
             d = __fadd_rn(d, 1.0f) / 2.0f;   // (decoded + 1) / 2   (dist_codec.py:56)
+            if (frozen) d = 0.0f;
             r = __fadd_rn(0.0f, d);          // reconstructed = 0 + decoded (dist_codec.py:39,57)
           } else {
+            if (frozen) d = 0.0f;
             r = __fadd_rn(rp_c[u], d);
           }
           p.recon_out[gi[u]] = r;
+          if (!has_img) continue;
           const float e = __fsub_rn(r, im_c[u]);
           if (p.loss_kind == LOSS_MAE) l_abs += static_cast<double>(fabsf(e));
           else if (p.loss_kind == LOSS_MSE) l_abs += static_cast<double>(e) * e;
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
     }
   }
 
-  if (has_tail) {
+  if (has_tail && has_img) {
     // block reduction of the loss terms -> one fp64 atomic pair per block
     for (int o = 16; o > 0; o >>= 1) {
       l_abs += __shfl_xor_sync(0xffffffffu, l_abs, o);

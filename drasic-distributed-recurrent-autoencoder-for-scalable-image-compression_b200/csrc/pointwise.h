@@ -27,6 +27,7 @@ struct BottleneckParams {
   int n_enc_groups, n_dec_groups;
   int precise, split;
   const int* group_img_end;  // device [n_groups]: exclusive end slot of each node
+  const uint8_t* bits_in;    // nullable: decode-only, symbols come from this packed stream [B, code*HW/8]
 };
 
 struct TailParams {
@@ -46,6 +47,8 @@ struct TailParams {
   int n_enc_groups, n_dec_groups;
   int precise, split;
   const int* group_img_end;  // device [n_groups]: exclusive end slot of each node
+  const int* group_iters;    // nullable: per-node iteration budget (heterogeneous rates)
+  int iter;
 };
 
 int launch_bottleneck(const BottleneckParams& p, cudaStream_t stream);

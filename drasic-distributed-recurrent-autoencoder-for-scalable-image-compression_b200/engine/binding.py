@@ -26,14 +26,15 @@ class ConvLSTMArgs(C.Structure):
 class BottleneckArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('h_e3', 'w_e4', 'w_d0', 'noise', 'perm', 'code_out', 'z_out', 'bits_out',
                                   'd1_in_hi', 'd1_in_lo', 'd0_out_f32', 'group_img_end')] + \
-               [(n, ip) for n in ('B_pad', 'HW', 'Ch', 'code', 'n_enc_groups', 'n_dec_groups', 'precise', 'split')]
+               [(n, ip) for n in ('B_pad', 'HW', 'Ch', 'code', 'n_enc_groups', 'n_dec_groups', 'precise', 'split')] + \
+               [('bits_in', vp)]
 
 
 class TailHeadArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('d3_next', 'w_d4', 'w_e0', 'b_e0', 'img', 'recon_prev', 'recon_out',
                                   'dec_out', 'loss_acc', 'e1_in_hi', 'e1_in_lo', 'perm', 'group_img_end')] + \
                [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'mode', 'loss_kind', 'n_enc_groups', 'n_dec_groups',
-                                  'precise', 'split')]
+                                  'precise', 'split')] + [('group_iters', vp), ('iter', ip)]
 
 
 class DgradArgs(C.Structure):
@@ -57,7 +58,8 @@ class BottleneckBwdArgs(C.Structure):
 class TailBwdArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('d3_next', 'w_d4', 'img', 'recon_t', 'gacc', 'dh_d3', 'dw_d4', 'perm',
                                   'group_img_end')] + [('loss_scale', C.c_float)] + \
-               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'loss_kind', 'n_dec_groups', 'has_acc')]
+               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'loss_kind', 'n_dec_groups', 'has_acc')] + \
+               [('group_iters', vp), ('iter', ip), ('n_enc_groups', ip)]
 
 
 class HeadBwdArgs(C.Structure):

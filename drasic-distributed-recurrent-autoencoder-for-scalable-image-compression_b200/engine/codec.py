@@ -257,9 +257,13 @@ class CodecEngine(object):
 
     # ------------------------------------------------------------------ the loop
     def forward(self, sd, img, label, num_iter, training=False, noise=None, loss_kind='mae',
-                label_host=None, want_z=False, save_for_backward=False, plan=None, pack_only=False):
+                label_host=None, want_z=False, save_for_backward=False, plan=None, pack_only=False,
+                node_iters=None):
         """sd: mapping reference state_dict key -> fp32 CUDA tensor.  img [B,C,H,W] fp32 in [0,1],
         label [B] node ids.  noise: None (eval / deterministic sign) or [T,B,code,H/8,W/8] uniforms.
+        node_iters: None, or one iteration budget per node (heterogeneous rates, BASELINE config 4, inferred
+        semantics restated in oracle.codec_forward): at iteration i >= node_iters[j] the samples of node j
+        receive no further refinement (their reconstruction stays, the loss keeps counting it).
         Returns dict(recon [T,B,C,H,W], codes [T,B,code,H/8,W/8], bits [T,B,code*HW/64/8] uint8,
         loss_acc [T,2] fp64 {sum loss terms, sum squared error}, z (optional))."""
         if loss_kind not in B.LOSS_KINDS:
@@ -282,6 +286,12 @@ class CodecEngine(object):
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
+        group_iters = None
+        if node_iters is not None:
+            ni = np.asarray(node_iters, dtype=np.int32).reshape(-1)
+            if ni.size != self.M or ni.min() < 0:
+                raise ValueError('Not valid node_iters')
+            group_iters = torch.from_numpy(ni).to(dev)
         A = self._get_arena(Bp, H, W, dev, T if save_for_backward else 0)
         keep = save_for_backward
         want_z = want_z or keep
@@ -353,6 +363,7 @@ class CodecEngine(object):
                 e1 = A['e1_in'][(t + 1) if keep else 0]
                 a.e1_in_hi, a.e1_in_lo = P(e1[0]), P(e1[1])
             a.group_img_end = P(plan.group_img_end)
+            a.group_iters, a.iter = P(group_iters), max(t, 0)
             a.B_pad, a.C, a.H, a.W, a.mode = Bp, Cc, H, W, mode
             a.loss_kind = B.LOSS_KINDS[loss_kind]
             a.n_enc_groups, a.n_dec_groups = self.M, self.Md
@@ -427,8 +438,104 @@ class CodecEngine(object):
             self._gen = getattr(self, '_gen', 0) + 1
             out['_bwd'] = dict(gen=self._gen, A=A, layers=layers, sd=sd, img=img, T=T, loss_kind=loss_kind, w_e0=w_e0, b_e0=b_e0,
                                w_e4=w_e4, w_d0=w_d0, w_d4=w_d4, enc_pref=enc_pref, dec_pref=dec_pref,
-                               shape=(Bn, Cc, H, W))
+                               shape=(Bn, Cc, H, W), group_iters=group_iters)
         return out
+
+    # ------------------------------------------------------------------ decode-only
+    def decode(self, sd, bits, label, hw, label_host=None):
+        """Reconstruct from the packed bitstream alone: bits [T', B, code*H*W/512] uint8 (the 'bits' output of
+        forward(), or any prefix of its iterations -- the codec is progressive), label [B] node ids (which
+        decoder a sample belongs to in the sep codec; unused by the shared decoder but kept for symmetry).
+        Runs only the decoder half of the loop (dist_codec.py:55-57): D0 -> D1 D2 D3 -> D4, recon += decoded.
+        Returns dict(recon [T',B,C,H,W], codes [T',B,code,H/8,W/8])"""
+        if not bits.is_cuda:
+            raise B.DrasicError('DRASIC B200 engine needs CUDA tensors; there is no CPU path')
+        L = B.lib()
+        dev = bits.device
+        H, W = hw
+        if H % 8 or W % 8 or (H * W) % 256:
+            raise ValueError('Not valid image size {}x{} for the fused path'.format(H, W))
+        code, hc, wc = self.code, H // 8, W // 8
+        bits = bits.detach().contiguous()
+        if bits.dtype != torch.uint8 or bits.dim() != 3 or bits.shape[2] != code * hc * wc // 8:
+            raise ValueError('Not valid bitstream shape')
+        T, Bn = int(bits.shape[0]), int(bits.shape[1])
+        if label_host is None:
+            label_host = label.detach().cpu().numpy()
+        plan = BatchPlan(label_host, self.M, dev)
+        Bp = plan.B_pad
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self.launches = 0
+        A = self._get_arena(Bp, H, W, dev, 0)
+        dec_pref = ['model.decoder.{}'.format(j) for j in range(self.M)] if self.separate else ['model.decoder']
+
+        def lstm_w(prefix, idx):
+            base = '{}.{}.cell.cell.0.'.format(prefix, idx)
+            return sd[base + 'in.cell.cell.main.weight'], sd[base + 'hidden.cell.cell.main.weight']
+
+        def stack(keys):
+            return torch.stack([sd[k].detach().float().reshape(sd[k].shape[0], -1) for k in keys]).contiguous()
+        layers = []
+        for (name, cin, co, div, io, oo, nmode, nf32) in DEC_LAYERS:
+            h, w = H // div, W // div
+            n_mtiles = Bp * h * w // 128
+            ly = _Layer()
+            ly.name, ly.cin, ly.co, ly.h, ly.w, ly.next_mode, ly.next_f32 = name, cin, co, h, w, nmode, nf32
+            ly.pair = self._use_pair(n_mtiles, h * w, co)
+            ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
+            ly.groups = len(dec_pref)
+            ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, DEC_IDX[name]) for p in dec_pref], cin, co, io, oo,
+                                                   ly.block_n, stream)[:3]
+            ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
+            layers.append(ly)
+        w_d0 = stack([p + '.0.cell.cell.main.weight' for p in dec_pref])
+        w_d4 = stack([p + '.7.cell.cell.main.weight' for p in dec_pref])
+        recon = torch.empty((T, Bn, self.C, H, W), dtype=torch.float32, device=dev)
+        codes = torch.empty((T, Bn, code, hc, wc), dtype=torch.float32, device=dev)
+        P = B.ptr
+        for t in range(T):
+            a = B.BottleneckArgs()
+            a.bits_in, a.w_d0, a.perm = bits[t].data_ptr(), P(w_d0), P(plan.perm)
+            a.code_out = codes[t].data_ptr()
+            d1 = A['d1_in'][0]
+            a.d1_in_hi, a.d1_in_lo = P(d1[0]), P(d1[1])
+            a.group_img_end = P(plan.group_img_end)
+            a.B_pad, a.HW, a.Ch, a.code = Bp, hc * wc, 128, code
+            a.n_enc_groups, a.n_dec_groups = self.M, self.Md
+            a.precise, a.split = self.precise, self.split
+            B.check(L.drasic_bottleneck_fwd(a, stream), 'bottleneck_fwd (decode)')
+            x = d1
+            for ly in layers:
+                Lb = A[ly.name]
+                g = B.ConvLSTMArgs()
+                cur, prv = Lb['h'][t & 1], Lb['h'][(t & 1) ^ 1]
+                g.c_state = P(Lb['c'][0])
+                nxt = Lb['next'][0]
+                g.x_hi, g.x_lo = P(x[0]), P(x[1])
+                if t > 0:
+                    g.h_hi, g.h_lo = P(prv[0]), P(prv[1])
+                g.w_hi, g.w_lo, g.w_inv_scale = P(ly.hi), P(ly.lo), P(ly.inv)
+                g.h_out_hi, g.h_out_lo = P(cur[0]), P(cur[1])
+                g.next_hi, g.next_lo = P(nxt[0]), P(nxt[1])
+                g.group_mtile_end = P(ly.mtile_end)
+                g.B_pad, g.H, g.W, g.Cin, g.Co = Bp, ly.h, ly.w, ly.cin, ly.co
+                g.n_groups, g.has_state = ly.groups, 1 if t > 0 else 0
+                g.next_mode, g.next_f32 = ly.next_mode, ly.next_f32
+                g.split, g.precise, g.block_n, g.cta_pair = self.split, self.precise, ly.block_n, int(ly.pair)
+                B.check(L.drasic_convlstm_fwd(g, stream), 'convlstm_fwd (decode)')
+                x = nxt
+            th = B.TailHeadArgs()
+            th.d3_next, th.w_d4 = P(A['D3']['next'][0][0]), P(w_d4)
+            th.recon_out = recon[t].data_ptr()
+            th.recon_prev = recon[t - 1].data_ptr() if t > 0 else None
+            th.perm, th.group_img_end = P(plan.perm), P(plan.group_img_end)
+            th.B_pad, th.C, th.H, th.W = Bp, self.C, H, W
+            th.mode = B.TAIL_FIRST if t == 0 else B.TAIL_STEP
+            th.n_enc_groups, th.n_dec_groups = self.M, self.Md
+            th.precise, th.split = self.precise, self.split
+            B.check(L.drasic_tail_head_fwd(th, stream), 'tail_head_fwd (decode)')
+            self.launches += 5
+        return {'recon': recon, 'codes': codes, 'plan': plan, '_keep': (w_d0, w_d4, bits)}
 
     # ------------------------------------------------------------------ backward through time
     def _packed_dgrad(self, ly, sd, stream):
@@ -570,6 +677,7 @@ class CodecEngine(object):
             a.loss_scale = loss_scale
             a.B_pad, a.C, a.H, a.W = Bp, Cc, H, W
             a.first, a.loss_kind, a.n_dec_groups, a.has_acc = int(t == 0), B.LOSS_KINDS[ctx['loss_kind']], self.Md, int(t < T - 1)
+            a.group_iters, a.iter, a.n_enc_groups = P(ctx['group_iters']), t, self.M
             self._timed('tail_bwd', 0.0, lambda: B.check(L.drasic_tail_bwd(a, stream), 'tail_bwd'))
             for name in ('D3', 'D2', 'D1'):
                 lstm_layer_bwd(by[name], t)

@@ -57,7 +57,7 @@ class _LoopFunction(torch.autograd.Function):
     def forward(ctx, model, img, label, noise, *params):
         ctx.model = model
         ctx.names = [k for k, _ in model.named_parameters()]
-        if config.PARAM.get('cuda_graph', False):
+        if config.PARAM.get('cuda_graph', False) and config.PARAM.get('node_iters') is None:
             # one graph holds forward AND backward-through-time; backward() only hands the gradients out
             out, ctx.grads = model._run_graphed(img, label, noise, with_backward=True)
         else:
@@ -155,7 +155,39 @@ class CodecModel(nn.Module):
         sd = {k: v for k, v in self.named_parameters()}
         return self._engine.forward(sd, img, label, config.PARAM['num_iter'], training=self.training,
                                     noise=noise, loss_kind=config.PARAM['loss_fn'],
-                                    save_for_backward=save_for_backward)
+                                    save_for_backward=save_for_backward, node_iters=config.PARAM.get('node_iters'))
+
+    # ---- progressive bitstream ---------------------------------------------------
+    def encode(self, input):
+        """Run the coding loop and return the real bitstream: {'bits': uint8 [T, B, code*H*W/512] (iteration-major,
+        so bits[:t] is the rate-t prefix), 'size': (H, W), 'label': node ids}.  1 bit per symbol, numpy packbits
+        order over the NCHW code tensor of each image."""
+        was_training = self.training
+        self.train(False)
+        try:
+            with torch.no_grad():
+                res = self._run_engine(input['img'], input['label'], None)
+        finally:
+            self.train(was_training)
+            apply_fn(self, 'free_hidden')
+        return {'bits': res['bits'], 'size': tuple(input['img'].shape[2:]), 'label': input['label']}
+
+    def decode(self, bits, label, size=(32, 32)):
+        """Decoder-only reconstruction from a bitstream prefix bits[:t] (t <= T): list of t cumulative
+        reconstructions, bit-identical to forward()['img'][:t] for the same weights."""
+        self._ensure_engine()
+        sd = {k: v for k, v in self.named_parameters()}
+        with torch.no_grad():
+            res = self._engine.decode(sd, bits, label, tuple(size))
+        apply_fn(self, 'free_hidden')
+        return [res['recon'][t] for t in range(res['recon'].shape[0])]
+
+    @staticmethod
+    def unpack_bits(bits, code_shape):
+        """uint8 [..., n/8] -> float +-1 symbols [..., *code_shape] (inverse of the device bit-pack)"""
+        shifts = torch.arange(7, -1, -1, device=bits.device, dtype=torch.uint8)
+        b = (bits.unsqueeze(-1) >> shifts) & 1
+        return (b.reshape(bits.shape[:-1] + tuple(code_shape)).float() * 2 - 1)
 
     def forward(self, input, noise=None):
         """input: {'img': [B,C,H,W] in [0,1], 'label': [B] node ids}; returns {'loss', 'img': list of T
@@ -167,17 +199,22 @@ class CodecModel(nn.Module):
         img, label = input['img'], input['label']
         params = [p for p in self.parameters()]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        mse = None
+        use_graph = config.PARAM.get('cuda_graph', False) and config.PARAM.get('node_iters') is None
         if need_grad:
             loss, recon, codes, bits = _LoopFunction.apply(self, img, label, noise, *params)
         else:
-            if config.PARAM.get('cuda_graph', False):
+            if use_graph:
                 res, _ = self._run_graphed(img, label, noise)
             else:
                 res = self._run_engine(img, label, noise)
             loss = CodecEngine.loss_from_acc(res['loss_acc'], img.numel())
             recon, codes, bits = res['recon'], res['codes'], res['bits']
+            mse = (res['loss_acc'][:, 1] / float(img.numel())).float()   # per-iteration MSE, stays on the device
         T = recon.shape[0]
         output = {'loss': loss, 'img': [recon[t] for t in range(T)], 'code': [], 'code_pm1': codes, 'bits': bits}
+        if mse is not None:
+            output['mse'] = mse                                     # metrics.psnr_per_iteration(output)
         if config.PARAM.get('pack_mode', 'reference') == 'bits':
             b = bits.cpu().numpy()                                  # one D2H per forward
             output['code'] = [np.ascontiguousarray(b[:t + 1].transpose(1, 2, 0).reshape(-1, t + 1)) for t in range(T)]

@@ -100,6 +100,9 @@ typedef struct {
   float* d0_out_f32;
   const int* group_img_end;       /* device [max(n_enc_groups,n_dec_groups)]: exclusive end slot per node */
   int B_pad, HW, Ch, code, n_enc_groups, n_dec_groups, precise, split;
+  const uint8_t* bits_in;         /* nullable.  Non-null = decode-only: the symbols come from this packed stream
+                                     ([B, code*HW/8], the layout of bits_out) instead of encoder tail + quantizer;
+                                     h_e3 / w_e4 are then unused (may be NULL) */
 } drasic_bottleneck_args;
 int drasic_bottleneck_fwd(const drasic_bottleneck_args* a, void* stream);
 
@@ -113,6 +116,10 @@ typedef struct {
   void* e1_in_hi; void* e1_in_lo; const int* perm;
   const int* group_img_end;       /* device, as above */
   int B_pad, C, H, W, mode, loss_kind, n_enc_groups, n_dec_groups, precise, split;
+  const int* group_iters;         /* nullable: device [n_enc_groups] iteration budget per node (heterogeneous rates,
+                                     BASELINE config 4): at iter >= budget the node's decoded refinement is zero */
+  int iter;                       /* iteration index of this call (used with group_iters) */
+  /* img == NULL (with mode != INIT and e1_in_hi == NULL) = decode-only: no loss, no residual */
 } drasic_tail_head_args;
 int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream);
 
@@ -185,6 +192,8 @@ typedef struct {
   float* dh_d3; float* dw_d4; const int* perm; const int* group_img_end;
   float loss_scale;
   int B_pad, C, H, W, first, loss_kind, n_dec_groups, has_acc;
+  const int* group_iters;         /* nullable, as in drasic_tail_head_args: frozen nodes pass no gradient to the decoder */
+  int iter, n_enc_groups;
 } drasic_tail_bwd_args;
 int drasic_tail_bwd(const drasic_tail_bwd_args* a, void* stream);
 

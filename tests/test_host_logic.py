@@ -129,3 +129,36 @@ def test_plane_layout_round_trip(order):
     assert (back - x).abs().max() < 2e-7          # hi + lo carries ~22 significand bits
     if order == B.ORDER_QUAD:                     # physical p = q*(C/4)+c  <->  logical c*4+q
         assert torch.allclose(rec[0, 1, 2, 1 * 4 + 3], x[0, 3 * 4 + 1, 1, 2], atol=2e-7)
+
+
+def test_oracle_decoder_half_reproduces_forward_reconstructions():
+    """codec_decode (decoder half alone, fed the emitted symbols) == codec_forward's reconstructions; the
+    real bitstream round-trips through pack_bits / unpack_bits"""
+    import torch
+    from oracle import drasic_oracle as O
+    for separate, M in ((False, 3), (True, 2)):
+        sd = O.init_state_dict(3, 8, M, separate=separate, seed=1)
+        g = torch.Generator().manual_seed(2)
+        img = torch.rand(5, 3, 32, 32, generator=g)
+        label = torch.randint(0, M, (5,), generator=g)
+        with torch.no_grad():
+            ref = O.codec_forward(sd, img, label, 3, M, separate=separate)
+            dec = O.codec_decode(sd, ref['code_pm1'], label, M, separate=separate)
+        for a, b in zip(dec, ref['img']):
+            assert torch.allclose(a, b, atol=1e-6)
+        bits = O.pack_bits(ref['code_pm1'][0])
+        assert bits.shape == (5, 16)
+        assert torch.equal(O.unpack_bits(bits, (8, 4, 4)), ref['code_pm1'][0])
+
+
+def test_metrics_module_definitions_on_cpu_tensors():
+    import torch
+    import metrics
+    from oracle import drasic_oracle as O
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(4, 3, 32, 32, generator=g), torch.rand(4, 3, 32, 32, generator=g)
+    assert abs(metrics.PSNR(a, b) - O.psnr(a, b)) < 1e-4
+    code = np.zeros((4 * 16, 3), dtype=np.uint8)
+    assert metrics.BPP(code, a) == O.bpp(code, a)
+    out = {'mse': torch.tensor([0.01, 0.001])}
+    assert np.allclose(metrics.psnr_per_iteration(out), [20.0, 30.0], atol=1e-4)
