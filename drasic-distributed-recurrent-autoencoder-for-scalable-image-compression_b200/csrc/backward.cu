@@ -92,6 +92,99 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdParams p) {
   if ((threadIdx.x & 31) == 0 && amax > 0.0f) atomicMax(p.amax_bits, __float_as_uint(amax));
 }
 
+// ------------------------------------------------------------------ fused: cell backward -> scaled fp16 planes
+__device__ __forceinline__ int shift_for(float amax, int target_exp) {
+  if (!(amax > 0.0f) || !isfinite(amax)) return 0;
+  int e;
+  frexpf(amax, &e);   // amax * 2^(target_exp - e) in [2^(target_exp-1), 2^target_exp)
+  return target_exp - e;
+}
+
+__global__ void __launch_bounds__(256, 3) lstm_bwd_fused_kernel(const LstmBwdFusedParams p) {
+  // predicted scale: the previous iteration's amax lands in [2^11, 2^12) -- 16x head-room for growth
+  const int shift_pred = shift_for(__uint_as_float(*p.prev_amax_bits), 12);
+  int shift = shift_pred;
+  if (p.verify) {
+    const float a = __uint_as_float(*p.amax_bits);
+    if (!(a > 0.0f)) return;                                 // all-zero tensor: any scale is exact
+    const float scaled = ldexpf(a, shift_pred);
+    if (isfinite(a) && scaled >= 16.0f && scaled <= 60000.0f) return;   // the prediction was good enough
+    shift = shift_for(a, 14);                                // exact: [2^13, 2^14)
+  }
+  const float scale = ldexpf(1.0f, shift);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.inv_scale_out = ldexpf(1.0f, -shift);
+  const int Co = p.Co;
+  const size_t n_vec = p.n_pix * Co / 8;
+  float amax = 0.0f;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < n_vec; v += stride) {
+    const size_t e0 = v * 8;
+    const size_t pix = e0 / Co;
+    const int ch = static_cast<int>(e0 - pix * Co);
+    auto ld8 = [](const float* src, float (&dst)[8]) {
+      const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+      dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+    };
+    float gi[8], gf[8], gg[8], go[8];
+    if (p.gates_f32) {
+      const float* gp = reinterpret_cast<const float*>(p.gates) + pix * (4 * Co) + ch;
+      ld8(gp, gi); ld8(gp + Co, gf); ld8(gp + 2 * Co, gg); ld8(gp + 3 * Co, go);
+    } else {
+      const __half* gp = reinterpret_cast<const __half*>(p.gates) + pix * (4 * Co) + ch;
+      auto ldh = [](const __half* src, float (&dst)[8]) {
+        alignas(16) __half t[8];
+        *reinterpret_cast<uint4*>(t) = *reinterpret_cast<const uint4*>(src);
+        for (int i = 0; i < 8; ++i) dst[i] = __half2float(t[i]);
+      };
+      ldh(gp, gi); ldh(gp + Co, gf); ldh(gp + 2 * Co, gg); ldh(gp + 3 * Co, go);
+    }
+    float ct[8], cp[8], dh[8], dcv[8];
+    ld8(p.c_t + e0, ct);
+    if (p.c_prev) ld8(p.c_prev + e0, cp);
+    else for (int i = 0; i < 8; ++i) cp[i] = 0.0f;
+    ld8(p.dh_above + e0, dh);
+    if (p.dh_rec) {
+      float r[8];
+      ld8(p.dh_rec + e0, r);
+      for (int i = 0; i < 8; ++i) dh[i] += r[i];
+    }
+    if (p.dc_in) ld8(p.dc_in + e0, dcv);
+    else for (int i = 0; i < 8; ++i) dcv[i] = 0.0f;
+    float d4[4][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float ig = gi[i], fg = gf[i], cg = gg[i], og = go[i];
+      const float tc = tanhf(ct[i]);
+      const float dct = fmaf(dh[i] * og, 1.0f - tc * tc, dcv[i]);
+      d4[3][i] = dh[i] * tc * og * (1.0f - og);
+      d4[0][i] = dct * cg * ig * (1.0f - ig);
+      d4[1][i] = dct * cp[i] * fg * (1.0f - fg);
+      d4[2][i] = dct * ig * (1.0f - cg * cg);
+      dcv[i] = dct * fg;
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d4[0][i]), fabsf(d4[1][i])), fmaxf(fabsf(d4[2][i]), fabsf(d4[3][i]))));
+    }
+    reinterpret_cast<float4*>(p.dc_out + e0)[0] = make_float4(dcv[0], dcv[1], dcv[2], dcv[3]);
+    reinterpret_cast<float4*>(p.dc_out + e0)[1] = make_float4(dcv[4], dcv[5], dcv[6], dcv[7]);
+    const size_t goff = pix * (4 * Co) + ch;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      alignas(16) __half h[8], l[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float s = d4[g][i] * scale;
+        h[i] = __float2half_rn(s);
+        l[i] = __float2half_rn(s - __half2float(h[i]));
+      }
+      *reinterpret_cast<uint4*>(p.hi + goff + g * Co) = *reinterpret_cast<const uint4*>(h);
+      if (p.lo) *reinterpret_cast<uint4*>(p.lo + goff + g * Co) = *reinterpret_cast<const uint4*>(l);
+    }
+  }
+  if (!p.verify) {
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0 && amax > 0.0f) atomicMax(p.amax_bits, __float_as_uint(amax));
+  }
+}
+
 // ------------------------------------------------------------------ fp32 -> scaled fp16 planes
 __global__ void __launch_bounds__(256) convert_scale_kernel(const ConvertParams p) {
   const float amax = __uint_as_float(*p.amax_bits);
@@ -563,6 +656,10 @@ inline int grid_for(size_t work_items, int threads) {
 
 int launch_lstm_bwd(const LstmBwdParams& p, cudaStream_t stream) {
   lstm_bwd_kernel<<<grid_for(p.n_pix * p.Co / 8, 256), 256, 0, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream) {
+  lstm_bwd_fused_kernel<<<grid_for(p.n_pix * p.Co / 8, 256), 256, 0, stream>>>(p);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_convert_scale(const ConvertParams& p, cudaStream_t stream) {

@@ -22,6 +22,24 @@ struct LstmBwdParams {
   int Co;
 };
 
+// Fused variant: cell backward that writes the scaled fp16 {hi, lo} operand planes of the dgrad / wgrad GEMMs
+// directly (no fp32 gate-gradient round trip).  The per-tensor power-of-two scale is *predicted* from the
+// amax of the previously processed iteration; the kernel also records the true amax.  A second launch
+// with verify != 0 re-does the tensor with the exact scale only if the prediction left the scaled amax
+// outside [2^4, 2^15.9] (it returns immediately otherwise).  Both launches read the same inputs.
+struct LstmBwdFusedParams {
+  const void* gates; int gates_f32;
+  const float* c_t; const float* c_prev;   // c_prev nullable (t == 0)
+  const float* dh_above; const float* dh_rec;   // dh_rec nullable (t == T-1)
+  const float* dc_in;                      // nullable (t == T-1): dL/dc_t carried from step t+1
+  float* dc_out;                           // dL/dc_{t-1} (a different buffer than dc_in)
+  __half* hi; __half* lo;                  // [P, 4, Co] scaled gate gradients; lo nullable
+  const unsigned int* prev_amax_bits;      // amax (float bits) of the previously processed iteration; 0 = unknown
+  unsigned int* amax_bits;                 // out: true amax of this tensor (zero before the first launch)
+  float* inv_scale_out;                    // out: 1 / scale actually in the planes
+  size_t n_pix; int Co; int verify;
+};
+
 // fp32 -> fp16 {hi, lo} planes with an exact power-of-two scale derived from amax
 struct ConvertParams {
   const float* src;
@@ -94,6 +112,7 @@ struct HeadBwdParams {
 
 int launch_lstm_bwd(const LstmBwdParams& p, cudaStream_t stream);
 int launch_convert_scale(const ConvertParams& p, cudaStream_t stream);
+int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream);
 int launch_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
                               int out_order, __half* out_hi, __half* out_lo, float* inv_scale_out,
                               unsigned int* scratch_amax, cudaStream_t stream);

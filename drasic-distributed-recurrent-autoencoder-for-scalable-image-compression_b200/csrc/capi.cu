@@ -294,6 +294,20 @@ int drasic_lstm_bwd_pointwise(const void* gates, int gates_f32, const float* c_t
   return cuda_fail(drasic::launch_lstm_bwd(p, static_cast<cudaStream_t>(stream)), "lstm_bwd_pointwise launch");
 }
 
+int drasic_lstm_bwd_fused(const drasic_lstm_bwd_fused_args* a, void* stream) {
+  if (!a || !a->gates || !a->c_t || !a->dh_above || !a->dc_out || !a->dg_hi || !a->prev_amax_bits || !a->amax_bits ||
+      !a->inv_scale_out || a->Co % 8 || a->n_pix == 0 || a->dc_in == a->dc_out)
+    return fail(DRASIC_ERR_INVALID, "lstm_bwd_fused: bad argument");
+  drasic::LstmBwdFusedParams p;
+  p.gates = a->gates; p.gates_f32 = a->gates_f32; p.c_t = a->c_t; p.c_prev = a->c_prev; p.dh_above = a->dh_above;
+  p.dh_rec = a->dh_rec; p.dc_in = a->dc_in; p.dc_out = a->dc_out;
+  p.hi = static_cast<__half*>(a->dg_hi); p.lo = static_cast<__half*>(a->dg_lo);
+  p.prev_amax_bits = static_cast<const unsigned int*>(a->prev_amax_bits);
+  p.amax_bits = static_cast<unsigned int*>(a->amax_bits); p.inv_scale_out = a->inv_scale_out;
+  p.n_pix = a->n_pix; p.Co = a->Co; p.verify = a->verify;
+  return cuda_fail(drasic::launch_lstm_bwd_fused(p, static_cast<cudaStream_t>(stream)), "lstm_bwd_fused launch");
+}
+
 int drasic_convert_scale(const float* src, void* hi, void* lo, const void* amax_bits,
                          float* inv_scale_out, size_t n, void* stream) {
   if (!src || !hi || !amax_bits || !inv_scale_out || n == 0 || n % 8)

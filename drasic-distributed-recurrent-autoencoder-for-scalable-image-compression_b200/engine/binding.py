@@ -49,6 +49,12 @@ class WgradArgs(C.Structure):
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'has_h', 'split', 'k_splits', 'cta_pair')]
 
 
+class LstmBwdFusedArgs(C.Structure):
+    _fields_ = [(n, vp) for n in ('gates', 'c_t', 'c_prev', 'dh_above', 'dh_rec', 'dc_in', 'dc_out', 'dg_hi', 'dg_lo',
+                                  'prev_amax_bits', 'amax_bits', 'inv_scale_out')] + [('n_pix', C.c_size_t)] + \
+               [(n, ip) for n in ('Co', 'gates_f32', 'verify')]
+
+
 class BottleneckBwdArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('dd0', 'h_e3', 'z', 'codes', 'w_e4', 'w_d0', 'perm', 'group_img_end', 'dh_e3',
                                   'dw_e4', 'dw_d0')] + \
@@ -73,7 +79,7 @@ DX_SAME, DX_INV_DOWN, DX_INV_UP = 0, 1, 2
 # every symbol include/drasic_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes',
            'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
-           'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_pointwise', 'drasic_convert_scale',
+           'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_pointwise', 'drasic_convert_scale', 'drasic_lstm_bwd_fused',
            'drasic_pack_dgrad_weights', 'drasic_convlstm_bwd_data', 'drasic_convlstm_bwd_weight',
            'drasic_unpack_wgrad', 'drasic_bottleneck_bwd', 'drasic_tail_bwd', 'drasic_head_bwd')
 
@@ -113,6 +119,8 @@ def lib():
     L.drasic_lstm_bwd_pointwise.argtypes = [vp, ip, vp, vp, vp, vp, vp, ip, vp, vp, C.c_size_t, ip, vp]
     L.drasic_convert_scale.restype = C.c_int
     L.drasic_convert_scale.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.drasic_lstm_bwd_fused.restype = C.c_int
+    L.drasic_lstm_bwd_fused.argtypes = [C.POINTER(LstmBwdFusedArgs), vp]
     L.drasic_pack_dgrad_weights.restype = C.c_int
     L.drasic_pack_dgrad_weights.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, vp]
     L.drasic_convlstm_bwd_data.restype = C.c_int

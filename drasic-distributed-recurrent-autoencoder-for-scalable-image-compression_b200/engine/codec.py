@@ -578,11 +578,11 @@ class CodecEngine(object):
         W_ = {}
         for ly in layers:
             n = (Bp, ly.h, ly.w, ly.co)
-            W_[ly.name] = dict(dh_above=torch.zeros(n, **f32), dh_rec=torch.zeros(n, **f32), dc=torch.zeros(n, **f32),
-                               dgates=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f32),
+            W_[ly.name] = dict(dh_above=torch.zeros(n, **f32), dh_rec=torch.zeros(n, **f32),
+                               dc=[torch.zeros(n, **f32), torch.zeros(n, **f32)],     # ping-pong: in (t+1) / out (t)
                                dg_hi=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16),
                                dg_lo=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16) if self.gsplit else None,
-                               amax=torch.zeros((1,), dtype=torch.int32, device=dev),
+                               last_amax=torch.zeros((1,), dtype=torch.int32, device=dev),   # carried across steps
                                inv=torch.ones((1,), **f32))
         W_['du1'] = torch.zeros((Bp, H // 2, W // 2, 128), **f32)
         W_['dd0'] = torch.zeros((Bp, H // 8, W // 8, 128), **f32)
@@ -615,6 +615,8 @@ class CodecEngine(object):
         dpk = {ly.name: self._packed_dgrad(ly, sd, stream) for ly in layers}
         by = {ly.name: ly for ly in layers}
         sms = self.sms()
+        # true amax (float bits) of every (layer, iteration) gate-gradient tensor of this backward pass
+        amax_tab = {ly.name: torch.zeros((T,), dtype=torch.int32, device=dev) for ly in layers}
 
         def group_kb_end(ly):
             return plan.kb_end(ly.h * ly.w)
@@ -629,14 +631,22 @@ class CodecEngine(object):
         def lstm_layer_bwd(ly, t):
             Lb, wb = A[ly.name], WB[ly.name]
             n_pix = Bp * ly.h * ly.w
-            wb['amax'].zero_()
-            self._timed('lstm_bwd', 0.0, lambda: B.check(L.drasic_lstm_bwd_pointwise(
-                P(Lb['gates'][t]), self.gsplit, P(Lb['c'][t]), P(Lb['c'][t - 1]) if t > 0 else None,
-                P(wb['dh_above']), P(wb['dh_rec']) if t < T - 1 else None, P(wb['dc']),
-                1 if t < T - 1 else 0, P(wb['dgates']), P(wb['amax']), n_pix, ly.co, stream), 'lstm_bwd_pointwise'))
-            self._timed('convert_scale', 0.0, lambda: B.check(L.drasic_convert_scale(
-                P(wb['dgates']), P(wb['dg_hi']), P(wb['dg_lo']), P(wb['amax']), P(wb['inv']),
-                n_pix * 4 * ly.co, stream), 'convert_scale'))
+            # fused cell backward -> scaled fp16 planes; scale predicted from the previously processed iteration
+            am = amax_tab[ly.name]
+            prev = am[t + 1:t + 2] if t < T - 1 else wb['last_amax']
+            f = B.LstmBwdFusedArgs()
+            f.gates, f.gates_f32 = P(Lb['gates'][t]), self.gsplit
+            f.c_t, f.c_prev = P(Lb['c'][t]), P(Lb['c'][t - 1]) if t > 0 else None
+            f.dh_above, f.dh_rec = P(wb['dh_above']), P(wb['dh_rec']) if t < T - 1 else None
+            f.dc_in = P(wb['dc'][(t + 1) & 1]) if t < T - 1 else None
+            f.dc_out = P(wb['dc'][t & 1])
+            f.dg_hi, f.dg_lo = P(wb['dg_hi']), P(wb['dg_lo'])
+            f.prev_amax_bits, f.amax_bits, f.inv_scale_out = prev.data_ptr(), am[t:t + 1].data_ptr(), P(wb['inv'])
+            f.n_pix, f.Co = n_pix, ly.co
+            for verify in (0, 1):
+                f.verify = verify
+                self._timed('lstm_bwd' if not verify else 'lstm_bwd_verify', 0.0,
+                            lambda: B.check(L.drasic_lstm_bwd_fused(f, stream), 'lstm_bwd_fused'))
             hi, lo, inv = dpk[ly.name]
             a = B.DgradArgs()
             a.dg_hi, a.dg_lo, a.w_hi, a.w_lo = P(wb['dg_hi']), P(wb['dg_lo']), P(hi), P(lo)
@@ -666,7 +676,7 @@ class CodecEngine(object):
             kb_per_group = max(1, Bp * ly.h * ly.w // 64 // ly.groups)
             w.k_splits = _pick_k_splits(tiles, units, max(1, kb_per_group // 16))
             self._timed('wgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_weight(w, stream), 'convlstm_bwd_weight'))
-            self.launches += 5
+            self.launches += 4
 
         loss_scale = 1.0 / (T * float(Bn * Cc * H * W))
         for t in range(T - 1, -1, -1):
@@ -700,6 +710,8 @@ class CodecEngine(object):
             self._timed('head_bwd', 0.0, lambda: B.check(L.drasic_head_bwd(h, stream), 'head_bwd'))
             self.launches += 3
 
+        for ly in layers:
+            WB[ly.name]['last_amax'].copy_(amax_tab[ly.name][T - 1:T])
         grads = {}
         for ly in layers:
             for g, pref in enumerate(ly.prefs):

@@ -136,6 +136,21 @@ int drasic_lstm_bwd_pointwise(const void* gates, int gates_f32, const float* c_t
                               const float* dh_above, const float* dh_rec, float* dc, int has_dc,
                               float* dgates, void* amax_bits, size_t n_pix, int Co, void* stream);
 
+/* The two calls above fused (no fp32 gate-gradient round trip): cell backward writing the scaled fp16
+ * {hi,lo} planes directly.  The power-of-two scale is predicted from *prev_amax_bits (the amax of the
+ * previously processed iteration; 0 = unknown); the true amax is recorded in *amax_bits (must be zero
+ * before the first call).  Call once with verify = 0, then once with verify = 1: the second call returns
+ * immediately unless the prediction left the scaled amax outside [2^4, 2^15.9], in which case it redoes
+ * the tensor with the exact scale.  dc_in / dc_out must be different buffers. */
+typedef struct {
+  const void* gates; const float* c_t; const float* c_prev; const float* dh_above; const float* dh_rec;
+  const float* dc_in; float* dc_out; void* dg_hi; void* dg_lo;
+  const void* prev_amax_bits; void* amax_bits; float* inv_scale_out;
+  size_t n_pix;
+  int Co, gates_f32, verify;
+} drasic_lstm_bwd_fused_args;
+int drasic_lstm_bwd_fused(const drasic_lstm_bwd_fused_args* a, void* stream);
+
 /* fp32 -> fp16 {hi,lo} planes scaled by 2^k so that amax lands in [2^13, 2^14); writes 2^-k. n % 8 == 0 */
 int drasic_convert_scale(const float* src, void* hi, void* lo, const void* amax_bits,
                          float* inv_scale_out, size_t n, void* stream);
