@@ -77,7 +77,9 @@ class CellRunner(object):
                 block_n = bn
                 break
         key = (w_in.data_ptr(), w_in._version, w_h.data_ptr(), w_h._version, block_n)
-        if key != self._wkey:
+        # re-packed at the start of every sequence as well: fused optimizers update parameters in place without
+        # bumping Tensor._version, so the version key alone cannot be trusted
+        if key != self._wkey or self.h is None:
             K = 9 * (cin + co)
             hi = torch.empty((4 * co, K), dtype=torch.float16, device=dev)
             lo = torch.empty((4 * co, K), dtype=torch.float16, device=dev)

@@ -145,6 +145,12 @@ class CodecEngine(object):
         self._sms = None
         self.launches = 0   # kernels launched by the last forward() (bench.py reports it)
         self.force_pack = False  # True while capturing a CUDA graph: always re-pack into the same buffers
+        # Fused optimizers (torch.optim.Adam(fused=True), the multi-tensor kernels) update parameters in place
+        # WITHOUT bumping Tensor._version, so (data_ptr, _version) alone cannot validate the packed-weight
+        # cache: a forward that saves state for backward always re-packs (the weights are about to change
+        # anyway) and leaves the cache marked stale for whatever forward comes next.
+        self._stale = False
+        self._repack = False
         self.profile = None  # set to [] to collect (label, flops, start_event, end_event) per launch
 
     # ------------------------------------------------------------------ helpers
@@ -227,7 +233,7 @@ class CodecEngine(object):
         """weights: list over groups of (w_in, w_h) fp32 tensors. Cached on tensor identity+version."""
         key = (name, block_n) + tuple((w.data_ptr(), w._version) for pair in weights for w in pair)
         hit = self._wcache.get(name)
-        if hit is not None and hit[0] == key and not self.force_pack:
+        if hit is not None and hit[0] == key and not (self.force_pack or self._repack):
             return hit[1]
         L = B.lib()
         G = len(weights)
@@ -310,6 +316,7 @@ class CodecEngine(object):
         enc_pref = ['model.encoder.{}'.format(j) for j in range(self.M)]
         dec_pref = ['model.decoder.{}'.format(j) for j in range(self.M)] if self.separate else ['model.decoder']
         layers = []
+        self._repack = bool(save_for_backward or self._stale)
         for (name, cin, co, div, io, oo, nmode, nf32) in ENC_LAYERS + DEC_LAYERS:
             is_enc = name[0] == 'E'
             prefs = enc_pref if is_enc else dec_pref
@@ -328,6 +335,8 @@ class CodecEngine(object):
             ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
             layers.append(ly)
 
+        self._repack = False
+        self._stale = bool(save_for_backward)
         if pack_only:
             return None
 
@@ -476,6 +485,7 @@ class CodecEngine(object):
         def stack(keys):
             return torch.stack([sd[k].detach().float().reshape(sd[k].shape[0], -1) for k in keys]).contiguous()
         layers = []
+        self._repack = bool(self._stale)
         for (name, cin, co, div, io, oo, nmode, nf32) in DEC_LAYERS:
             h, w = H // div, W // div
             n_mtiles = Bp * h * w // 128
@@ -488,6 +498,7 @@ class CodecEngine(object):
                                                    ly.block_n, stream)[:3]
             ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
             layers.append(ly)
+        self._repack = False      # (the encoder planes stay stale: _stale is cleared only by a full forward)
         w_d0 = stack([p + '.0.cell.cell.main.weight' for p in dec_pref])
         w_d4 = stack([p + '.7.cell.cell.main.weight' for p in dec_pref])
         recon = torch.empty((T, Bn, self.C, H, W), dtype=torch.float32, device=dev)
@@ -545,7 +556,7 @@ class CodecEngine(object):
         weights = [lstm_w(p, ly.idx) for p in ly.prefs]
         key = tuple((w.data_ptr(), w._version) for pair in weights for w in pair)
         hit = self._wcache.get('dgrad_' + ly.name)
-        if hit is not None and hit[0] == key and not self.force_pack:
+        if hit is not None and hit[0] == key and not (self.force_pack or self._repack):
             return hit[1][:3]
         L = B.lib()
         dev = weights[0][0].device
@@ -612,7 +623,9 @@ class CodecEngine(object):
         db_e0 = torch.zeros_like(ctx['b_e0']) if ctx['b_e0'] is not None else None
         dw_e4, dw_d0, dw_d4 = torch.zeros_like(ctx['w_e4']), torch.zeros_like(ctx['w_d0']), torch.zeros_like(ctx['w_d4'])
         gw = {ly.name: torch.zeros((ly.groups, 4 * ly.co, 9 * (ly.cin + ly.co)), **f32) for ly in layers}
+        self._repack = True      # once per step; parameter versions cannot be trusted (fused optimizers)
         dpk = {ly.name: self._packed_dgrad(ly, sd, stream) for ly in layers}
+        self._repack = False
         by = {ly.name: ly for ly in layers}
         sms = self.sms()
         # true amax (float bits) of every (layer, iteration) gate-gradient tensor of this backward pass
@@ -786,7 +799,7 @@ class GraphedCodec(object):
         return tuple(v._version for v in self.sd.values())
 
     def _refresh_weights(self):
-        if self._versions() == self._seen:
+        if self._versions() == self._seen and not self.eng._stale:
             return
         # a parameter changed since capture: re-pack eagerly into the buffers the graph reads
         self.eng.force_pack = True

@@ -129,6 +129,51 @@ def test_optimizer_trajectory_follows_oracle_and_weights_are_repacked():
     assert (out['code_pm1'].cpu() != torch.stack(ref['code_pm1'])).float().mean().item() < 5e-3
 
 
+def test_fused_adam_updates_reach_the_packed_weights():
+    """torch.optim.Adam(fused=True) (train_model.py:161 on a CUDA box) updates parameters in place WITHOUT
+    bumping Tensor._version; the packed fp16 weight planes must follow anyway.  After two steps the model
+    must behave exactly like a fresh model (fresh engine, fresh packing) loaded with its state_dict, and
+    its loss trajectory must track the CPU oracle's Adam."""
+    m = build_model('dist_codec', 'CIFAR10', 2, 3, seed=15)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True)
+    opt_ref = torch.optim.Adam(list(sd.values()), lr=1e-3)
+    g = torch.Generator().manual_seed(16)
+    img = torch.rand(8, 3, 32, 32, generator=g)
+    label = torch.randint(0, 2, (8,), generator=g)
+    inp = {'img': img.cuda(), 'label': label.cuda()}
+    v0 = [p._version for p in m.parameters()]
+    losses = []
+    for it in range(3):
+        noise = torch.rand(3, 8, 8, 4, 4, generator=g)
+        opt_ref.zero_grad()
+        ref = O.codec_forward(sd, img, label, 3, 2, training=True, noise=[n for n in noise])
+        ref['loss'].backward()
+        opt_ref.step()
+        m.train(True)
+        opt.zero_grad()
+        out = m(inp, noise=noise.cuda())
+        out['loss'].backward()
+        opt.step()
+        losses.append((out['loss'].item(), ref['loss'].item()))
+    assert [p._version for p in m.parameters()] == v0          # the premise: versions did not move
+    assert losses[0][0] != losses[2][0]                         # ... while the weights did
+    for a, b in losses:
+        assert abs(a - b) < 5e-4, losses
+    m.train(False)
+    with torch.no_grad():
+        out = m(inp)
+    m2 = build_model('dist_codec', 'CIFAR10', 2, 3, seed=99)
+    m2.load_state_dict(m.state_dict())
+    m2.train(False)
+    with torch.no_grad():
+        out2 = m2(inp)
+    assert torch.equal(out['code_pm1'], out2['code_pm1']) and torch.equal(out['img'][-1], out2['img'][-1])
+    # the decoder-only path sees the updated weights too
+    rec = m.decode(out['bits'], inp['label'])
+    assert torch.equal(rec[-1], out['img'][-1])
+
+
 def test_backward_requires_matching_forward():
     m = build_model('dist_codec', 'MNIST', 1, 2, seed=0)
     inp = {'img': torch.rand(4, 1, 32, 32).cuda(), 'label': torch.zeros(4, dtype=torch.long).cuda()}
