@@ -61,12 +61,16 @@ struct WTile {
 __device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile, int m_units) {
   const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
   WTile t;
-  const int ks = tile % p.k_splits;
-  int r = tile / p.k_splits;
+  // order: N tile fastest, then M unit, then K split, then node -- the tiles that run concurrently on the
+  // persistent grid share their K range, so its dG / activation pixels come from DRAM once and are then
+  // served from L2 to the other (M, N) tiles (with the K split fastest every wave re-read the whole tensor)
+  int r = tile;
   const int nt = r % nt_total;
   r /= nt_total;
   t.mt = r % m_units;      // M tile (single CTA) or pair of M tiles (CTA pair)
-  t.g = r / m_units;
+  r /= m_units;
+  const int ks = r % p.k_splits;
+  t.g = r / p.k_splits;
   t.is_h = nt >= p.n_tiles_x;
   const int ntl = t.is_h ? nt - p.n_tiles_x : nt;
   const int units = 9 * ((t.is_h ? p.Co : p.Cin) / 64);
@@ -169,17 +173,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          if (!PAIR) ptx::mbar_expect_tx(&full_bar[stage], bytes);
-          else if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * bytes);
+          uint32_t xbytes = bytes;   // diagnostics: 3 = no A loads, 4 = no B loads, 5 = centre tap only
+          if (p.dbg == 3) xbytes = (SPLIT ? 2 : 1) * (my_units * BOX_BYTES);
+          if (p.dbg == 4) xbytes = (SPLIT ? 2 : 1) * C::A_BYTES;
+          if (!PAIR) ptx::mbar_expect_tx(&full_bar[stage], xbytes);
+          else if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * xbytes);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
             uint8_t* sa = st + pl * C::A_BYTES;
             uint8_t* sb = st + (SPLIT ? 2 : 1) * C::A_BYTES + pl * C::B_BYTES;
-            if (PAIR) ptx::tma_load_5d_pair(sa, &p.tm_g[pl], full_remote[stage], 0, x0, y0, n0, mt * 2);
+            if (p.dbg == 3) {
+            } else if (PAIR) ptx::tma_load_5d_pair(sa, &p.tm_g[pl], full_remote[stage], 0, x0, y0, n0, mt * 2);
             else ptx::tma_load_5d(sa, &p.tm_g[pl], &full_bar[stage], 0, x0, y0, n0, mt * 2);
+            if (p.dbg == 4) continue;
             for (int u = 0; u < my_units; u += 2) {   // a pair of 64-channel chunks of the same tap
               const int unit = my_u0 + u;
-              const int tap = unit / cpu, chunk = unit - tap * cpu;
+              int tap = unit / cpu;
+              const int chunk = unit - tap * cpu;
+              if (p.dbg == 5) tap = 4;
               if (PAIR)
                 ptx::tma_load_5d_pair(sb + u * BOX_BYTES, &tb[pl], full_remote[stage], 0, x0 + tap % 3 - 1,
                                       y0 + tap / 3 - 1, n0, chunk);
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           const uint32_t a_lo = a_hi + C::A_BYTES;
           const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * C::A_BYTES;
           const uint32_t b_lo = b_hi + C::B_BYTES;
-          if (p.dbg != 2)
+          if (p.dbg < 2)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {            // 4 x UMMA_K(16 pixels) per 64-pixel K block
             const uint32_t koff = k * 16 * 128;    // 16 K rows of 128 bytes
