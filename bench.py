@@ -288,6 +288,14 @@ def run_ours(args):
     achieved = g_fl / (g_ms * 1e-3) / 1e12
     mma_per_mac = 3 if args.precision == 'parity' else 1
     flop_per_img = FLOP_PER_IMG_FWD * (3 if train else 1)
+    # DRAM bytes per gate-kernel launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full capture
+    # committed as profiles/r1_ncu_full_eval_parity_B1024_summary.csv: one iteration t >= 1 moves
+    # E1 826 + E2 408 + E3 163 + D1 305 + D2 1190 + D3 794 MB = 3686 MB over 6 launches
+    traffic, traffic_note = None, 'no ncu capture for this configuration'
+    if args.precision == 'parity' and B == 1024:
+        traffic = 3686e6 / 6
+        traffic_note = ('forward gate kernels only, average per launch, from profiles/r1_ncu_full_eval_parity_B1024_summary.csv; '
+                        'algorithmic (compulsory) bytes of the same six launches: 1.9 GB (x, h hi+lo in; c in/out; h, consumer copy out; weights)')
     sd = {k: v for k, v in model.named_parameters()}
     line = {
         'metric': METRIC, 'value': world * B / ms * 1e3, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
@@ -314,7 +322,7 @@ def run_ours(args):
                      if train else 'conv_gemm_kernel<gates> (6 layers x 16 iterations)',
                      'achieved': achieved, 'peak': sust, 'unit': 'TFLOP/s', 'frac': achieved / sust,
                      'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained ({}); burst {}'.format(how, burst),
-                     'traffic': None, 'launches': g_n, 'avg_launch_ms': g_ms / max(g_n, 1),
+                     'traffic': traffic, 'traffic_note': traffic_note, 'launches': g_n, 'avg_launch_ms': g_ms / max(g_n, 1),
                      'share_of_step': g_ms / all_ms, 'tensor_mma_per_algorithmic_mac': mma_per_mac,
                      'per_kind_tflops': {kk: sum(v[2] for k, v in gate if k.startswith(kk)) / max(1e-9, sum(v[1] for k, v in gate if k.startswith(kk))) / 1e9
                                          for kk in ('gates', 'dgrad', 'wgrad') if any(k.startswith(kk) for k, _ in gate)},
