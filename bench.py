@@ -295,7 +295,7 @@ def run_ours(args):
     if args.precision == 'parity' and B == 1024:
         traffic = 3686e6 / 6
         traffic_note = ('forward gate kernels only, average per launch, from profiles/r1_ncu_full_eval_parity_B1024_summary.csv; '
-                        'algorithmic (compulsory) bytes of the same six launches: 1.9 GB (x, h hi+lo in; c in/out; h, consumer copy out; weights)')
+                        'compulsory bytes of the same six launches: 3.1 GB (x, h hi+lo in; c in/out; h, consumer copy out; weights) -> 1.19x')
     sd = {k: v for k, v in model.named_parameters()}
     line = {
         'metric': METRIC, 'value': world * B / ms * 1e3, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
