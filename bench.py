@@ -111,8 +111,10 @@ def run_reference(args):
     torch.set_num_threads(cores)
     train = args.mode == 'train'
     sd = O.init_state_dict(CHANNELS, 8, M_NODES, seed=0)
+    opt = None
     if train:
         sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+        opt = torch.optim.Adam(list(sd.values()), lr=1e-3)           # train_model.py:161
 
     def step(img, label, n_iter=T_ITER):
         if train:                                                    # forward + full BPTT, like train_model.py:113-115
@@ -120,6 +122,7 @@ def run_reference(args):
                 v.grad = None
             out = O.codec_forward(sd, img, label, n_iter, M_NODES, training=True)
             out['loss'].backward()
+            opt.step()                                               # train_model.py:116
         else:
             with torch.no_grad():
                 O.codec_forward(sd, img, label, n_iter, M_NODES)
@@ -147,7 +150,7 @@ def run_reference(args):
                    'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                          'sample': 'oracle/drasic_oracle.py codec_forward{}, B={} M=8 T=16 per step'.format(
-                             ' + backward (stochastic binarizer, full BPTT)' if train else ' (eval)', sample)},
+                             ' + backward (stochastic binarizer, full BPTT) + Adam step' if train else ' (eval)', sample)},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
