@@ -62,6 +62,7 @@ struct WgradParams {
   int n_kb;                 // total K blocks = B_pad*H*W/64
   int has_h;                // 0 at t == 0
   int n_groups, m_tiles, n_tiles_x, n_tiles_h, k_splits;
+  int wide;                 // CTA pairs only: 512-column tiles (n_tiles_* count units of 8 instead of 4)
   int dbg;                  // diagnostics only (env DRASIC_WGRAD_DBG): 1 = skip the TMA loads, 2 = skip the MMAs
 };
 

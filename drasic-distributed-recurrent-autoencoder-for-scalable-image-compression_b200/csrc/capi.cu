@@ -396,7 +396,9 @@ int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream) {
   p.H = H; p.W = W; p.Cin = Cin; p.Co = Co; p.kbw = kbw; p.kbh = kbh; p.kbn = kbn;
   p.n_kb = static_cast<int>(static_cast<long long>(B) * H * W / 64);
   p.has_h = a->has_h ? 1 : 0; p.n_groups = a->n_groups; p.m_tiles = 4 * Co / 128;
-  p.n_tiles_x = (9 * (Cin / 64) + 3) / 4; p.n_tiles_h = (9 * (Co / 64) + 3) / 4; p.k_splits = a->k_splits;
+  p.wide = (a->cta_pair == 2) ? 1 : 0;      // cta_pair: 0 single CTAs, 1 pairs with 256-column tiles, 2 pairs with 512-column tiles
+  const int upt = p.wide ? 8 : 4;
+  p.n_tiles_x = (9 * (Cin / 64) + upt - 1) / upt; p.n_tiles_h = (9 * (Co / 64) + upt - 1) / upt; p.k_splits = a->k_splits;
   {
     static const int dbg = getenv("DRASIC_WGRAD_DBG") ? atoi(getenv("DRASIC_WGRAD_DBG")) : 0;
     p.dbg = dbg;

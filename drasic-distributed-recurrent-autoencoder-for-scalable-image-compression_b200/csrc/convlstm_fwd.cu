@@ -368,6 +368,11 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t smem0 = ptx::smem_u32(smem);
+      const uint64_t desc_a_hi = ptx::umma_desc_sw128(smem0);
+      const uint64_t desc_a_lo = ptx::umma_desc_sw128(smem0 + A_TILE_BYTES);
+      const uint64_t desc_b_hi = ptx::umma_desc_sw128(smem0 + (SPLIT ? 2 : 1) * A_TILE_BYTES);
+      const uint64_t desc_b_lo = ptx::umma_desc_sw128(smem0 + (SPLIT ? 2 : 1) * A_TILE_BYTES + C::B_TILE_BYTES);
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
         // dgrad: the last N tile of a row may be narrower than BLOCK_N (UMMA N is a runtime field)
         int width = BLOCK_N;
@@ -381,18 +386,16 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t a_lo = a_hi + A_TILE_BYTES;
-          const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * A_TILE_BYTES;
-          const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+          // descriptors differ from the stage-0 / k-0 ones only in the 14-bit start-address field
+          const uint32_t st_off = static_cast<uint32_t>(stage) * (C::STAGE_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 2;  // bytes inside the 128-byte swizzle row
-            const uint64_t da_hi = ptx::umma_desc_sw128(a_hi + koff);
-            const uint64_t db_hi = ptx::umma_desc_sw128(b_hi + koff);
+            const uint32_t off = st_off + k * ((UMMA_K * 2) >> 4);  // bytes inside the 128-byte swizzle row
+            const uint64_t da_hi = desc_a_hi + off;
+            const uint64_t db_hi = desc_b_hi + off;
             if (SPLIT) {
-              const uint64_t da_lo = ptx::umma_desc_sw128(a_lo + koff);
-              const uint64_t db_lo = ptx::umma_desc_sw128(b_lo + koff);
+              const uint64_t da_lo = desc_a_lo + off;
+              const uint64_t db_lo = desc_b_lo + off;
               // small terms first, then the dominant one
               if (PAIR) {
                 ptx::umma_f16_pair(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0);

@@ -28,10 +28,15 @@ constexpr int WG_DATA_BUDGET = 196608;
 
 // PAIR: two CTAs of a cluster (cta_group::2) own 256 gate channels x up to 256 columns: each stages its own
 // 128 gate channels of dG and half of the activation columns (32 KB instead of 48 KB per K block and CTA).
-template <bool SPLIT, bool PAIR = false>
+// WIDE (pairs only): the pair owns 256 gate channels x up to 512 columns -- two N = 256 MMAs per K step that
+// share the dG operand, the whole TMEM as one accumulator (no epilogue overlap; wgrad tiles run for
+// hundreds of K blocks).  L2 -> SMEM bytes per unit of MMA work drop from 32 KB to 24 KB per CTA: the kernel
+// is bound by that fill rate (~43 B/clk/SM, the L2 throughput cap), not by the tensor pipe.
+template <bool SPLIT, bool PAIR = false, bool WIDE = false>
 struct WCfg {
+  static constexpr int UNITS = WIDE ? 8 : 4;                    // 64-column units per tile
   static constexpr int A_BYTES = 2 * BOX_BYTES;                 // 128 gate channels
-  static constexpr int B_BYTES = (PAIR ? 2 : 4) * BOX_BYTES;    // columns staged by one CTA
+  static constexpr int B_BYTES = (PAIR ? UNITS / 2 : UNITS) * BOX_BYTES;    // columns staged by one CTA
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int STAGES = WG_DATA_BUDGET / STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * WG_BLOCK_N;
@@ -58,7 +63,7 @@ struct WTile {
   int g, mt, is_h, u0, nunits, kb_lo, kb_hi;
 };
 
-__device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile, int m_units) {
+__device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile, int m_units, int upt) {
   const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
   WTile t;
   // order: N tile fastest, then M unit, then K split, then node -- the tiles that run concurrently on the
@@ -74,8 +79,8 @@ __device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile, int
   t.is_h = nt >= p.n_tiles_x;
   const int ntl = t.is_h ? nt - p.n_tiles_x : nt;
   const int units = 9 * ((t.is_h ? p.Co : p.Cin) / 64);
-  t.u0 = ntl * 4;
-  t.nunits = min(4, units - t.u0);
+  t.u0 = ntl * upt;
+  t.nunits = min(upt, units - t.u0);
   const int g_lo = (t.g == 0 || !p.group_kb_end) ? 0 : p.group_kb_end[t.g - 1];
   const int g_hi = p.group_kb_end ? p.group_kb_end[t.g] : p.n_kb;
   const int len = g_hi - g_lo;
@@ -85,9 +90,10 @@ __device__ __forceinline__ WTile decode_tile(const WgradParams& p, int tile, int
   return t;
 }
 
-template <bool SPLIT, bool PAIR>
+template <bool SPLIT, bool PAIR, bool WIDE>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using C = WCfg<SPLIT, PAIR>;
+  using C = WCfg<SPLIT, PAIR, WIDE>;
+  static_assert(!WIDE || PAIR, "wide tiles are a CTA-pair mode");
   const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
@@ -148,14 +154,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       if (PAIR)
         for (int s = 0; s < C::STAGES; ++s) full_remote[s] = ptx::mapa_u32(&full_bar[s], 0);
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
-        const WTile t = decode_tile(p, tile, m_units);
+        const WTile t = decode_tile(p, tile, m_units, C::UNITS);
         const CUtensorMap* tb = t.is_h ? p.tm_h : p.tm_x;
         const int cpu = (t.is_h ? p.Co : p.Cin) / 64;
         // a pair: this CTA stages gate channels of M tile 2*mt + rank and columns [rank*nunits/2, ...) --
         // always one 2-box TMA (with nunits == 2 its second box is unused filler)
         const int mt = PAIR ? 2 * t.mt + static_cast<int>(cta_rank) : t.mt;
-        const int my_u0 = PAIR ? t.u0 + static_cast<int>(cta_rank) * (t.nunits >> 1) : t.u0;
-        const int my_units = PAIR ? 2 : t.nunits;
+        // pairs: per MMA group of up to 4 units this CTA stages half of the group's units, always as one 2-box
+        // TMA (with a 2-unit group its second box is unused filler)
+        const int n_grp = WIDE ? (t.nunits + 3) >> 2 : 1;
+        const int my_units = PAIR ? 2 * n_grp : t.nunits;
         const uint32_t bytes = (SPLIT ? 2 : 1) * (C::A_BYTES + my_units * BOX_BYTES);
         for (int kb = t.kb_lo; kb < t.kb_hi; ++kb) {
           int n0, y0, x0;
@@ -187,7 +195,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             else ptx::tma_load_5d(sa, &p.tm_g[pl], &full_bar[stage], 0, x0, y0, n0, mt * 2);
             if (p.dbg == 4) continue;
             for (int u = 0; u < my_units; u += 2) {   // a pair of 64-channel chunks of the same tap
-              const int unit = my_u0 + u;
+              int unit = t.u0 + u;
+              if (PAIR) {
+                const int grp = WIDE ? u >> 1 : 0;
+                const int cnt = WIDE ? min(4, t.nunits - 4 * grp) : t.nunits;
+                unit = t.u0 + 4 * grp + static_cast<int>(cta_rank) * (cnt >> 1);
+              }
               int tap = unit / cpu;
               const int chunk = unit - tap * cpu;
               if (p.dbg == 5) tap = 4;
@@ -209,46 +222,60 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t smem0 = ptx::smem_u32(smem);
+      const uint64_t desc_a_hi = umma_desc_mn_sw128(smem0);
+      const uint64_t desc_a_lo = umma_desc_mn_sw128(smem0 + C::A_BYTES);
+      const uint64_t desc_b_hi = umma_desc_mn_sw128(smem0 + (SPLIT ? 2 : 1) * C::A_BYTES);
+      const uint64_t desc_b_lo = umma_desc_mn_sw128(smem0 + (SPLIT ? 2 : 1) * C::A_BYTES + C::B_BYTES);
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
-        const WTile t = decode_tile(p, tile, m_units);
+        const WTile t = decode_tile(p, tile, m_units, C::UNITS);
         if (t.kb_hi <= t.kb_lo) continue;  // empty node / empty k-split: nothing to add
-        const uint32_t idesc = idesc_mn(PAIR ? 256 : 128, t.nunits * 64);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        // MMA groups of up to 256 columns sharing the A operand (two only with WIDE tiles)
+        const int cnt0 = WIDE ? min(4, t.nunits) : t.nunits;
+        const int cnt1 = WIDE ? t.nunits - cnt0 : 0;
+        const uint32_t idesc0 = idesc_mn(PAIR ? 256 : 128, cnt0 * 64);
+        const uint32_t idesc1 = idesc_mn(PAIR ? 256 : 128, cnt1 * 64);
+        const int acc = WIDE ? 0 : it & 1;
+        const uint32_t acc_phase = WIDE ? (it & 1) : (it >> 1) & 1;
         ++it;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * WG_BLOCK_N;
+        const uint32_t d_base = tmem_base + acc * WG_BLOCK_N;
         for (int kb = t.kb_lo; kb < t.kb_hi; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t a_lo = a_hi + C::A_BYTES;
-          const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * C::A_BYTES;
-          const uint32_t b_lo = b_hi + C::B_BYTES;
+          // descriptors differ from the stage-0 / k-0 ones only in the 14-bit start-address field
+          const uint32_t st_off = static_cast<uint32_t>(stage) * (C::STAGE_BYTES >> 4);
           if (p.dbg < 2)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {            // 4 x UMMA_K(16 pixels) per 64-pixel K block
-            const uint32_t koff = k * 16 * 128;    // 16 K rows of 128 bytes
-            const uint64_t da_hi = umma_desc_mn_sw128(a_hi + koff);
-            const uint64_t db_hi = umma_desc_mn_sw128(b_hi + koff);
-            const uint32_t first = (kb != t.kb_lo || k != 0) ? 1u : 0u;
-            if (SPLIT) {
-              const uint64_t da_lo = umma_desc_mn_sw128(a_lo + koff);
-              const uint64_t db_lo = umma_desc_mn_sw128(b_lo + koff);
-              if (PAIR) {
-                ptx::umma_f16_pair(d_tmem, da_lo, db_hi, idesc, first);
-                ptx::umma_f16_pair(d_tmem, da_hi, db_lo, idesc, 1);
-                ptx::umma_f16_pair(d_tmem, da_hi, db_hi, idesc, 1);
+          for (int grp = 0; grp < (WIDE ? 2 : 1); ++grp) {
+            if (grp == 1 && cnt1 == 0) break;
+            const uint32_t idesc = grp == 0 ? idesc0 : idesc1;
+            const uint32_t d_tmem = d_base + grp * WG_BLOCK_N;
+            const uint32_t g_off = st_off + grp * ((2 * BOX_BYTES) >> 4);  // this group's boxes in the CTA's B region
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {            // 4 x UMMA_K(16 pixels) per 64-pixel K block
+              const uint32_t k_off = k * ((16 * 128) >> 4);    // 16 K rows of 128 bytes
+              const uint64_t da_hi = desc_a_hi + (st_off + k_off);
+              const uint64_t db_hi = desc_b_hi + (g_off + k_off);
+              const uint32_t first = (kb != t.kb_lo || k != 0) ? 1u : 0u;
+              if (SPLIT) {
+                const uint64_t da_lo = desc_a_lo + (st_off + k_off);
+                const uint64_t db_lo = desc_b_lo + (g_off + k_off);
+                if (PAIR) {
+                  ptx::umma_f16_pair(d_tmem, da_lo, db_hi, idesc, first);
+                  ptx::umma_f16_pair(d_tmem, da_hi, db_lo, idesc, 1);
+                  ptx::umma_f16_pair(d_tmem, da_hi, db_hi, idesc, 1);
+                } else {
+                  ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, first);
+                  ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+                  ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                }
+              } else if (PAIR) {
+                ptx::umma_f16_pair(d_tmem, da_hi, db_hi, idesc, first);
               } else {
-                ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, first);
-                ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1);
-                ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, first);
               }
-            } else if (PAIR) {
-              ptx::umma_f16_pair(d_tmem, da_hi, db_hi, idesc, first);
-            } else {
-              ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, first);
             }
           }
           if (PAIR) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
@@ -268,10 +295,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       for (int a = 0; a < 2; ++a) tmem_empty_leader[a] = ptx::mapa_u32(&tmem_empty[a], 0);
     int it = 0;
     for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
-      const WTile t = decode_tile(p, tile, m_units);
+      const WTile t = decode_tile(p, tile, m_units, C::UNITS);
       if (t.kb_hi <= t.kb_lo) continue;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = WIDE ? 0 : it & 1;
+      const uint32_t acc_phase = WIDE ? (it & 1) : (it >> 1) & 1;
       ++it;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
@@ -305,10 +332,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   }
 }
 
-template <bool SPLIT, bool PAIR>
+template <bool SPLIT, bool PAIR, bool WIDE>
 int launch_w(const WgradParams& p, int num_sms, cudaStream_t stream) {
-  using C = WCfg<SPLIT, PAIR>;
-  auto kern = wgrad_kernel<SPLIT, PAIR>;
+  using C = WCfg<SPLIT, PAIR, WIDE>;
+  auto kern = wgrad_kernel<SPLIT, PAIR, WIDE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -343,9 +370,11 @@ int launch_w(const WgradParams& p, int num_sms, cudaStream_t stream) {
 int launch_wgrad(const WgradParams& p, bool split, bool pair, int num_sms, cudaStream_t stream) {
   if (pair) {
     if (p.m_tiles & 1) return static_cast<int>(cudaErrorInvalidValue);
-    return split ? launch_w<true, true>(p, num_sms, stream) : launch_w<false, true>(p, num_sms, stream);
+    if (p.wide) return split ? launch_w<true, true, true>(p, num_sms, stream) : launch_w<false, true, true>(p, num_sms, stream);
+    return split ? launch_w<true, true, false>(p, num_sms, stream) : launch_w<false, true, false>(p, num_sms, stream);
   }
-  return split ? launch_w<true, false>(p, num_sms, stream) : launch_w<false, false>(p, num_sms, stream);
+  if (p.wide) return static_cast<int>(cudaErrorInvalidValue);
+  return split ? launch_w<true, false, false>(p, num_sms, stream) : launch_w<false, false, false>(p, num_sms, stream);
 }
 
 }  // namespace drasic

@@ -6,6 +6,8 @@ ConvLSTM weights if they changed, then launch per iteration
     E1 E2 E3 (gate kernels, grouped by node) -> bottleneck -> D1 D2 D3 (gate kernels) -> tail/head
 on the caller's CUDA stream through the C ABI.  torch is used for device memory and streams only.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -134,6 +136,7 @@ class CodecEngine(object):
         if cta_pair not in ('auto', 'on', 'off'):
             raise ValueError('Not valid cta_pair')
         self.cta_pair = cta_pair  # CTA pairs (cta_group::2) for the gate / dgrad / wgrad GEMMs
+        self.wgrad_pair_mode = int(os.environ.get('DRASIC_WGRAD_PAIR', '2'))   # 1: 256-column, 2: 512-column pair tiles
         self.gsplit = 1 if grad_precision == 'parity' else 0
         self.C, self.code, self.M, self.separate = num_channel, code_size, num_node, separate
         self.split = 1 if precision == 'parity' else 0
@@ -681,12 +684,15 @@ class CodecEngine(object):
             w.group_kb_end = P(group_kb_end(ly)) if ly.groups > 1 else None
             w.B_pad, w.H, w.W, w.Cin, w.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             w.n_groups, w.has_h, w.split = ly.groups, 1 if t > 0 else 0, self.gsplit
-            w.cta_pair = 0 if self.cta_pair == 'off' else 1      # 4Co/128 M tiles: always even
-            tiles = ly.groups * (4 * ly.co // 128) * ((9 * ly.cin // 64 + 3) // 4 + ((9 * ly.co // 64 + 3) // 4 if t > 0 else 0))
+            kb_per_group = max(1, Bp * ly.h * ly.w // 64 // ly.groups)
+            # 4Co/128 M tiles: always even.  512-column pair tiles (one TMEM-wide accumulator, no epilogue overlap)
+            # only where a tile's K loop is long enough to amortise the exposed epilogue
+            w.cta_pair = 0 if self.cta_pair == 'off' else (self.wgrad_pair_mode if kb_per_group >= 256 else 1)
+            upt = 8 if w.cta_pair == 2 else 4
+            tiles = ly.groups * (4 * ly.co // 128) * ((9 * ly.cin // 64 + upt - 1) // upt + ((9 * ly.co // 64 + upt - 1) // upt if t > 0 else 0))
             units = sms
             if w.cta_pair:
                 tiles, units = tiles // 2, sms // 2
-            kb_per_group = max(1, Bp * ly.h * ly.w // 64 // ly.groups)
             w.k_splits = _pick_k_splits(tiles, units, max(1, kb_per_group // 16))
             self._timed('wgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_weight(w, stream), 'convlstm_bwd_weight'))
             self.launches += 4

@@ -186,7 +186,8 @@ typedef struct {
   const float* dg_inv_scale;
   const int* group_kb_end;                /* device [n_groups]: exclusive end 64-pixel block per node */
   int B_pad, H, W, Cin, Co, n_groups, has_h, split, k_splits;
-  int cta_pair;                           /* 1: CTA pairs, each pair owns 256 gate channels x 256 columns */
+  int cta_pair;                           /* 1: CTA pairs, each pair owns 256 gate channels x 256 columns; 2: x 512 columns
+                                             (one TMEM-wide accumulator, less L2 -> SMEM traffic per MMA) */
 } drasic_wgrad_args;
 int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream);
 int drasic_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,
