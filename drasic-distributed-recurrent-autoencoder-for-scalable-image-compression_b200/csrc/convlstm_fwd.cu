@@ -314,9 +314,8 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t full_remote[C::STAGES];  // the leader's full barriers (shared::cluster addresses)
-      if (PAIR)
-        for (int s = 0; s < C::STAGES; ++s) full_remote[s] = ptx::mapa_u32(&full_bar[s], 0);
+      // the leader's full barriers (shared::cluster addresses; the CTA windows map linearly)
+      const uint32_t full_remote0 = PAIR ? ptx::mapa_u32(&full_bar[0], 0) : 0u;
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
         const int nt = tile % p.n_ntiles;
         const int mt = PAIR ? 2 * (tile / p.n_ntiles) + static_cast<int>(cta_rank) : tile / p.n_ntiles;
@@ -327,14 +326,11 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
           if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
           wrow += static_cast<int>(cta_rank) * (width >> 1);
         }
+        // K blocks walk (source x | h, tap, 64-channel chunk); the position advances incrementally
+        bool is_h = false;
+        int tap = 0, cc = 0, chunks = cx_chunks, kcol = 0;
         for (int kb = 0; kb < nkb; ++kb) {
-          const bool is_h = kb >= 9 * cx_chunks;
-          const int kk = is_h ? kb - 9 * cx_chunks : kb;
-          const int chunks = is_h ? ch_chunks : cx_chunks;
-          const int tap = kk / chunks;
-          const int cc = kk - tap * chunks;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          const int kcol = (is_h ? 9 * p.Cin : 0) + kk * BLOCK_K;
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           const CUtensorMap* ta = is_h ? p.tm_h : p.tm_x;
@@ -342,7 +338,7 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
           if (PAIR) {
             // both CTAs' bytes are accounted on the leader's barrier (its MMA thread consumes both halves)
             if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            const uint32_t fb = full_remote[stage];
+            const uint32_t fb = full_remote0 + 8u * stage;
             ptx::tma_load_4d_pair(st, &ta[0], fb, cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
             if (SPLIT)
               ptx::tma_load_4d_pair(st + A_TILE_BYTES, &ta[1], fb, cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
@@ -357,6 +353,11 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
             ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], kcol, wrow);
             if (SPLIT)
               ptx::tma_load_2d(sb + C::B_TILE_BYTES, &p.tm_w[1], &full_bar[stage], kcol, wrow);
+          }
+          kcol += BLOCK_K;
+          if (++cc == chunks) {
+            cc = 0;
+            if (++tap == 9) { tap = 0; is_h = true; chunks = ch_chunks; }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }

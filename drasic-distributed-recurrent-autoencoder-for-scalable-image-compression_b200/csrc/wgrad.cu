@@ -150,9 +150,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t full_remote[C::STAGES];  // the leader's full barriers (shared::cluster addresses)
-      if (PAIR)
-        for (int s = 0; s < C::STAGES; ++s) full_remote[s] = ptx::mapa_u32(&full_bar[s], 0);
+      // the leader's full barriers (shared::cluster addresses; the CTA windows map linearly)
+      const uint32_t full_remote0 = PAIR ? ptx::mapa_u32(&full_bar[0], 0) : 0u;
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
         const WTile t = decode_tile(p, tile, m_units, C::UNITS);
         const CUtensorMap* tb = t.is_h ? p.tm_h : p.tm_x;
@@ -165,16 +164,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         const int n_grp = WIDE ? (t.nunits + 3) >> 2 : 1;
         const int my_units = PAIR ? 2 * n_grp : t.nunits;
         const uint32_t bytes = (SPLIT ? 2 : 1) * (C::A_BYTES + my_units * BOX_BYTES);
-        for (int kb = t.kb_lo; kb < t.kb_hi; ++kb) {
-          int n0, y0, x0;
-          if (HW >= 64) {
-            n0 = kb / kb_per_img;
-            const int rem = kb - n0 * kb_per_img;
-            y0 = (rem / kbx) * p.kbh;
-            x0 = (rem % kbx) * p.kbw;
-          } else {
-            n0 = kb * p.kbn; y0 = 0; x0 = 0;
+        // per-tile constants of the B loads: (tap offset, chunk) of each 2-box TMA
+        int u_dx[C::UNITS / 2], u_dy[C::UNITS / 2], u_chunk[C::UNITS / 2];
+#pragma unroll
+        for (int uu = 0; uu < C::UNITS / 2; ++uu) {
+          const int u = 2 * uu;
+          int unit = t.u0 + u;
+          if (PAIR) {
+            const int grp = WIDE ? u >> 1 : 0;
+            const int cnt = WIDE ? min(4, t.nunits - 4 * grp) : t.nunits;
+            unit = t.u0 + 4 * grp + static_cast<int>(cta_rank) * (cnt >> 1);
           }
+          int tap = unit / cpu;
+          u_chunk[uu] = unit - tap * cpu;
+          if (p.dbg == 5) tap = 4;
+          u_dx[uu] = tap % 3 - 1;
+          u_dy[uu] = tap / 3 - 1;
+        }
+        // pixel box of the first K block; later blocks advance incrementally (no divisions in the loop)
+        int n0, y0, x0;
+        if (HW >= 64) {
+          n0 = t.kb_lo / kb_per_img;
+          const int rem = t.kb_lo - n0 * kb_per_img;
+          y0 = (rem / kbx) * p.kbh;
+          x0 = (rem % kbx) * p.kbw;
+        } else {
+          n0 = t.kb_lo * p.kbn; y0 = 0; x0 = 0;
+        }
+        for (int kb = t.kb_lo; kb < t.kb_hi; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.dbg == 1) {
             ptx::mbar_arrive(&full_bar[stage]);
@@ -191,26 +208,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             uint8_t* sa = st + pl * C::A_BYTES;
             uint8_t* sb = st + (SPLIT ? 2 : 1) * C::A_BYTES + pl * C::B_BYTES;
             if (p.dbg == 3) {
-            } else if (PAIR) ptx::tma_load_5d_pair(sa, &p.tm_g[pl], full_remote[stage], 0, x0, y0, n0, mt * 2);
+            } else if (PAIR) ptx::tma_load_5d_pair(sa, &p.tm_g[pl], (full_remote0 + 8u * stage), 0, x0, y0, n0, mt * 2);
             else ptx::tma_load_5d(sa, &p.tm_g[pl], &full_bar[stage], 0, x0, y0, n0, mt * 2);
             if (p.dbg == 4) continue;
-            for (int u = 0; u < my_units; u += 2) {   // a pair of 64-channel chunks of the same tap
-              int unit = t.u0 + u;
-              if (PAIR) {
-                const int grp = WIDE ? u >> 1 : 0;
-                const int cnt = WIDE ? min(4, t.nunits - 4 * grp) : t.nunits;
-                unit = t.u0 + 4 * grp + static_cast<int>(cta_rank) * (cnt >> 1);
-              }
-              int tap = unit / cpu;
-              const int chunk = unit - tap * cpu;
-              if (p.dbg == 5) tap = 4;
+#pragma unroll
+            for (int uu = 0; uu < C::UNITS / 2; ++uu) {   // a pair of 64-channel chunks of the same tap
+              if (2 * uu >= my_units) break;
               if (PAIR)
-                ptx::tma_load_5d_pair(sb + u * BOX_BYTES, &tb[pl], full_remote[stage], 0, x0 + tap % 3 - 1,
-                                      y0 + tap / 3 - 1, n0, chunk);
+                ptx::tma_load_5d_pair(sb + 2 * uu * BOX_BYTES, &tb[pl], (full_remote0 + 8u * stage), 0, x0 + u_dx[uu],
+                                      y0 + u_dy[uu], n0, u_chunk[uu]);
               else
-                ptx::tma_load_5d(sb + u * BOX_BYTES, &tb[pl], &full_bar[stage], 0, x0 + tap % 3 - 1,
-                                 y0 + tap / 3 - 1, n0, chunk);
+                ptx::tma_load_5d(sb + 2 * uu * BOX_BYTES, &tb[pl], &full_bar[stage], 0, x0 + u_dx[uu],
+                                 y0 + u_dy[uu], n0, u_chunk[uu]);
             }
+          }
+          // next K block's pixel box
+          if (HW >= 64) {
+            x0 += p.kbw;
+            if (x0 == p.W) {
+              x0 = 0;
+              y0 += p.kbh;
+              if (y0 == p.H) { y0 = 0; ++n0; }
+            }
+          } else {
+            n0 += p.kbn;
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
