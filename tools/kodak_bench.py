@@ -11,11 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, 'drasic-distributed-recurrent-autoencoder-for-scalable-image-compression_b200')
 sys.path.insert(0, ROOT)
 sys.path.insert(0, PKG)
-from oracle import drasic_oracle as O      # seeded parameter construction only
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+from _params import make_state_dict
 from engine.codec import CodecEngine
 
 prec = sys.argv[1] if len(sys.argv) > 1 else 'parity'
-sd = {k: v.cuda() for k, v in O.init_state_dict(3, 8, 1, seed=0).items()}
+sd = make_state_dict(3, 8, 1, seed=0)
 eng = CodecEngine(3, 8, 1, precision=prec)
 g = torch.Generator().manual_seed(1)
 

@@ -10,14 +10,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, 'drasic-distributed-recurrent-autoencoder-for-scalable-image-compression_b200')
 sys.path.insert(0, ROOT)
 sys.path.insert(0, PKG)
-from oracle import drasic_oracle as O      # seeded parameter construction only
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+from _params import make_state_dict
 from engine.codec import CodecEngine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 prec = sys.argv[2] if len(sys.argv) > 2 else 'parity'
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 gprec = sys.argv[4] if len(sys.argv) > 4 else 'fp16'
-sd = {k: v.cuda() for k, v in O.init_state_dict(3, 8, 8, seed=0).items()}
+sd = make_state_dict(3, 8, 8, seed=0)
 g = torch.Generator().manual_seed(1)
 img = torch.rand(B, 3, 32, 32, generator=g).cuda()
 lab = torch.randint(0, 8, (B,), generator=g)
