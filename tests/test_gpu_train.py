@@ -228,3 +228,42 @@ def test_cuda_graph_matches_eager_eval_and_train():
             assert (a - b).norm().item() <= 1e-4 * max(b.norm().item(), 1e-30), k
         opt.step()
     config.PARAM['cuda_graph'] = False
+
+
+def test_config2_full_size_training_step_properties():
+    """BASELINE configs[1] at the bench size (B=1024, 8 sources by random subsets, T=16): too big for the CPU
+    oracle, checked through size-independent properties of one training step."""
+    import config
+    M, T, B = 8, 16, 1024
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=40)
+    g = torch.Generator().manual_seed(41)
+    img = torch.rand(B, 3, 32, 32, generator=g)
+    label = torch.randint(0, M - 1, (B,), generator=g)            # node M-1 sees no data in this batch
+    noise = torch.rand(T, B, 8, 4, 4, generator=g)
+    out = train_step(m, img, label, noise)
+    codes = out['code_pm1']
+    assert bool(((codes == 1) | (codes == -1)).all()) and torch.isfinite(out['loss'])
+    # (1) the loss is the mean over iterations of the L1 error of the returned reconstructions (dist_codec.py:58,61)
+    l1 = torch.stack([(r - img.cuda()).abs().mean() for r in out['img']]).mean().item()
+    assert abs(l1 - out['loss'].item()) < 1e-6
+    # (2) every parameter has a finite gradient; the encoder nobody used has exactly zero gradient
+    for k, p in m.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+        if k.startswith('model.encoder.{}.'.format(M - 1)):
+            assert float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert float(p.grad.abs().max()) > 0.0, k
+    # (3) samples are independent: the gradient of the global-mean loss is the sample-weighted sum of the gradients
+    #     of two halves of the batch (the property the multi-GPU all-reduce relies on)
+    ref = {k: p.grad.clone() for k, p in m.named_parameters()}
+    acc = {k: torch.zeros_like(v) for k, v in ref.items()}
+    for lo, hi in ((0, 384), (384, 1024)):
+        o = train_step(m, img[lo:hi], label[lo:hi], noise[:, lo:hi])
+        assert torch.equal(o['code_pm1'], codes[:, lo:hi])       # same symbols as inside the big batch
+        for k, p in m.named_parameters():
+            acc[k] += p.grad * ((hi - lo) / float(B))
+    worst = max(float((acc[k] - ref[k]).norm() / (ref[k].norm() + 1e-20)) for k in ref if float(ref[k].abs().max()) > 0)
+    assert worst < 2e-3, worst
+    # (4) the decoder-only path reproduces the training-mode reconstructions from the emitted bits
+    rec = m.decode(out['bits'][:4], label.cuda())
+    assert torch.equal(rec[3], out['img'][3].detach())

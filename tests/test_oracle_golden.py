@@ -134,3 +134,24 @@ def test_loop_sep_codec(golden_dir):
     assert np.array_equal(torch.stack(out['code_pm1']).numpy().astype(np.int8), g['codes'])
     np.testing.assert_allclose(torch.stack(out['img']).numpy(), g['recon'], rtol=0, atol=1e-6)
     assert abs(out['loss'].item() - float(g['loss'])) < 1e-6
+
+
+def test_oracle_heterogeneous_rates_semantics():
+    """BASELINE config 4 (inferred semantics): a node whose iteration budget is spent keeps its reconstruction;
+    nodes with budget left are untouched by the others' budgets (samples are independent)."""
+    import torch
+    from oracle import drasic_oracle as O
+    M, T = 2, 4
+    sd = O.init_state_dict(3, 8, M, seed=3)
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(6, 3, 32, 32, generator=g)
+    label = torch.tensor([0, 1, 0, 1, 1, 0])
+    with torch.no_grad():
+        full = O.codec_forward(sd, img, label, T, M)
+        het = O.codec_forward(sd, img, label, T, M, node_iters=[T, 2])
+    a, b = label == 0, label == 1
+    for t in range(T):
+        assert torch.equal(het['img'][t][a], full['img'][t][a])
+    assert torch.equal(het['img'][1][b], full['img'][1][b])
+    assert torch.equal(het['img'][3][b], het['img'][1][b])
+    assert not torch.equal(full['img'][3][b], full['img'][1][b])
