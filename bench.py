@@ -344,7 +344,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        nb = 32 if train else 256
+        nb = 96 if train else 512                                   # ~10-15 s of CPU work on 16 cores
         sdc = {k: v.detach().cpu().clone().requires_grad_(train) for k, v in sd.items()}
         ci, cl = synth_batch(nb, 7)
         with torch.no_grad():

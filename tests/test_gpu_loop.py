@@ -194,3 +194,30 @@ def test_config5_kodak_patches_properties():
     #     guaranteed -- but the loss must equal the mean L1 over iterations of the returned images
     l1 = torch.stack([(r - patches.cuda()).abs().mean() for r in out['img']]).mean().item()
     assert abs(l1 - out['loss'].item()) < 1e-6
+
+
+@pytest.mark.parametrize('data,M,code,B', [('MNIST', 10, 8, 13), ('CIFAR10', 2, 16, 5), ('CIFAR10', 3, 4, 1),
+                                           ('CIFAR10', 10, 8, 100)])
+def test_other_controls_vs_oracle(data, M, code, B):
+    """the reference's control space around the BASELINE point: its default num_node=10 (config.py:7), other
+    code sizes (the rate per iteration), single-image and odd batch sizes, the paper's global batch of 100"""
+    T = 3
+    m = build_model('dist_codec', data, M, T, seed=50, code_size=code)
+    C = 1 if data == 'MNIST' else 3
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(51)
+    img = torch.rand(B, C, 32, 32, generator=g)
+    label = torch.randint(0, M, (B,), generator=g)
+    with torch.no_grad():
+        ref = O.codec_forward(sd, img, label, T, M)
+    out = run(m, img, label)
+    codes, refc, refz = out['code_pm1'].cpu(), torch.stack(ref['code_pm1']), torch.stack(ref['z'])
+    assert tuple(codes.shape) == (T, B, code, 4, 4)
+    margins, clean = first_mismatch_margins(codes, refc, refz)
+    assert all(mg < MARGIN_TOL for mg in margins), margins
+    if clean == B:
+        assert (torch.stack(out['img']).cpu() - torch.stack(ref['img'])).abs().max().item() < RECON_TOL
+        assert abs(out['loss'].item() - ref['loss'].item()) < 1e-5
+        want = np.stack([O.pack_bits(c) for c in refc])
+        assert np.array_equal(out['bits'].cpu().numpy(), want)
+    assert out['code'][-1].nbytes == B * code * 16 // 8 * T            # BPP container contract (metrics.py:84-89)
