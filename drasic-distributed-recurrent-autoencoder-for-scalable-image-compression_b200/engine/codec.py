@@ -154,6 +154,7 @@ class CodecEngine(object):
         # anyway) and leaves the cache marked stale for whatever forward comes next.
         self._stale = False
         self._repack = False
+        self.overlap_wgrad = os.environ.get('DRASIC_OVERLAP_WGRAD', '1') != '0'   # wgrad GEMMs on a side stream
         self.profile = None  # set to [] to collect (label, flops, start_event, end_event) per launch
 
     # ------------------------------------------------------------------ helpers
@@ -594,10 +595,12 @@ class CodecEngine(object):
             n = (Bp, ly.h, ly.w, ly.co)
             W_[ly.name] = dict(dh_above=torch.zeros(n, **f32), dh_rec=torch.zeros(n, **f32),
                                dc=[torch.zeros(n, **f32), torch.zeros(n, **f32)],     # ping-pong: in (t+1) / out (t)
-                               dg_hi=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16),
-                               dg_lo=torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16) if self.gsplit else None,
+                               # gate-gradient planes and their scale ping-pong by iteration parity: wgrad of
+                               # iteration t runs on a side stream while the main stream already produces t-1
+                               dg_hi=[torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16) for _ in range(2)],
+                               dg_lo=[torch.zeros((Bp, ly.h, ly.w, 4 * ly.co), **f16) if self.gsplit else None for _ in range(2)],
                                last_amax=torch.zeros((1,), dtype=torch.int32, device=dev),   # carried across steps
-                               inv=torch.ones((1,), **f32))
+                               inv=[torch.ones((1,), **f32) for _ in range(2)])
         W_['du1'] = torch.zeros((Bp, H // 2, W // 2, 128), **f32)
         W_['dd0'] = torch.zeros((Bp, H // 8, W // 8, 128), **f32)
         self._bwd_buf, self._bwd_key = W_, key
@@ -633,6 +636,18 @@ class CodecEngine(object):
         sms = self.sms()
         # true amax (float bits) of every (layer, iteration) gate-gradient tensor of this backward pass
         amax_tab = {ly.name: torch.zeros((T,), dtype=torch.int32, device=dev) for ly in layers}
+        # The weight-gradient GEMMs are off the critical path of backward-through-time (nothing but the final
+        # unpack reads their result): they go to a side stream, so the HBM-bound cell / tail / head backward
+        # kernels of the main stream run next to them instead of between the GEMMs.
+        main = torch.cuda.current_stream(dev)
+        overlap = self.overlap_wgrad and self.profile is None
+        side = None
+        if overlap:
+            if getattr(self, '_side', None) is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+            side.wait_stream(main)          # gw and the buffers above are initialised on the main stream
+        wgrad_done = {}                     # (layer, t) -> event recorded on the side stream after wgrad(layer, t)
 
         def group_kb_end(ly):
             return plan.kb_end(ly.h * ly.w)
@@ -656,17 +671,26 @@ class CodecEngine(object):
             f.dh_above, f.dh_rec = P(wb['dh_above']), P(wb['dh_rec']) if t < T - 1 else None
             f.dc_in = P(wb['dc'][(t + 1) & 1]) if t < T - 1 else None
             f.dc_out = P(wb['dc'][t & 1])
-            f.dg_hi, f.dg_lo = P(wb['dg_hi']), P(wb['dg_lo'])
-            f.prev_amax_bits, f.amax_bits, f.inv_scale_out = prev.data_ptr(), am[t:t + 1].data_ptr(), P(wb['inv'])
+            pp = t & 1
+            dg_hi, dg_lo, inv_dg = wb['dg_hi'][pp], wb['dg_lo'][pp], wb['inv'][pp]
+            ev = wgrad_done.pop((ly.name, t + 2), None)
+            if ev is not None:
+                main.wait_event(ev)          # the planes of this parity were last read by wgrad(ly, t+2)
+            f.dg_hi, f.dg_lo = P(dg_hi), P(dg_lo)
+            f.prev_amax_bits, f.amax_bits, f.inv_scale_out = prev.data_ptr(), am[t:t + 1].data_ptr(), P(inv_dg)
             f.n_pix, f.Co = n_pix, ly.co
             for verify in (0, 1):
                 f.verify = verify
                 self._timed('lstm_bwd' if not verify else 'lstm_bwd_verify', 0.0,
                             lambda: B.check(L.drasic_lstm_bwd_fused(f, stream), 'lstm_bwd_fused'))
+            planes_ready = None
+            if overlap:
+                planes_ready = torch.cuda.Event()
+                planes_ready.record(main)
             hi, lo, inv = dpk[ly.name]
             a = B.DgradArgs()
-            a.dg_hi, a.dg_lo, a.w_hi, a.w_lo = P(wb['dg_hi']), P(wb['dg_lo']), P(hi), P(lo)
-            a.w_inv_scale, a.dg_inv_scale = P(inv), P(wb['inv'])
+            a.dg_hi, a.dg_lo, a.w_hi, a.w_lo = P(dg_hi), P(dg_lo), P(hi), P(lo)
+            a.w_inv_scale, a.dg_inv_scale = P(inv), P(inv_dg)
             a.dx_out = P(dx_of[ly.name][0])
             a.dhrec_out = P(wb['dh_rec']) if t > 0 else None
             a.group_mtile_end = P(ly.mtile_end)
@@ -677,10 +701,10 @@ class CodecEngine(object):
             self._timed('dgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_data(a, stream), 'convlstm_bwd_data'))
             w = B.WgradArgs()
             xp = x_of[ly.name](t)
-            w.dg_hi, w.dg_lo, w.x_hi, w.x_lo = P(wb['dg_hi']), P(wb['dg_lo']), P(xp[0]), P(xp[1])
+            w.dg_hi, w.dg_lo, w.x_hi, w.x_lo = P(dg_hi), P(dg_lo), P(xp[0]), P(xp[1])
             if t > 0:
                 w.h_hi, w.h_lo = P(Lb['h'][t - 1][0]), P(Lb['h'][t - 1][1])
-            w.gw, w.dg_inv_scale = P(gw[ly.name]), P(wb['inv'])
+            w.gw, w.dg_inv_scale = P(gw[ly.name]), P(inv_dg)
             w.group_kb_end = P(group_kb_end(ly)) if ly.groups > 1 else None
             w.B_pad, w.H, w.W, w.Cin, w.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             w.n_groups, w.has_h, w.split = ly.groups, 1 if t > 0 else 0, self.gsplit
@@ -694,7 +718,14 @@ class CodecEngine(object):
             if w.cta_pair:
                 tiles, units = tiles // 2, sms // 2
             w.k_splits = _pick_k_splits(tiles, units, max(1, kb_per_group // 16))
-            self._timed('wgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_weight(w, stream), 'convlstm_bwd_weight'))
+            if overlap:
+                side.wait_event(planes_ready)
+                B.check(L.drasic_convlstm_bwd_weight(w, side.cuda_stream), 'convlstm_bwd_weight')
+                done = torch.cuda.Event()
+                done.record(side)
+                wgrad_done[(ly.name, t)] = done
+            else:
+                self._timed('wgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_weight(w, stream), 'convlstm_bwd_weight'))
             self.launches += 4
 
         loss_scale = 1.0 / (T * float(Bn * Cc * H * W))
@@ -729,6 +760,8 @@ class CodecEngine(object):
             self._timed('head_bwd', 0.0, lambda: B.check(L.drasic_head_bwd(h, stream), 'head_bwd'))
             self.launches += 3
 
+        if overlap:
+            main.wait_stream(side)          # join: the unpack below reads the accumulated weight gradients
         for ly in layers:
             WB[ly.name]['last_amax'].copy_(amax_tab[ly.name][T - 1:T])
         grads = {}
