@@ -214,6 +214,7 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   p.bw = bw; p.bh = bh; p.bn = bn;
   p.n_mtiles = static_cast<int>(static_cast<long long>(B) * H * W / 128);
   p.n_ntiles = 4 * Co / a->block_n;
+  { static const int ord = getenv("DRASIC_TILE_ORDER") ? atoi(getenv("DRASIC_TILE_ORDER")) : 0; p.tile_order = ord; }
   p.has_hidden = a->has_state ? 1 : 0;
   p.has_cell = a->has_state ? 1 : 0;
   p.next_mode = a->next_mode;
@@ -361,6 +362,7 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   p.bw = bw; p.bh = bh; p.bn = bn;
   p.n_mtiles = static_cast<int>(static_cast<long long>(B) * H * W / 128);
   p.n_ntiles = (Nout + 255) / 256;
+  { static const int ord = getenv("DRASIC_TILE_ORDER") ? atoi(getenv("DRASIC_TILE_ORDER")) : 0; p.tile_order = ord; }
   p.n_groups = a->n_groups; p.group_mtile_end = a->group_mtile_end;
   p.w_group_rows = Nout; p.n_out = Nout; p.n_x = Cin; p.dx_mode = a->dx_mode;
   p.dx_out = a->dx_out; p.dhrec_out = a->dhrec_out;

@@ -89,6 +89,13 @@ __device__ __forceinline__ void store_f32x16(float* __restrict__ dst, const floa
     reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
+// work unit index -> (N tile, M unit).  tile_order 0: N tile fastest (units running side by side share their
+// pixels, i.e. the A operand); 1: M unit fastest (they share the weight tile, the B operand)
+__device__ __forceinline__ void tile_split(const GateParams& p, int tile, int m_units, int& nt, int& mu) {
+  if (p.tile_order == 0) { nt = tile % p.n_ntiles; mu = tile / p.n_ntiles; }
+  else { mu = tile % m_units; nt = tile / m_units; }
+}
+
 struct TileCoord {
   int n0, y0, x0;
 };
@@ -302,7 +309,8 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
   // tile walk: a work unit is one M tile (1 CTA) or one pair of adjacent M tiles (CTA pair) x one N tile
   const int unit_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
   const int unit_first = PAIR ? blockIdx.x >> 1 : blockIdx.x;
-  const int total_tiles = (PAIR ? p.n_mtiles >> 1 : p.n_mtiles) * p.n_ntiles;
+  const int m_units = PAIR ? p.n_mtiles >> 1 : p.n_mtiles;
+  const int total_tiles = m_units * p.n_ntiles;
   const int cx_chunks = p.Cin / BLOCK_K;
   const int ch_chunks = p.Co / BLOCK_K;
   const int nkb = 9 * cx_chunks + (p.has_hidden ? 9 * ch_chunks : 0);
@@ -317,8 +325,9 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       // the leader's full barriers (shared::cluster addresses; the CTA windows map linearly)
       const uint32_t full_remote0 = PAIR ? ptx::mapa_u32(&full_bar[0], 0) : 0u;
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
-        const int nt = tile % p.n_ntiles;
-        const int mt = PAIR ? 2 * (tile / p.n_ntiles) + static_cast<int>(cta_rank) : tile / p.n_ntiles;
+        int nt, mu;
+        tile_split(p, tile, m_units, nt, mu);
+        const int mt = PAIR ? 2 * mu + static_cast<int>(cta_rank) : mu;
         const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
         int wrow = group_of(p, mt) * p.w_group_rows + nt * BLOCK_N;
         if (PAIR) {  // this CTA stages its half of the (possibly narrower, dgrad) N tile
@@ -377,7 +386,11 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
         // dgrad: the last N tile of a row may be narrower than BLOCK_N (UMMA N is a runtime field)
         int width = BLOCK_N;
-        if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - (tile % p.n_ntiles) * BLOCK_N);
+        if (EPI == EPI_DGRAD) {
+          int nt, mu;
+          tile_split(p, tile, m_units, nt, mu);
+          width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
+        }
         const uint32_t idesc = ptx::umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, width);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -433,8 +446,9 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     if (PAIR)
       for (int a = 0; a < 2; ++a) tmem_empty_leader[a] = ptx::mapa_u32(&tmem_empty[a], 0);
     for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
-      const int nt = tile % p.n_ntiles;
-      const int mt = PAIR ? 2 * (tile / p.n_ntiles) + static_cast<int>(cta_rank) : tile / p.n_ntiles;
+      int nt, mu;
+      tile_split(p, tile, m_units, nt, mu);
+      const int mt = PAIR ? 2 * mu + static_cast<int>(cta_rank) : mu;
       const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
       const int g = group_of(p, mt);
       const int acc = it & 1;

@@ -49,6 +49,7 @@ struct GateParams {
   int H, W, Cin, Co;
   int bw, bh, bn;  // TMA box (pixels): bw*bh*bn == 128
   int n_mtiles, n_ntiles;
+  int tile_order;  // 0: N tile fastest in the persistent walk, 1: M unit fastest
   int has_hidden, has_cell;  // 0 on the first iteration (state is zero)
   int next_mode, next_f32;
   int precise;               // 1: IEEE exp/div/tanh (parity mode); 0: tanh.approx
