@@ -157,6 +157,14 @@ class CodecEngine(object):
         self.overlap_wgrad = os.environ.get('DRASIC_OVERLAP_WGRAD', '1') != '0'   # wgrad GEMMs on a side stream
         self.profile = None  # set to [] to collect (label, flops, start_event, end_event) per launch
 
+    def release(self):
+        """free the device arenas and caches of this engine"""
+        self._arena = self._arena_key = None
+        self._bwd_buf = self._bwd_key = None
+        self._wcache = {}
+        self._gen = getattr(self, '_gen', 0) + 1      # a pending backward() can no longer run
+        self._stale = False
+
     # ------------------------------------------------------------------ helpers
     def sms(self):
         if self._sms is None:

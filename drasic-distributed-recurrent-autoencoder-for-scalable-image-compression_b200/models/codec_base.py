@@ -157,6 +157,14 @@ class CodecModel(nn.Module):
                                     noise=noise, loss_kind=config.PARAM['loss_fn'],
                                     save_for_backward=save_for_backward, node_iters=config.PARAM.get('node_iters'))
 
+    def release(self):
+        """Drop the engine's device arenas (recurrent state, per-iteration saved tensors, backward work space,
+        packed weight planes, captured graphs); they are rebuilt on the next call.  The training arena at
+        B=1024, T=16 is ~44 GB (2.6 MB per image and iteration)."""
+        self._graphs = {}
+        if self._engine is not None:
+            self._engine.release()
+
     # ---- progressive bitstream (SURVEY 8f N1) ---------------------------------------------------
     def encode(self, input):
         """Run the coding loop and return the real bitstream: {'bits': uint8 [T, B, code*H*W/512] (iteration-major,

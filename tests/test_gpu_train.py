@@ -174,6 +174,22 @@ def test_fused_adam_updates_reach_the_packed_weights():
     assert torch.equal(rec[-1], out['img'][-1])
 
 
+def test_release_frees_arenas_and_next_call_rebuilds():
+    m = build_model('dist_codec', 'CIFAR10', 2, 3, seed=17)
+    g = torch.Generator().manual_seed(18)
+    img, label = torch.rand(8, 3, 32, 32, generator=g), torch.randint(0, 2, (8,), generator=g)
+    noise = torch.rand(3, 8, 8, 4, 4, generator=g)
+    out1 = train_step(m, img, label, noise)
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    used = torch.cuda.memory_allocated()
+    m.release()
+    assert m._engine._arena is None and torch.cuda.memory_allocated() < used
+    out2 = train_step(m, img, label, noise)
+    assert torch.equal(out1['code_pm1'], out2['code_pm1']) and out1['loss'].item() == out2['loss'].item()
+    for k, p in m.named_parameters():
+        assert float((p.grad - g1[k]).abs().max()) <= 1e-3 * float(g1[k].abs().max()) + 1e-12, k
+
+
 def test_backward_requires_matching_forward():
     m = build_model('dist_codec', 'MNIST', 1, 2, seed=0)
     inp = {'img': torch.rand(4, 1, 32, 32).cuda(), 'label': torch.zeros(4, dtype=torch.long).cuda()}
