@@ -1,2 +1,4 @@
-from .shuffle import *   # noqa: F401,F403
-from .quantize import *  # noqa: F401,F403
+"""The reference's `functions` package surface: Quantize (autograd function) and the functional pixel
+(un)shuffle."""
+from .quantize import Quantize  # noqa: F401
+from .shuffle import pixel_shuffle, pixel_unshuffle  # noqa: F401
