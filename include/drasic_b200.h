@@ -111,9 +111,15 @@ int drasic_bottleneck_fwd(const drasic_bottleneck_args* a, void* stream);
  * models/dist_codec.py:101-103 (ConvCell 32->C), :56-59 and :38, :71-74 (ConvCell C->32, unshuffle).
  */
 typedef struct {
-  const float* d3_next; const float* w_d4; const float* w_e0; const float* b_e0;
-  const float* img; const float* recon_prev; float* recon_out; float* dec_out; double* loss_acc;
-  void* e1_in_hi; void* e1_in_lo; const int* perm;
+  const float* d3_next;           /* [B_pad,H/2,W/2,128] fp32: the last decoder ConvLSTM's h in its own (QUAD) order, i.e.
+                                     pixel-major over 2x2 quads: element ((slot*H*W + quad*4 + dy*2+dx)*32 + c) */
+  const float* w_d4; const float* w_e0; const float* b_e0;   /* [n_dec_groups][C,32], [n_enc_groups][32,C], nullable [..][32] */
+  const float* img; const float* recon_prev; float* recon_out;   /* [B,C,H,W] fp32, the caller's batch order */
+  float* dec_out;                 /* nullable: raw tanh decoder output */
+  double* loss_acc;               /* [2]: += {sum of loss terms, sum of squared error} of this iteration */
+  void* e1_in_hi; void* e1_in_lo; /* [B_pad,H/2,W/2,128] fp16 planes: first encoder ConvLSTM input (same quad-major order);
+                                     NULL on the last iteration */
+  const int* perm;
   const int* group_img_end;       /* device, as above */
   int B_pad, C, H, W, mode, loss_kind, n_enc_groups, n_dec_groups, precise, split;
   const int* group_iters;         /* nullable: device [n_enc_groups] iteration budget per node (heterogeneous rates,
