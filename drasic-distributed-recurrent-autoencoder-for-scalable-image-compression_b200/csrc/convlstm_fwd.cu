@@ -41,7 +41,6 @@ struct Cfg {
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int STAGES_RAW = SMEM_DATA_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SLOTS = BLOCK_N / 4;  // channels per N tile (gates epilogue)
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -122,19 +121,19 @@ __device__ __forceinline__ int group_of(const GateParams& p, int mt) {
 template <bool SPLIT, int BLOCK_N>
 __device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_row, int nt, int g, int n,
                                                int y, int x) {
-  using C = Cfg<SPLIT, BLOCK_N>;
+  constexpr int SLOTS = BLOCK_N / 4;  // channels per N tile
   const int H = p.H, W = p.W, Co = p.Co;
   const float inv = __ldg(&p.w_inv_scale[g]);
   const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
 #pragma unroll 1
-  for (int j = 0; j < C::SLOTS / 16; ++j) {
+  for (int j = 0; j < SLOTS / 16; ++j) {
     float gi[16], gf[16], gg[16], go[16];
-    ptx::tmem_ld16(t_row + 0 * C::SLOTS + j * 16, gi);
-    ptx::tmem_ld16(t_row + 1 * C::SLOTS + j * 16, gf);
-    ptx::tmem_ld16(t_row + 2 * C::SLOTS + j * 16, gg);
-    ptx::tmem_ld16(t_row + 3 * C::SLOTS + j * 16, go);
+    ptx::tmem_ld16(t_row + 0 * SLOTS + j * 16, gi);
+    ptx::tmem_ld16(t_row + 1 * SLOTS + j * 16, gf);
+    ptx::tmem_ld16(t_row + 2 * SLOTS + j * 16, gg);
+    ptx::tmem_ld16(t_row + 3 * SLOTS + j * 16, go);
     ptx::tmem_ld_wait();
-    const int p0 = nt * C::SLOTS + j * 16;  // first physical channel of this chunk
+    const int p0 = nt * SLOTS + j * 16;  // first physical channel of this chunk
     float cv[16];
     if (p.has_cell) {
       const float* cp = (p.c_prev ? p.c_prev : p.c_state) + pix * Co + p0;
