@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
       for (int u = 0; u < U; ++u) xv[u] = mine ? __fsub_rn(__fmul_rn(im_c[u], 2.0f), 1.0f) : 0.0f;
     } else {
       float pre[U];
+      float pa = 0.0f, ps = 0.0f;   // this pass's loss terms (U elements), added to the fp64 sums once per pass
 #pragma unroll
       for (int u = 0; u < U; ++u) pre[u] = 0.0f;
 #pragma unroll
@@ -323,16 +324,18 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
           p.recon_out[gi[u]] = r;
           if (!has_img) continue;
           const float e = __fsub_rn(r, im_c[u]);
-          if (p.loss_kind == LOSS_MAE) l_abs += static_cast<double>(fabsf(e));
-          else if (p.loss_kind == LOSS_MSE) l_abs += static_cast<double>(e) * e;
+          if (p.loss_kind == LOSS_MAE) pa += fabsf(e);
+          else if (p.loss_kind == LOSS_MSE) pa = fmaf(e, e, pa);
           else {  // bce with torch's log clamp at -100
             const float lr = fmaxf(logf(r), -100.0f), l1r = fmaxf(logf(1.0f - r), -100.0f);
-            l_abs += -static_cast<double>(im_c[u] * lr + (1.0f - im_c[u]) * l1r);
+            pa -= im_c[u] * lr + (1.0f - im_c[u]) * l1r;
           }
-          l_sq += static_cast<double>(e) * e;
+          ps = fmaf(e, e, ps);
           xv[u] = __fsub_rn(im_c[u], r);  // x = img - reconstructed   (dist_codec.py:59)
         }
       }
+      l_abs += static_cast<double>(pa);
+      l_sq += static_cast<double>(ps);
     }
     if (!has_head) continue;  // last iteration: no next encoder pass (uniform)
     // encoder head + pixel_unshuffle(2): E1 input [(slot*HW + i)*32 + k]
@@ -341,8 +344,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int c = 0; c < NC; ++c) x[u][c] = __shfl_sync(0xffffffffu, xv[u], lane_base + c);
-    alignas(16) __half hi[U][8];
-    alignas(16) __half lo[U][8];
+    alignas(16) __half2 hi[U][4];
+    alignas(16) __half2 lo[U][4];
+    float ev[U][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float w[NC];
@@ -354,12 +358,18 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
         float a = b;
 #pragma unroll
         for (int c = NC - 1; c >= 0; --c) a = fmaf(w[c], x[u][c], a);
-        float e = PRECISE ? tanhf(a) : tanh_fast_pw(a);
-        e *= ACT_SCALE;
-        hi[u][j] = __float2half_rn(e);
-        lo[u][j] = __float2half_rn(e - __half2float(hi[u][j]));
+        ev[u][j] = (PRECISE ? tanhf(a) : tanh_fast_pw(a)) * ACT_SCALE;
       }
     }
+    // fp16 {hi, lo} split, two channels per conversion
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        hi[u][q] = __floats2half2_rn(ev[u][2 * q], ev[u][2 * q + 1]);
+        const float2 hf = __half22float2(hi[u][q]);
+        lo[u][q] = __floats2half2_rn(ev[u][2 * q] - hf.x, ev[u][2 * q + 1] - hf.y);
+      }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const size_t off = (static_cast<size_t>(slot) * HW + i0 + 8 * u) * FEAT + 8 * sub;
@@ -463,7 +473,7 @@ int pixel_blocks_per_image(int B_pad, int HW, int pix_per_pass, int min_blocks) 
 int launch_tail_head(const TailParams& p, cudaStream_t stream) {
   const int HW = p.H * p.W;
   if (HW % TAIL_THREADS != 0 || p.C > MAX_C || p.C < 1 || ((p.H | p.W) & 1)) return static_cast<int>(cudaErrorInvalidValue);
-  const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TAIL_PIX * TAIL_U, 148 * 8);
+  const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TAIL_PIX * TAIL_U, 148 * 4);
 #define DRASIC_TAIL_LAUNCH(NC)                                                            \
   if (p.precise) tail_head_kernel<true, NC><<<grid, TAIL_THREADS, 0, stream>>>(p);        \
   else tail_head_kernel<false, NC><<<grid, TAIL_THREADS, 0, stream>>>(p)
