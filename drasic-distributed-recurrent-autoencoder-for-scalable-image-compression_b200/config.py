@@ -8,6 +8,8 @@ loop, forward and backward, as one CUDA graph per batch shape)."""
 
 def init():
     global PARAM
+    import compat
+    compat.apply()
     PARAM = dict(
         data_name='MNIST', subset='label', model_name='dist_codec',
         control=dict(normalization='none', activation='tanh', num_iter='16', code_size='8', num_node='10'),

@@ -1,0 +1,88 @@
+"""the reference's caller flow (train_model.py: runExperiment :47-102, train :105-131, test :134-151,
+make_optimizer / make_scheduler :154-191; test_model.py's resume + evaluate) driven end to end against this
+package's config / data / models / metrics / logger / utils -- the same calls in the same order, restated here
+because the reference tree does not travel to the GPU box."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.optim as optim
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_epoch(loader, model, optimizer, logger, metric, train):
+    import config
+    from utils import collate, to_device
+    model.train(train)
+    losses = []
+    for i, input in enumerate(loader):
+        input = to_device(collate(input), config.PARAM['device'])              # train_model.py:109-111
+        if train:
+            model.zero_grad()
+            output = model(input)
+            output['loss'].backward()
+            optimizer.step()
+        else:
+            with torch.no_grad():
+                output = model(input)
+        tag = 'train' if train else 'test'
+        evaluation = metric.evaluate(config.PARAM['metric_names'][tag], input, output)   # :128 / :144
+        logger.append(evaluation, tag, n=len(input['img']))
+        losses.append(evaluation['Loss'])
+    tag = 'train' if train else 'test'
+    logger.append({'info': ['Model: t', '{} epoch'.format(tag)]}, tag, mean=False)
+    logger.write(tag, config.PARAM['metric_names'][tag])
+    return float(np.mean(losses))
+
+
+def test_reference_training_flow_runs_end_to_end(tmp_path, capsys):
+    import config
+    config.init()                                                               # also applies the torch-2.x shim
+    config.PARAM.update(data_name='CIFAR10', device='cuda', num_epochs=3, lr=2e-3, patience=0,
+                        data_size={'train': 96, 'test': 32}, batch_size={'train': 16, 'test': 32})
+    config.PARAM['control'] = {'normalization': 'none', 'activation': 'tanh', 'num_iter': '4', 'code_size': '8', 'num_node': '2'}
+    from utils import process_control_name, save, resume
+    process_control_name()
+    import models
+    from data import fetch_dataset, make_data_loader
+    from metrics import Metric
+    from logger import Logger
+    torch.manual_seed(0)
+    data_loader = make_data_loader(fetch_dataset(config.PARAM['data_name'], config.PARAM['subset']))
+    model = eval('models.{}().to(config.PARAM["device"])'.format(config.PARAM['model_name']))   # :58
+    optimizer = optim.Adam(model.parameters(), lr=config.PARAM['lr'], weight_decay=config.PARAM['weight_decay'])
+    scheduler = optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode='min', factor=config.PARAM['factor'],
+                                                     patience=config.PARAM['patience'], verbose=True,
+                                                     threshold=config.PARAM['threshold'], threshold_mode='rel')   # :179-182
+    logger = Logger(str(tmp_path / 'runs'))
+    metric = Metric()
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        train_losses = []
+        for epoch in range(1, config.PARAM['num_epochs'] + 1):
+            logger.safe(True)
+            train_losses.append(_run_epoch(data_loader['train'], model, optimizer, logger, metric, True))
+            test_loss = _run_epoch(data_loader['test'], model, optimizer, logger, metric, False)
+            scheduler.step(metrics=logger.tracker['test/Loss'], epoch=epoch)     # :84
+            logger.safe(False)
+            save({'config': config.PARAM, 'epoch': epoch + 1, 'model_dict': model.state_dict(),
+                  'optimizer_dict': optimizer.state_dict(), 'scheduler_dict': scheduler.state_dict(), 'logger': logger},
+                 './output/model/t_checkpoint.pt')                               # :88-93
+            logger.reset()
+        assert all(np.isfinite(train_losses)) and train_losses[-1] < train_losses[0]      # it learns
+        assert isinstance(logger.history['test/PSNR'][-1], list) and len(logger.history['test/PSNR'][-1]) == 4
+        assert logger.history['test/BPP'][-1] == [0.125 * (t + 1) for t in range(4)]
+        # test_model.py: a fresh model resumed from the checkpoint evaluates to the same numbers
+        torch.manual_seed(123)
+        model2 = models.dist_codec().to('cuda')
+        last_epoch, model2, _, _, _ = resume(model2, 't')
+        assert last_epoch == config.PARAM['num_epochs'] + 1
+        logger2 = Logger(str(tmp_path / 'runs2'))
+        again = _run_epoch(data_loader['test'], model2, None, logger2, metric, False)
+        assert abs(again - test_loss) < 1e-6
+    finally:
+        os.chdir(cwd)
+    assert 'Loss:' in capsys.readouterr().out

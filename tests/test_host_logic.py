@@ -162,3 +162,43 @@ def test_metrics_module_definitions_on_cpu_tensors():
     assert metrics.BPP(code, a) == O.bpp(code, a)
     out = {'mse': torch.tensor([0.01, 0.001])}
     assert np.allclose(metrics.psnr_per_iteration(out), [20.0, 30.0], atol=1e-4)
+
+
+def test_caller_shims_torch2_scheduler_data_and_logger(tmp_path):
+    """SURVEY 8f N2 host pieces: config.init() makes ReduceLROnPlateau(verbose=True) (train_model.py:179-182)
+    constructible on torch 2.x; the synthetic data module and the logger keep the reference's interfaces"""
+    import pickle
+    import torch
+    import config
+    config.init()
+    p = torch.nn.Parameter(torch.zeros(2))
+    opt = torch.optim.Adam([p], lr=1.0)
+    s = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode='min', factor=0.1, patience=0, verbose=True,
+                                                   threshold=1e-3, threshold_mode='rel')
+    s.step(1.0)
+    s.step(2.0)
+    assert abs(opt.param_groups[0]['lr'] - 0.1) < 1e-12
+    import data
+    import utils
+    config.PARAM.update(data_size={'train': 6, 'test': 3}, batch_size={'train': 4, 'test': 3})
+    config.PARAM['control']['num_node'] = '3'
+    ds = data.fetch_dataset('MNIST', 'label')
+    assert len(ds['train']) == 6 and len(ds['test']) == 3
+    a, b = ds['train'][2], ds['train'][2]
+    assert torch.equal(a['img'], b['img']) and tuple(a['img'].shape) == (1, 32, 32) and 0 <= int(a['label']) < 3
+    batch = utils.collate(next(iter(data.make_data_loader(ds)['test'])))
+    assert tuple(batch['img'].shape) == (3, 1, 32, 32) and batch['label'].dtype == torch.int64
+    with pytest.raises(ValueError):
+        data.fetch_dataset('NoSuchData', 'label')
+    from logger import Logger
+    lg = Logger(str(tmp_path / 'log'))
+    lg.append({'info': ['m', 'e']}, 'test', mean=False)
+    lg.append({'Loss': 1.0, 'PSNR': [10.0, 20.0]}, 'test', n=2)
+    lg.append({'Loss': 3.0, 'PSNR': [20.0, 40.0]}, 'test', n=2)
+    assert lg.mean['test/Loss'] == 2.0 and lg.mean['test/PSNR'] == [15.0, 30.0] and lg.tracker['test/Loss'] == 3.0
+    lg.write('test', ['Loss', 'PSNR'])
+    lg.reset()
+    assert lg.history['test/Loss'] == [2.0] and lg.tracker['test/Loss'] == 0
+    with pytest.raises(ValueError):
+        lg.append({'x': 'str'}, 'test')
+    pickle.loads(pickle.dumps(lg))
