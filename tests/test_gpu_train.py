@@ -283,3 +283,25 @@ def test_config2_full_size_training_step_properties():
     # (4) the decoder-only path reproduces the training-mode reconstructions from the emitted bits
     rec = m.decode(out['bits'][:4], label.cuda())
     assert torch.equal(rec[3], out['img'][3].detach())
+
+
+@pytest.mark.parametrize('M,code,B', [(10, 16, 21), (2, 4, 6)])
+def test_training_other_controls_vs_oracle(M, code, B):
+    """training away from the BASELINE point: the reference's default num_node=10, other code sizes"""
+    T = 2
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=60, code_size=code)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(61)
+    img = torch.rand(B, 3, 32, 32, generator=g)
+    label = torch.randint(0, M, (B,), generator=g)
+    noise = torch.rand(T, B, code, 4, 4, generator=g)
+    ref = O.codec_forward(sd, img, label, T, M, training=True, noise=[n for n in noise])
+    ref['loss'].backward()
+    out = train_step(m, img, label, noise)
+    assert np.array_equal(out['code_pm1'].cpu().numpy(), torch.stack(ref['code_pm1']).numpy())
+    assert abs(out['loss'].item() - ref['loss'].item()) < 1e-5
+    for k, p in m.named_parameters():
+        if sd[k].grad is None:
+            assert float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert rel_err(p.grad.cpu(), sd[k].grad) < GRAD_TOL['fp16'], k
