@@ -480,12 +480,13 @@ template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
 int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<SPLIT, BLOCK_N, PAIR>;
   auto kern = conv_gemm_kernel<SPLIT, BLOCK_N, EPI, PAIR>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  static bool configured[64] = {};  // per instantiation and device (the attribute is per device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    configured[dev] = true;
   }
   const int total = (PAIR ? p.n_mtiles / 2 : p.n_mtiles) * p.n_ntiles;
   if (!PAIR) {

@@ -357,11 +357,13 @@ template <bool SPLIT, bool PAIR, bool WIDE>
 int launch_w(const WgradParams& p, int num_sms, cudaStream_t stream) {
   using C = WCfg<SPLIT, PAIR, WIDE>;
   auto kern = wgrad_kernel<SPLIT, PAIR, WIDE>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};  // per instantiation and device (the attribute is per device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    configured[dev] = true;
   }
   const int nt_total = p.n_tiles_x + (p.has_h ? p.n_tiles_h : 0);
   const int total = p.n_groups * (PAIR ? p.m_tiles / 2 : p.m_tiles) * nt_total * p.k_splits;

@@ -274,9 +274,28 @@ class CodecEngine(object):
         return val
 
     # ------------------------------------------------------------------ the loop
-    def forward(self, sd, img, label, num_iter, training=False, noise=None, loss_kind='mae',
-                label_host=None, want_z=False, save_for_backward=False, plan=None, pack_only=False,
-                node_iters=None):
+    def forward(self, sd, img, *args, **kwargs):
+        """see _forward; runs with the tensors' device current (the C ABI launches on the current device)"""
+        if not img.is_cuda:
+            raise B.DrasicError('DRASIC B200 engine needs CUDA tensors; there is no CPU path')
+        with torch.cuda.device(img.device):
+            return self._forward(sd, img, *args, **kwargs)
+
+    def backward(self, out, g_loss=None):
+        """see _backward"""
+        with torch.cuda.device(out['_bwd']['img'].device):
+            return self._backward(out, g_loss)
+
+    def decode(self, sd, bits, *args, **kwargs):
+        """see _decode"""
+        if not bits.is_cuda:
+            raise B.DrasicError('DRASIC B200 engine needs CUDA tensors; there is no CPU path')
+        with torch.cuda.device(bits.device):
+            return self._decode(sd, bits, *args, **kwargs)
+
+    def _forward(self, sd, img, label, num_iter, training=False, noise=None, loss_kind='mae',
+                 label_host=None, want_z=False, save_for_backward=False, plan=None, pack_only=False,
+                 node_iters=None):
         """sd: mapping reference state_dict key -> fp32 CUDA tensor.  img [B,C,H,W] fp32 in [0,1],
         label [B] node ids.  noise: None (eval / deterministic sign) or [T,B,code,H/8,W/8] uniforms.
         node_iters: None, or one iteration budget per node (heterogeneous rates, BASELINE config 4, inferred
@@ -463,7 +482,7 @@ class CodecEngine(object):
         return out
 
     # ------------------------------------------------------------------ decode-only
-    def decode(self, sd, bits, label, hw, label_host=None):
+    def _decode(self, sd, bits, label, hw, label_host=None):
         """Reconstruct from the packed bitstream alone: bits [T', B, code*H*W/512] uint8 (the 'bits' output of
         forward(), or any prefix of its iterations -- the codec is progressive), label [B] node ids (which
         decoder a sample belongs to in the sep codec; unused by the shared decoder but kept for symmetry).
@@ -614,7 +633,7 @@ class CodecEngine(object):
         self._bwd_buf, self._bwd_key = W_, key
         return W_
 
-    def backward(self, out, g_loss=None):
+    def _backward(self, out, g_loss=None):
         """Backward-through-time for the forward that produced `out` (save_for_backward=True).
         Returns {state_dict key: fp32 gradient} for every parameter of the codec."""
         ctx = out['_bwd']

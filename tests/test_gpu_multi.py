@@ -72,3 +72,23 @@ def test_two_gpu_gradients_equal_single_gpu(shards):
         # fp16 backward GEMMs scale each rank's gradient planes by its own power of two: equal within fp16-grade noise
         assert results['dloss'] < 1e-6, dict(results)
         assert results['worst'] < 2e-3, dict(results)
+
+
+def test_one_process_two_devices():
+    """a model on cuda:1 in a process whose current device is cuda:0 (and then one on cuda:0): the engine makes the
+    tensors' device current for its launches and configures its kernels per device"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from conftest import build_model
+    g = torch.Generator().manual_seed(70)
+    img = torch.rand(9, 3, 32, 32, generator=g)
+    label = torch.randint(0, 2, (9,), generator=g)
+    outs = []
+    for dev in ('cuda:1', 'cuda:0'):
+        m = build_model('dist_codec', 'CIFAR10', 2, 3, seed=71, device=dev)
+        m.train(False)
+        assert torch.cuda.current_device() == 0
+        with torch.no_grad():
+            out = m({'img': img.to(dev), 'label': label.to(dev)})
+        outs.append((out['code_pm1'].cpu(), out['img'][-1].cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
