@@ -359,6 +359,25 @@ def run_ours(args):
         line['cpu_baseline'] = {'value': nb / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                 'sample': 'oracle codec_forward{} B={} M=8 T=16, one pass ({:.1f} s)'.format(
                                     ' + backward (BPTT)' if train else ' eval', nb, dt)}
+    # ---- parity of this build against the CPU oracle on a small sample of the same workload (eval mode, T=16)
+    if world == 1 and not args.no_cpu:
+        pi, pl = synth_batch(16, 11)
+        sdc = {k: v.detach().cpu() for k, v in sd.items()}
+        with torch.no_grad():
+            ref = O.codec_forward(sdc, pi, pl, T_ITER, M_NODES)
+            was = model.training
+            model.train(False)
+            prec = config.PARAM['precision']
+            config.PARAM['precision'] = 'parity'
+            out = model({'img': pi.to(dev), 'label': pl.to(dev)})
+            config.PARAM['precision'] = prec
+            model.train(was)
+        refc = torch.stack(ref['code_pm1'])
+        mism = int((out['code_pm1'].cpu() != refc).sum())
+        rec_err = float((torch.stack(out['img']).cpu() - torch.stack(ref['img'])).abs().max())
+        dps = max(abs(O.psnr(a.cpu(), pi) - O.psnr(b, pi)) for a, b in zip(out['img'], ref['img']))
+        line['parity'] = {'sample': 'eval, parity precision, B=16 M=8 T=16 vs oracle/drasic_oracle.py', 'code_mismatches': mism,
+                          'code_symbols': int(refc.numel()), 'recon_max_abs_err': rec_err, 'psnr_max_abs_diff_db': dps}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
