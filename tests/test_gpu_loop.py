@@ -221,3 +221,29 @@ def test_other_controls_vs_oracle(data, M, code, B):
         want = np.stack([O.pack_bits(c) for c in refc])
         assert np.array_equal(out['bits'].cpu().numpy(), want)
     assert out['code'][-1].nbytes == B * code * 16 // 8 * T            # BPP container contract (metrics.py:84-89)
+
+
+@pytest.mark.parametrize('scale', [3.0, 0.25])
+def test_trained_like_weight_scales_vs_oracle(scale):
+    """SURVEY 8d stress set: weights scaled so the gate non-linearities saturate (x3: realistic |z| margins,
+    large pre-activations) or barely move (x0.25); the per-(cell, node) power-of-two weight scaling and the
+    split-fp16 path must stay fp32-grade at both ends."""
+    M, T, B = 4, 8, 24
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=80)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(scale)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(81)
+    img = torch.rand(B, 3, 32, 32, generator=g)
+    label = torch.randint(0, M, (B,), generator=g)
+    with torch.no_grad():
+        ref = O.codec_forward(sd, img, label, T, M)
+    out = run(m, img, label)
+    codes, refc, refz = out['code_pm1'].cpu(), torch.stack(ref['code_pm1']), torch.stack(ref['z'])
+    margins, clean = first_mismatch_margins(codes, refc, refz)
+    assert all(mg < MARGIN_TOL for mg in margins), margins
+    assert clean >= B - 2
+    ok = torch.tensor([bool((codes[:, b] == refc[:, b]).all()) for b in range(B)])
+    err = (torch.stack(out['img']).cpu()[:, ok] - torch.stack(ref['img'])[:, ok]).abs().max().item()
+    assert err < RECON_TOL
