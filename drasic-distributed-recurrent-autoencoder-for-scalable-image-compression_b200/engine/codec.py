@@ -311,6 +311,9 @@ class CodecEngine(object):
         dev = img.device
         img = img.detach().contiguous().float()
         Bn, Cc, H, W = img.shape
+        if Bn == 0:
+            # the reference fails in torch.cat over an empty list of per-node outputs (dist_codec.py:49)
+            raise RuntimeError('torch.cat(): expected a non-empty list of Tensors (empty batch)')
         if Cc != self.C:
             raise ValueError('Not valid input channels')
         if H % 8 or W % 8 or (H * W) % 256:

@@ -157,6 +157,12 @@ def test_other_loss_functions():
         assert abs(out['loss'].item() - ref['loss'].item()) < 1e-5 * max(1.0, abs(ref['loss'].item()))
 
 
+def test_empty_batch_raises_like_the_reference():
+    m = build_model('dist_codec', 'CIFAR10', 2, 2, seed=0)
+    with pytest.raises(RuntimeError):
+        run(m, torch.zeros(0, 3, 32, 32), torch.zeros(0, dtype=torch.long))
+
+
 def test_label_out_of_range_raises_index_error():
     m = build_model('dist_codec', 'MNIST', 2, 2, seed=0)
     with pytest.raises(IndexError):
