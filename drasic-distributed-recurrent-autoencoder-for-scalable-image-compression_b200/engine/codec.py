@@ -26,7 +26,17 @@ ENC_IDX = {'E1': 2, 'E2': 4, 'E3': 6}   # nn.Sequential indices, dist_codec.py:7
 DEC_IDX = {'D1': 1, 'D2': 3, 'D3': 5}   # dist_codec.py:88-104
 
 
-def plan_arrays(label_host, num_node, pad_total=None):
+def choose_pad(counts, batch):
+    """slots per node are a multiple of 8 images (one 128-pixel M tile at 4x4) -- or of 16, which lets the 4x4
+    layers run as CTA pairs too, when that costs less than 1 % more slots (a single source, or large nodes)"""
+    if os.environ.get('DRASIC_PAD'):
+        return int(os.environ['DRASIC_PAD'])
+    counts = np.asarray(counts, dtype=np.int64)
+    extra = int(((counts + 15) // 16 * 16).sum() - ((counts + PAD - 1) // PAD * PAD).sum())
+    return 16 if extra * 100 <= max(int(batch), 1) else PAD
+
+
+def plan_arrays(label_host, num_node, pad_total=None, pad=None):
     """node-sort one batch: (perm [B_pad] slot -> original index or -1, exclusive end slot per node)"""
     label_host = np.asarray(label_host).astype(np.int64).reshape(-1)
     if label_host.size and (label_host.min() < 0 or label_host.max() >= num_node):
@@ -34,10 +44,11 @@ def plan_arrays(label_host, num_node, pad_total=None):
         raise IndexError('label out of range for num_node={}'.format(num_node))
     order = np.argsort(label_host, kind='stable')              # keeps the reference's within-node order
     counts = np.bincount(label_host, minlength=num_node)
-    padded = (counts + PAD - 1) // PAD * PAD
+    pad = PAD if pad is None else int(pad)
+    padded = (counts + pad - 1) // pad * pad
     ends = np.cumsum(padded)
     B_pad = int(ends[-1]) if pad_total is None else int(pad_total)
-    if B_pad < int(ends[-1]) or B_pad % PAD:
+    if B_pad < int(ends[-1]) or B_pad % pad:
         raise ValueError('Not valid pad_total')
     perm = np.full(B_pad, -1, dtype=np.int32)
     starts = ends - padded
@@ -58,10 +69,11 @@ class BatchPlan(object):
     """Node-sorted, padded slot layout of one batch.  With `static_hw` the plan owns fixed device
     buffers (worst-case slot count) that update() refreshes in place -- what a captured CUDA graph reads."""
 
-    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None):
+    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None, pad=None):
         self.num_node, self.device = num_node, device
         self.pad_total = pad_total
-        perm, ends, counts = plan_arrays(label_host, num_node, pad_total)
+        self.pad = PAD if pad is None else int(pad)      # padding unit of every node's slot range
+        perm, ends, counts = plan_arrays(label_host, num_node, pad_total, self.pad)
         self.B, self.B_pad = int(np.asarray(label_host).size), int(perm.size)
         self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
         self.perm = torch.from_numpy(perm).to(device)
@@ -90,7 +102,7 @@ class BatchPlan(object):
 
     def update(self, label_host):
         """refresh the device buffers in place for a new batch of the same size"""
-        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad)
+        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad, self.pad)
         if int(np.asarray(label_host).size) != self.B:
             raise ValueError('Not valid batch size for this static plan')
         self._frozen = True
@@ -198,10 +210,10 @@ class CodecEngine(object):
                 return bn
         return 64
 
-    def _use_pair(self, n_mtiles, hw, co):
+    def _use_pair(self, n_mtiles, hw, co, pad=PAD):
         """CTA pairs need 256-column N tiles and node boundaries on even M tiles: a node's slots are a
-        multiple of 8 images, i.e. hw/16 M tiles -- even once an image has at least 32 pixels."""
-        if self.cta_pair == 'off' or (8 * hw // 128) % 2 or n_mtiles % 2:
+        multiple of `pad` images, i.e. pad*hw/128 M tiles -- even once pad*hw >= 256."""
+        if self.cta_pair == 'off' or (pad * hw) % 256 or n_mtiles % 2:
             return False
         if self.cta_pair == 'on':
             return True
@@ -322,7 +334,10 @@ class CodecEngine(object):
         if plan is None:
             if label_host is None:
                 label_host = label.detach().cpu().numpy()      # the one host sync per forward
-            plan = BatchPlan(label_host, self.M, dev)
+            lh = np.asarray(label_host).astype(np.int64).reshape(-1)
+            in_range = lh.size == 0 or (lh.min() >= 0 and lh.max() < self.M)
+            pad = choose_pad(np.bincount(lh, minlength=self.M), lh.size) if in_range and self.cta_pair != 'off' else PAD
+            plan = BatchPlan(label_host, self.M, dev, pad=pad)
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
@@ -361,7 +376,7 @@ class CodecEngine(object):
             ly.name, ly.cin, ly.co, ly.h, ly.w = name, cin, co, h, w
             ly.next_mode, ly.next_f32 = nmode, nf32
             ly.in_order, ly.out_order, ly.is_enc, ly.idx, ly.prefs = io, oo, is_enc, idx, prefs
-            ly.pair = self._use_pair(n_mtiles, h * w, co)
+            ly.pair = self._use_pair(n_mtiles, h * w, co, plan.pad)
             ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.groups = len(prefs)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
@@ -371,6 +386,7 @@ class CodecEngine(object):
 
         self._repack = False
         self._stale = bool(save_for_backward)
+        self._last_layers = layers      # (tests / tools: which layers ran as CTA pairs)
         if pack_only:
             return None
 
@@ -505,7 +521,10 @@ class CodecEngine(object):
         T, Bn = int(bits.shape[0]), int(bits.shape[1])
         if label_host is None:
             label_host = label.detach().cpu().numpy()
-        plan = BatchPlan(label_host, self.M, dev)
+        lh = np.asarray(label_host).astype(np.int64).reshape(-1)
+        in_range = lh.size == 0 or (lh.min() >= 0 and lh.max() < self.M)
+        pad = choose_pad(np.bincount(lh, minlength=self.M), lh.size) if in_range and self.cta_pair != 'off' else PAD
+        plan = BatchPlan(label_host, self.M, dev, pad=pad)
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
@@ -525,7 +544,7 @@ class CodecEngine(object):
             n_mtiles = Bp * h * w // 128
             ly = _Layer()
             ly.name, ly.cin, ly.co, ly.h, ly.w, ly.next_mode, ly.next_f32 = name, cin, co, h, w, nmode, nf32
-            ly.pair = self._use_pair(n_mtiles, h * w, co)
+            ly.pair = self._use_pair(n_mtiles, h * w, co, plan.pad)
             ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.groups = len(dec_pref)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, DEC_IDX[name]) for p in dec_pref], cin, co, io, oo,

@@ -305,3 +305,31 @@ def test_training_other_controls_vs_oracle(M, code, B):
             assert float(p.grad.abs().max()) == 0.0, k
         else:
             assert rel_err(p.grad.cpu(), sd[k].grad) < GRAD_TOL['fp16'], k
+
+
+def test_single_source_pairs_on_the_4x4_layers():
+    """one source: node slots are padded to 16 images, so E3 / D1 (one M tile per 8 images) run as CTA pairs as
+    well; forward codes and training gradients against the oracle"""
+    M, T, B = 1, 3, 48
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=90, cta_pair='on')
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(91)
+    img = torch.rand(B, 3, 32, 32, generator=g)
+    label = torch.zeros(B, dtype=torch.long)
+    noise = torch.rand(T, B, 8, 4, 4, generator=g)
+    ref = O.codec_forward(sd, img, label, T, M, training=True, noise=[n for n in noise])
+    ref['loss'].backward()
+    out = train_step(m, img, label, noise)
+    layers = {ly.name: ly.pair for ly in m._engine._last_layers} if hasattr(m._engine, '_last_layers') else None
+    assert layers is None or all(layers.values()), layers
+    assert np.array_equal(out['code_pm1'].cpu().numpy(), torch.stack(ref['code_pm1']).numpy())
+    assert abs(out['loss'].item() - ref['loss'].item()) < 1e-5
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad.cpu(), sd[k].grad) < GRAD_TOL['fp16'], k
+    # eval, deterministic sign
+    with torch.no_grad():
+        ref_e = O.codec_forward({k: v.detach() for k, v in sd.items()}, img, label, T, M)
+    m.train(False)
+    with torch.no_grad():
+        out_e = m({'img': img.cuda(), 'label': label.cuda()})
+    assert np.array_equal(out_e['code_pm1'].cpu().numpy(), torch.stack(ref_e['code_pm1']).numpy())
