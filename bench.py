@@ -310,7 +310,7 @@ def run_ours(args):
         'config': {'workload': workload_name(args.mode), 'batch_per_gpu': B,
                    'global_batch': world * B, 'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8,
                    'precision': args.precision, 'cuda_graph': args.graph,
-                   'cta_pair': 'cta_group::2 pairs on E1 E2 D2 D3 (gates, dgrad) and all wgrad GEMMs; single CTAs on the 4x4 layers E3 D1',
+                   'cta_pair': 'cta_group::2 pairs on every gate / dgrad / wgrad GEMM (pair units formed inside each node)',
                    'parallelism': ('dp{}: batch sharded, one NCCL all-reduce of gradients per step'.format(world) if train
                                    else 'batch-sharded replicas x{} (no collective)'.format(world)),
                    'l2': 'per-step working set (activations+state, ~1 MB/image) exceeds the 126 MB L2'},

@@ -95,6 +95,27 @@ __device__ __forceinline__ void tile_split(const GateParams& p, int tile, int m_
   else { mu = tile % m_units; nt = tile / m_units; }
 }
 
+// CTA pairs: M unit `mu` -> the M tile of this CTA.  Pair units never straddle two nodes: node g owns
+// ceil(tiles_g / 2) units (group_pair_end[] holds the running ends); when a node has an odd number of M tiles
+// the second CTA of its last unit has no tile of its own -- it stages the first CTA's pixels again (the
+// cta_group::2 MMA reads both CTAs' shared memory) and skips its epilogue.
+__device__ __forceinline__ int pair_mtile(const GateParams& p, int mu, int rank, bool& valid) {
+  int first, end;
+  if (p.n_groups > 1 && p.group_pair_end != nullptr) {
+    int g = 0;
+    while (g + 1 < p.n_groups && mu >= p.group_pair_end[g]) ++g;
+    const int unit0 = g ? p.group_pair_end[g - 1] : 0;
+    const int tile0 = g ? p.group_mtile_end[g - 1] : 0;
+    first = tile0 + 2 * (mu - unit0);
+    end = p.group_mtile_end[g];
+  } else {
+    first = 2 * mu;
+    end = p.n_mtiles;
+  }
+  valid = first + rank < end;
+  return valid ? first + rank : first;
+}
+
 struct TileCoord {
   int n0, y0, x0;
 };
@@ -308,7 +329,7 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
   // tile walk: a work unit is one M tile (1 CTA) or one pair of adjacent M tiles (CTA pair) x one N tile
   const int unit_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
   const int unit_first = PAIR ? blockIdx.x >> 1 : blockIdx.x;
-  const int m_units = PAIR ? p.n_mtiles >> 1 : p.n_mtiles;
+  const int m_units = PAIR ? p.n_munits : p.n_mtiles;
   const int total_tiles = m_units * p.n_ntiles;
   const int cx_chunks = p.Cin / BLOCK_K;
   const int ch_chunks = p.Co / BLOCK_K;
@@ -326,7 +347,8 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
         int nt, mu;
         tile_split(p, tile, m_units, nt, mu);
-        const int mt = PAIR ? 2 * mu + static_cast<int>(cta_rank) : mu;
+        bool own_tile = true;
+        const int mt = PAIR ? pair_mtile(p, mu, static_cast<int>(cta_rank), own_tile) : mu;
         const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
         int wrow = group_of(p, mt) * p.w_group_rows + nt * BLOCK_N;
         if (PAIR) {  // this CTA stages its half of the (possibly narrower, dgrad) N tile
@@ -447,7 +469,8 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
       int nt, mu;
       tile_split(p, tile, m_units, nt, mu);
-      const int mt = PAIR ? 2 * mu + static_cast<int>(cta_rank) : mu;
+      bool own_tile = true;
+      const int mt = PAIR ? pair_mtile(p, mu, static_cast<int>(cta_rank), own_tile) : mu;
       const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
       const int g = group_of(p, mt);
       const int acc = it & 1;
@@ -455,7 +478,9 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-      if (EPI == EPI_GATES)
+      if (!own_tile) {
+        // the filler CTA of an odd node: nothing to store
+      } else if (EPI == EPI_GATES)
         epilogue_gates<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl);
       else
         epilogue_dgrad<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl);
@@ -488,7 +513,7 @@ int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured[dev] = true;
   }
-  const int total = (PAIR ? p.n_mtiles / 2 : p.n_mtiles) * p.n_ntiles;
+  const int total = (PAIR ? p.n_munits : p.n_mtiles) * p.n_ntiles;
   if (!PAIR) {
     const int grid = total < num_sms ? total : num_sms;
     kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
@@ -526,7 +551,7 @@ size_t convlstm_gates_smem_bytes(bool split, int block_n) {
 int launch_convlstm_gates(const GateParams& p, bool split, int block_n, bool pair, int num_sms,
                           cudaStream_t stream) {
   if (pair) {  // CTA pairs: 256-pixel x 256-column tiles only
-    if (block_n != 256 || (p.n_mtiles & 1)) return static_cast<int>(cudaErrorInvalidValue);
+    if (block_n != 256 || p.n_munits <= 0) return static_cast<int>(cudaErrorInvalidValue);
     return split ? launch_t<true, 256, EPI_GATES, true>(p, num_sms, stream)
                  : launch_t<false, 256, EPI_GATES, true>(p, num_sms, stream);
   }
@@ -548,7 +573,7 @@ int launch_convlstm_gates(const GateParams& p, bool split, int block_n, bool pai
 
 int launch_convlstm_dgrad(const GateParams& p, bool split, bool pair, int num_sms, cudaStream_t stream) {
   if (pair) {
-    if (p.n_mtiles & 1) return static_cast<int>(cudaErrorInvalidValue);
+    if (p.n_munits <= 0) return static_cast<int>(cudaErrorInvalidValue);
     return split ? launch_t<true, 256, EPI_DGRAD, true>(p, num_sms, stream)
                  : launch_t<false, 256, EPI_DGRAD, true>(p, num_sms, stream);
   }

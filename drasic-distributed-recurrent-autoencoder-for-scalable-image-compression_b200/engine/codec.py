@@ -78,11 +78,12 @@ class BatchPlan(object):
         self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
         self.perm = torch.from_numpy(perm).to(device)
         self.group_img_end = torch.from_numpy(ends).to(device)
-        self._mtile_end, self._kb_end = {}, {}
+        self._mtile_end, self._kb_end, self._pair_end = {}, {}, {}
         self.static = static_hw is not None
         for hw in static_hw or ():
             self.mtile_end(hw)
             self.kb_end(hw)
+            self.pair_end(hw)
 
     def _scaled(self, cache, hw, unit):
         if hw not in cache:
@@ -100,6 +101,24 @@ class BatchPlan(object):
         """exclusive end K block (64 pixels) of each node, for the wgrad GEMM"""
         return self._scaled(self._kb_end, hw, 64)
 
+    def _pair_ends_host(self, hw):
+        ends = (self.group_img_end_host.astype(np.int64) * hw) // 128
+        tiles = np.diff(np.concatenate(([0], ends)))
+        return np.cumsum((tiles + 1) // 2).astype(np.int32)
+
+    def pair_end(self, hw):
+        """CTA pairs: running ends of the pair units (two M tiles of the same node; a node with an odd number of
+        M tiles gets a half-filled last unit).  Returns (device array, total units)."""
+        host = self._pair_ends_host(hw)
+        if hw not in self._pair_end:
+            if self.static and getattr(self, '_frozen', False):
+                raise RuntimeError('static batch plan has no buffer for hw={}'.format(hw))
+            self._pair_end[hw] = torch.from_numpy(host).to(self.device)
+        total = int(host[-1]) if host.size else 0
+        if self.static:      # a captured graph launches a fixed unit count: the bound for any labelling (extra units are no-ops)
+            total = (self.B_pad * hw // 128 + self.num_node + 1) // 2
+        return self._pair_end[hw], total
+
     def update(self, label_host):
         """refresh the device buffers in place for a new batch of the same size"""
         perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad, self.pad)
@@ -112,6 +131,8 @@ class BatchPlan(object):
         for cache, unit in ((self._mtile_end, 128), (self._kb_end, 64)):
             for hw, t in cache.items():
                 t.copy_(torch.from_numpy(((ends.astype(np.int64) * hw) // unit).astype(np.int32)))
+        for hw, t in self._pair_end.items():
+            t.copy_(torch.from_numpy(self._pair_ends_host(hw)))
 
 
 class _Layer(object):
@@ -211,13 +232,13 @@ class CodecEngine(object):
         return 64
 
     def _use_pair(self, n_mtiles, hw, co, pad=PAD):
-        """CTA pairs need 256-column N tiles and node boundaries on even M tiles: a node's slots are a
-        multiple of `pad` images, i.e. pad*hw/128 M tiles -- even once pad*hw >= 256."""
-        if self.cta_pair == 'off' or (pad * hw) % 256 or n_mtiles % 2:
+        """CTA pairs (256-column N tiles): pair units are formed inside each node (BatchPlan.pair_end), a node
+        with an odd number of M tiles leaves half of its last unit idle"""
+        if self.cta_pair == 'off':
             return False
         if self.cta_pair == 'on':
             return True
-        return n_mtiles // 2 * (4 * co // 256) >= self.sms() // 2
+        return (n_mtiles + 1) // 2 * (4 * co // 256) >= self.sms() // 2
 
     def _get_arena(self, B_pad, H, W, device, T=0):
         """T == 0: inference arena (h ping-pongs, c in place, one buffer per edge).  T > 0: training
@@ -382,6 +403,9 @@ class CodecEngine(object):
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
             ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
+            ly.pair_end, ly.pair_units = (None, (n_mtiles + 1) // 2)
+            if ly.pair and ly.groups > 1:
+                ly.pair_end, ly.pair_units = plan.pair_end(h * w)
             layers.append(ly)
 
         self._repack = False
@@ -457,6 +481,7 @@ class CodecEngine(object):
             a.next_mode, a.next_f32 = ly.next_mode, ly.next_f32
             a.split, a.precise, a.block_n = self.split, self.precise, ly.block_n
             a.cta_pair = int(ly.pair)
+            a.group_pair_end, a.n_pair_units = P(ly.pair_end), ly.pair_units
             # algorithmic FLOPs of this launch: real images only, hidden conv skipped on zero state
             k = 9 * (ly.cin + (ly.co if t > 0 else 0))
             flops = 2.0 * Bn * ly.h * ly.w * 4 * ly.co * k
@@ -550,6 +575,9 @@ class CodecEngine(object):
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, DEC_IDX[name]) for p in dec_pref], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
             ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
+            ly.pair_end, ly.pair_units = (None, (n_mtiles + 1) // 2)
+            if ly.pair and ly.groups > 1:
+                ly.pair_end, ly.pair_units = plan.pair_end(h * w)
             layers.append(ly)
         self._repack = False      # (the encoder planes stay stale: _stale is cleared only by a full forward)
         w_d0 = stack([p + '.0.cell.cell.main.weight' for p in dec_pref])
@@ -586,6 +614,7 @@ class CodecEngine(object):
                 g.n_groups, g.has_state = ly.groups, 1 if t > 0 else 0
                 g.next_mode, g.next_f32 = ly.next_mode, ly.next_f32
                 g.split, g.precise, g.block_n, g.cta_pair = self.split, self.precise, ly.block_n, int(ly.pair)
+                g.group_pair_end, g.n_pair_units = P(ly.pair_end), ly.pair_units
                 B.check(L.drasic_convlstm_fwd(g, stream), 'convlstm_fwd (decode)')
                 x = nxt
             th = B.TailHeadArgs()
@@ -746,6 +775,7 @@ class CodecEngine(object):
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.gsplit
             a.cta_pair = int(ly.pair)
+            a.group_pair_end, a.n_pair_units = P(ly.pair_end), ly.pair_units
             fl = 2.0 * Bn * ly.h * ly.w * 36 * ly.co * (ly.cin + (ly.co if t > 0 else 0))
             self._timed('dgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_data(a, stream), 'convlstm_bwd_data'))
             w = B.WgradArgs()

@@ -84,8 +84,10 @@ typedef struct {
   int precise;                          /* 1: IEEE exp/div/tanh, 0: tanh.approx */
   int block_n;                          /* N tile: 256, 128 or 64 (must match the packing) */
   int gates_f32;                        /* dtype of gates_out */
-  int cta_pair;                         /* 1: CTA pairs (cta_group::2) on 256-pixel x 256-column tiles; needs block_n == 256, an even
-                                           number of M tiles and node boundaries on even M tiles */
+  int cta_pair;                         /* 1: CTA pairs (cta_group::2) on 256-pixel x 256-column tiles; needs block_n == 256 */
+  const int* group_pair_end;            /* cta_pair with n_groups > 1: device [n_groups], running ends of the pair units
+                                           (node g owns ceil(tiles_g / 2) of them; a pair never straddles two nodes) */
+  int n_pair_units;                     /* cta_pair: total pair units = group_pair_end[n_groups-1], or ceil(M tiles / 2) */
 } drasic_convlstm_args;
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream);
 
@@ -179,6 +181,7 @@ typedef struct {
   const int* group_mtile_end;
   int B_pad, H, W, Cin, Co, n_groups, dx_mode, split;
   int cta_pair;                           /* as in drasic_convlstm_args */
+  const int* group_pair_end; int n_pair_units;
 } drasic_dgrad_args;
 int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream);
 
