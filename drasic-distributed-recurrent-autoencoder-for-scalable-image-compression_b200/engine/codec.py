@@ -26,16 +26,6 @@ ENC_IDX = {'E1': 2, 'E2': 4, 'E3': 6}   # nn.Sequential indices, dist_codec.py:7
 DEC_IDX = {'D1': 1, 'D2': 3, 'D3': 5}   # dist_codec.py:88-104
 
 
-def choose_pad(counts, batch):
-    """slots per node are a multiple of 8 images (one 128-pixel M tile at 4x4) -- or of 16, which lets the 4x4
-    layers run as CTA pairs too, when that costs less than 1 % more slots (a single source, or large nodes)"""
-    if os.environ.get('DRASIC_PAD'):
-        return int(os.environ['DRASIC_PAD'])
-    counts = np.asarray(counts, dtype=np.int64)
-    extra = int(((counts + 15) // 16 * 16).sum() - ((counts + PAD - 1) // PAD * PAD).sum())
-    return 16 if extra * 100 <= max(int(batch), 1) else PAD
-
-
 def plan_arrays(label_host, num_node, pad_total=None, pad=None):
     """node-sort one batch: (perm [B_pad] slot -> original index or -1, exclusive end slot per node)"""
     label_host = np.asarray(label_host).astype(np.int64).reshape(-1)
@@ -355,10 +345,7 @@ class CodecEngine(object):
         if plan is None:
             if label_host is None:
                 label_host = label.detach().cpu().numpy()      # the one host sync per forward
-            lh = np.asarray(label_host).astype(np.int64).reshape(-1)
-            in_range = lh.size == 0 or (lh.min() >= 0 and lh.max() < self.M)
-            pad = choose_pad(np.bincount(lh, minlength=self.M), lh.size) if in_range and self.cta_pair != 'off' else PAD
-            plan = BatchPlan(label_host, self.M, dev, pad=pad)
+            plan = BatchPlan(label_host, self.M, dev)
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
@@ -546,10 +533,7 @@ class CodecEngine(object):
         T, Bn = int(bits.shape[0]), int(bits.shape[1])
         if label_host is None:
             label_host = label.detach().cpu().numpy()
-        lh = np.asarray(label_host).astype(np.int64).reshape(-1)
-        in_range = lh.size == 0 or (lh.min() >= 0 and lh.max() < self.M)
-        pad = choose_pad(np.bincount(lh, minlength=self.M), lh.size) if in_range and self.cta_pair != 'off' else PAD
-        plan = BatchPlan(label_host, self.M, dev, pad=pad)
+        plan = BatchPlan(label_host, self.M, dev)
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
