@@ -362,11 +362,13 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   p.H = H; p.W = W; p.Cin = Cg; p.Co = Co;
   p.bw = bw; p.bh = bh; p.bn = bn;
   p.n_mtiles = static_cast<int>(static_cast<long long>(B) * H * W / 128);
-  p.n_ntiles = (Nout + 255) / 256;
+  // without a dH_{t-1} destination (t == 0) only the dX columns are computed
+  const int Nuse = a->dhrec_out ? Nout : Cin;
+  p.n_ntiles = (Nuse + 255) / 256;
   { static const int ord = getenv("DRASIC_TILE_ORDER") ? atoi(getenv("DRASIC_TILE_ORDER")) : 0; p.tile_order = ord; }
   p.n_groups = a->n_groups; p.group_mtile_end = a->group_mtile_end;
   p.group_pair_end = a->group_pair_end; p.n_munits = a->n_pair_units;
-  p.w_group_rows = Nout; p.n_out = Nout; p.n_x = Cin; p.dx_mode = a->dx_mode;
+  p.w_group_rows = Nout; p.n_out = Nuse; p.n_x = Cin; p.dx_mode = a->dx_mode;
   p.dx_out = a->dx_out; p.dhrec_out = a->dhrec_out;
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
