@@ -195,8 +195,9 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   }
   const int K = 9 * (Cin + Co);
   const bool pair = a->cta_pair != 0;
-  if (pair && (a->block_n != 256 || a->n_pair_units <= 0 || (a->n_groups > 1 && !a->group_pair_end)))
-    return fail(DRASIC_ERR_INVALID, "convlstm_fwd: cta_pair needs block_n == 256, n_pair_units and (n_groups > 1) group_pair_end");
+  if (pair && a->block_n != 256) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: cta_pair needs block_n == 256");
+  if (a->n_units <= 0 || (a->n_groups > 1 && (!a->group_mtile_start || !a->group_unit_end || !a->group_img_end)))
+    return fail(DRASIC_ERR_INVALID, "convlstm_fwd: n_units and (n_groups > 1) group_mtile_start / group_unit_end / group_img_end");
   const int w_box_rows = pair ? a->block_n / 2 : a->block_n;   // each CTA of a pair stages half of the N tile
   if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * 4 * Co, K, w_box_rows))) return rc;
   if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * 4 * Co, K, w_box_rows))) return rc;
@@ -222,7 +223,8 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   p.precise = a->precise;
   p.n_groups = a->n_groups;
   p.group_mtile_end = a->group_mtile_end;
-  p.group_pair_end = a->group_pair_end; p.n_munits = a->n_pair_units;
+  p.group_mtile_start = a->group_mtile_start; p.group_unit_end = a->group_unit_end; p.group_img_end = a->group_img_end;
+  p.n_munits = a->n_units;
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
   return cuda_fail(drasic::launch_convlstm_gates(p, a->split != 0, a->block_n, pair, sms, static_cast<cudaStream_t>(stream)),
@@ -354,8 +356,8 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   if ((rc = make_act_map(&p.tm_x[0], a->dg_hi, B, H, W, Cg, bw, bh, bn))) return rc;
   if (a->split && (rc = make_act_map(&p.tm_x[1], a->dg_lo, B, H, W, Cg, bw, bh, bn))) return rc;
   const bool pair = a->cta_pair != 0;
-  if (pair && (a->n_pair_units <= 0 || (a->n_groups > 1 && !a->group_pair_end)))
-    return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: cta_pair needs n_pair_units and (n_groups > 1) group_pair_end");
+  if (a->n_units <= 0 || (a->n_groups > 1 && (!a->group_mtile_start || !a->group_unit_end || !a->group_img_end)))
+    return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: n_units and (n_groups > 1) group_mtile_start / group_unit_end / group_img_end");
   if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * Nout, K, pair ? 128 : 256))) return rc;
   if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * Nout, K, pair ? 128 : 256))) return rc;
   p.w_inv_scale = a->w_inv_scale; p.a_inv_scale = a->dg_inv_scale;
@@ -367,7 +369,8 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   p.n_ntiles = (Nuse + 255) / 256;
   { static const int ord = getenv("DRASIC_TILE_ORDER") ? atoi(getenv("DRASIC_TILE_ORDER")) : 0; p.tile_order = ord; }
   p.n_groups = a->n_groups; p.group_mtile_end = a->group_mtile_end;
-  p.group_pair_end = a->group_pair_end; p.n_munits = a->n_pair_units;
+  p.group_mtile_start = a->group_mtile_start; p.group_unit_end = a->group_unit_end; p.group_img_end = a->group_img_end;
+  p.n_munits = a->n_units;
   p.w_group_rows = Nout; p.n_out = Nuse; p.n_x = Cin; p.dx_mode = a->dx_mode;
   p.dx_out = a->dx_out; p.dhrec_out = a->dhrec_out;
   const int sms = num_sms();

@@ -95,25 +95,42 @@ __device__ __forceinline__ void tile_split(const GateParams& p, int tile, int m_
   else { mu = tile % m_units; nt = tile / m_units; }
 }
 
-// CTA pairs: M unit `mu` -> the M tile of this CTA.  Pair units never straddle two nodes: node g owns
-// ceil(tiles_g / 2) units (group_pair_end[] holds the running ends); when a node has an odd number of M tiles
-// the second CTA of its last unit has no tile of its own -- it stages the first CTA's pixels again (the
-// cta_group::2 MMA reads both CTAs' shared memory) and skips its epilogue.
-__device__ __forceinline__ int pair_mtile(const GateParams& p, int mu, int rank, bool& valid) {
+// Work units of the M dimension.  A node's slots are a multiple of 4 images, so at the 4x4 layers (one M tile =
+// 8 images) a tile can hold images of two nodes: every node walks ALL tiles that overlap its slot range
+// (group_mtile_start / group_mtile_end, ranges of neighbouring nodes may share a tile) with its own weights
+// and the epilogue stores only the rows of its own images (group_img_end).  Units are single tiles, or -- CTA
+// pairs -- two consecutive tiles of the same node; group_unit_end[] holds the running unit counts.  When a
+// node has an odd number of tiles the second CTA of its last pair has no tile of its own: it stages the first
+// CTA's pixels again (the cta_group::2 MMA reads both CTAs' shared memory) and stores nothing.
+struct MUnit {
+  int mt;        // M tile this CTA stages
+  int g;         // node (weight group)
+  int img_lo, img_hi;   // slots whose rows this unit may store
+  bool own;      // false: filler CTA of an odd pair
+};
+template <bool PAIR>
+__device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank) {
+  MUnit u;
   int first, end;
-  if (p.n_groups > 1 && p.group_pair_end != nullptr) {
+  if (p.n_groups > 1) {
     int g = 0;
-    while (g + 1 < p.n_groups && mu >= p.group_pair_end[g]) ++g;
-    const int unit0 = g ? p.group_pair_end[g - 1] : 0;
-    const int tile0 = g ? p.group_mtile_end[g - 1] : 0;
-    first = tile0 + 2 * (mu - unit0);
+    while (g + 1 < p.n_groups && mu >= p.group_unit_end[g]) ++g;
+    const int unit0 = g ? p.group_unit_end[g - 1] : 0;
+    first = p.group_mtile_start[g] + (PAIR ? 2 : 1) * (mu - unit0);
     end = p.group_mtile_end[g];
+    u.g = g;
+    u.img_lo = g ? p.group_img_end[g - 1] : 0;
+    u.img_hi = p.group_img_end[g];
   } else {
-    first = 2 * mu;
+    first = (PAIR ? 2 : 1) * mu;
     end = p.n_mtiles;
+    u.g = 0;
+    u.img_lo = 0;
+    u.img_hi = 0x7fffffff;
   }
-  valid = first + rank < end;
-  return valid ? first + rank : first;
+  u.own = first + rank < end;
+  u.mt = u.own ? first + rank : first;
+  return u;
 }
 
 struct TileCoord {
@@ -131,17 +148,12 @@ __device__ __forceinline__ TileCoord tile_coord(const GateParams& p, int mt, int
   }
   return t;
 }
-__device__ __forceinline__ int group_of(const GateParams& p, int mt) {
-  int g = 0;
-  while (g + 1 < p.n_groups && mt >= p.group_mtile_end[g]) ++g;
-  return g;
-}
 
 // ---------------------------------------------------------------- epilogues (one tile row per thread)
 // ConvLSTM gates: the N tile holds i,f,g,o of SLOTS channels (columns gate*SLOTS + s)
 template <bool SPLIT, int BLOCK_N>
 __device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_row, int nt, int g, int n,
-                                               int y, int x) {
+                                               int y, int x, bool row_ok) {
   constexpr int SLOTS = BLOCK_N / 4;  // channels per N tile
   const int H = p.H, W = p.W, Co = p.Co;
   const float inv = __ldg(&p.w_inv_scale[g]);
@@ -154,6 +166,7 @@ __device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_r
     ptx::tmem_ld16(t_row + 2 * SLOTS + j * 16, gg);
     ptx::tmem_ld16(t_row + 3 * SLOTS + j * 16, go);
     ptx::tmem_ld_wait();
+    if (!row_ok) continue;   // (the TMEM loads above are warp-collective; everything below is per row)
     const int p0 = nt * SLOTS + j * 16;  // first physical channel of this chunk
     float cv[16];
     if (p.has_cell) {
@@ -235,7 +248,7 @@ __device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_r
 // dgrad: columns are output channels [dX (n_x) | dH_prev (n_out - n_x)], fp32 stores
 template <bool SPLIT, int BLOCK_N>
 __device__ __forceinline__ void epilogue_dgrad(const GateParams& p, uint32_t t_row, int nt, int g, int n,
-                                               int y, int x) {
+                                               int y, int x, bool row_ok) {
   const int H = p.H, W = p.W;
   const float inv = __ldg(&p.w_inv_scale[g]) * __ldg(p.a_inv_scale);
   const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
@@ -246,6 +259,7 @@ __device__ __forceinline__ void epilogue_dgrad(const GateParams& p, uint32_t t_r
     float v[16];
     ptx::tmem_ld16(t_row + j * 16, v);
     ptx::tmem_ld_wait();
+    if (!row_ok) continue;
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] *= inv;
     const int c = col0 + j * 16;
@@ -329,7 +343,7 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
   // tile walk: a work unit is one M tile (1 CTA) or one pair of adjacent M tiles (CTA pair) x one N tile
   const int unit_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
   const int unit_first = PAIR ? blockIdx.x >> 1 : blockIdx.x;
-  const int m_units = PAIR ? p.n_munits : p.n_mtiles;
+  const int m_units = p.n_munits;
   const int total_tiles = m_units * p.n_ntiles;
   const int cx_chunks = p.Cin / BLOCK_K;
   const int ch_chunks = p.Co / BLOCK_K;
@@ -347,10 +361,10 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
         int nt, mu;
         tile_split(p, tile, m_units, nt, mu);
-        bool own_tile = true;
-        const int mt = PAIR ? pair_mtile(p, mu, static_cast<int>(cta_rank), own_tile) : mu;
+        const MUnit un = m_unit<PAIR>(p, mu, static_cast<int>(cta_rank));
+        const int mt = un.mt;
         const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
-        int wrow = group_of(p, mt) * p.w_group_rows + nt * BLOCK_N;
+        int wrow = un.g * p.w_group_rows + nt * BLOCK_N;
         if (PAIR) {  // this CTA stages its half of the (possibly narrower, dgrad) N tile
           int width = BLOCK_N;
           if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
@@ -469,21 +483,20 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
       int nt, mu;
       tile_split(p, tile, m_units, nt, mu);
-      bool own_tile = true;
-      const int mt = PAIR ? pair_mtile(p, mu, static_cast<int>(cta_rank), own_tile) : mu;
-      const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
-      const int g = group_of(p, mt);
+      const MUnit un = m_unit<PAIR>(p, mu, static_cast<int>(cta_rank));
+      const TileCoord tc = tile_coord(p, un.mt, tiles_x, tiles_per_img);
+      const int g = un.g;
+      // rows of another node's images (a shared 4x4 tile) and the filler CTA of an odd pair store nothing
+      const bool row_ok = un.own && tc.n0 + nl >= un.img_lo && tc.n0 + nl < un.img_hi;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-      if (!own_tile) {
-        // the filler CTA of an odd node: nothing to store
-      } else if (EPI == EPI_GATES)
-        epilogue_gates<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl);
+      if (EPI == EPI_GATES)
+        epilogue_gates<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl, row_ok);
       else
-        epilogue_dgrad<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl);
+        epilogue_dgrad<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl, row_ok);
       // release the accumulator to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
@@ -513,7 +526,7 @@ int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured[dev] = true;
   }
-  const int total = (PAIR ? p.n_munits : p.n_mtiles) * p.n_ntiles;
+  const int total = p.n_munits * p.n_ntiles;
   if (!PAIR) {
     const int grid = total < num_sms ? total : num_sms;
     kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);

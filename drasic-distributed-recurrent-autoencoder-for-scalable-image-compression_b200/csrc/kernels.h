@@ -54,9 +54,14 @@ struct GateParams {
   int next_mode, next_f32;
   int precise;               // 1: IEEE exp/div/tanh (parity mode); 0: tanh.approx
   int n_groups;
-  const int* group_mtile_end;  // device [n_groups]: group g owns m-tiles [end[g-1], end[g])
-  const int* group_pair_end;   // CTA pairs, n_groups > 1: device [n_groups] running ends of ceil(tiles_g / 2) pair units
-  int n_munits;                // CTA pairs: total pair units
+  // n_groups > 1 (device arrays of n_groups ints): node g walks the M tiles [start[g], end[g]) -- neighbouring
+  // ranges may share a tile -- as units (tiles, or pairs of tiles) numbered up to unit_end[g], and stores the
+  // rows of the slots [img_end[g-1], img_end[g])
+  const int* group_mtile_start;
+  const int* group_mtile_end;
+  const int* group_unit_end;
+  const int* group_img_end;
+  int n_munits;                // total work units of the M dimension
   // ---- dgrad epilogue (EPI_DGRAD): D[pixels, Nout] = conv3x3^T(dG) ; Cin here = 4*Co of the layer
   int w_group_rows;            // weight-matrix rows per group (4Co for gates, Nout rounded for dgrad)
   int n_out;                   // dgrad: output columns = layer Cin + layer Co

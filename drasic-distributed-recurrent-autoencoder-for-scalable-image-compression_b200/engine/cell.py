@@ -113,6 +113,7 @@ class CellRunner(object):
         a.next_hi = P(self.h_f32)
         a.B_pad, a.H, a.W, a.Cin, a.Co = n_pad, H, W, cin, co
         a.n_groups = 1
+        a.n_units = n_mtiles              # one work unit per M tile (single CTAs, one weight group)
         a.has_state = 1 if self.t > 0 else 0
         a.next_mode, a.next_f32 = B.NEXT_SAME, 1
         a.split, a.precise, a.block_n = self.split, self.precise, block_n

@@ -13,7 +13,8 @@ import torch
 
 from . import binding as B
 
-PAD = 8  # slots per node are padded to a multiple of 8 images (one 128-pixel M tile at 4x4)
+PAD = 4        # slots per node are padded to a multiple of 4 images (one 64-pixel wgrad K block at the 4x4 layers)
+TOTAL_PAD = 8  # ... and the whole batch to 8 (one 128-pixel M tile at the 4x4 layers)
 
 # (name, Cin, Co, spatial divisor, in_order, out_order, next_mode, next_f32)
 ENC_LAYERS = (('E1', 128, 128, 2, B.ORDER_QUAD, B.ORDER_IDENT, B.NEXT_DOWN, 0),
@@ -26,7 +27,7 @@ ENC_IDX = {'E1': 2, 'E2': 4, 'E3': 6}   # nn.Sequential indices, dist_codec.py:7
 DEC_IDX = {'D1': 1, 'D2': 3, 'D3': 5}   # dist_codec.py:88-104
 
 
-def plan_arrays(label_host, num_node, pad_total=None, pad=None):
+def plan_arrays(label_host, num_node, pad_total=None):
     """node-sort one batch: (perm [B_pad] slot -> original index or -1, exclusive end slot per node)"""
     label_host = np.asarray(label_host).astype(np.int64).reshape(-1)
     if label_host.size and (label_host.min() < 0 or label_host.max() >= num_node):
@@ -34,11 +35,11 @@ def plan_arrays(label_host, num_node, pad_total=None, pad=None):
         raise IndexError('label out of range for num_node={}'.format(num_node))
     order = np.argsort(label_host, kind='stable')              # keeps the reference's within-node order
     counts = np.bincount(label_host, minlength=num_node)
-    pad = PAD if pad is None else int(pad)
-    padded = (counts + pad - 1) // pad * pad
+    padded = (counts + PAD - 1) // PAD * PAD
     ends = np.cumsum(padded)
-    B_pad = int(ends[-1]) if pad_total is None else int(pad_total)
-    if B_pad < int(ends[-1]) or B_pad % pad:
+    need = (int(ends[-1]) + TOTAL_PAD - 1) // TOTAL_PAD * TOTAL_PAD
+    B_pad = need if pad_total is None else int(pad_total)
+    if B_pad < need or B_pad % TOTAL_PAD:
         raise ValueError('Not valid pad_total')
     perm = np.full(B_pad, -1, dtype=np.int32)
     starts = ends - padded
@@ -47,82 +48,88 @@ def plan_arrays(label_host, num_node, pad_total=None, pad=None):
         n = int(counts[j])
         perm[starts[j]:starts[j] + n] = order[src:src + n]
         src += n
+    # the alignment slots at the end belong to the last node: every slot is inside exactly one node's range, so
+    # every row of every tensor is (re)written each pass -- padding rows carry zeros through backward
+    ends = ends.copy()
+    ends[-1] = B_pad
     return perm, ends.astype(np.int32), counts
 
 
 def worst_case_pad(B, num_node):
     """slot count that fits any assignment of B samples to num_node nodes"""
-    return (B + (PAD - 1) * min(num_node, B) + PAD - 1) // PAD * PAD
+    return (B + (PAD - 1) * min(num_node, B) + TOTAL_PAD - 1) // TOTAL_PAD * TOTAL_PAD
 
 
 class BatchPlan(object):
     """Node-sorted, padded slot layout of one batch.  With `static_hw` the plan owns fixed device
     buffers (worst-case slot count) that update() refreshes in place -- what a captured CUDA graph reads."""
 
-    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None, pad=None):
+    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None):
         self.num_node, self.device = num_node, device
         self.pad_total = pad_total
-        self.pad = PAD if pad is None else int(pad)      # padding unit of every node's slot range
-        perm, ends, counts = plan_arrays(label_host, num_node, pad_total, self.pad)
+        perm, ends, counts = plan_arrays(label_host, num_node, pad_total)
         self.B, self.B_pad = int(np.asarray(label_host).size), int(perm.size)
         self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
         self.perm = torch.from_numpy(perm).to(device)
         self.group_img_end = torch.from_numpy(ends).to(device)
-        self._mtile_end, self._kb_end, self._pair_end = {}, {}, {}
+        self._kb_end, self._units = {}, {}
         self.static = static_hw is not None
         for hw in static_hw or ():
-            self.mtile_end(hw)
             self.kb_end(hw)
-            self.pair_end(hw)
-
-    def _scaled(self, cache, hw, unit):
-        if hw not in cache:
-            if self.static and getattr(self, '_frozen', False):
-                raise RuntimeError('static batch plan has no buffer for hw={}'.format(hw))
-            e = (self.group_img_end_host.astype(np.int64) * hw) // unit
-            cache[hw] = torch.from_numpy(e.astype(np.int32)).to(self.device)
-        return cache[hw]
-
-    def mtile_end(self, hw):
-        """exclusive end M-tile (128 pixels) of each node at a layer with hw pixels per image"""
-        return self._scaled(self._mtile_end, hw, 128)
+            for pair in (False, True):
+                self.m_units(hw, pair)
 
     def kb_end(self, hw):
-        """exclusive end K block (64 pixels) of each node, for the wgrad GEMM"""
-        return self._scaled(self._kb_end, hw, 64)
-
-    def _pair_ends_host(self, hw):
-        ends = (self.group_img_end_host.astype(np.int64) * hw) // 128
-        tiles = np.diff(np.concatenate(([0], ends)))
-        return np.cumsum((tiles + 1) // 2).astype(np.int32)
-
-    def pair_end(self, hw):
-        """CTA pairs: running ends of the pair units (two M tiles of the same node; a node with an odd number of
-        M tiles gets a half-filled last unit).  Returns (device array, total units)."""
-        host = self._pair_ends_host(hw)
-        if hw not in self._pair_end:
+        """exclusive end K block (64 pixels) of each node, for the wgrad GEMM (node ranges are multiples of 4
+        images, so K blocks never mix two nodes)"""
+        if hw not in self._kb_end:
             if self.static and getattr(self, '_frozen', False):
                 raise RuntimeError('static batch plan has no buffer for hw={}'.format(hw))
-            self._pair_end[hw] = torch.from_numpy(host).to(self.device)
-        total = int(host[-1]) if host.size else 0
+            self._kb_end[hw] = torch.from_numpy(self._kb_host(hw)).to(self.device)
+        return self._kb_end[hw]
+
+    def _kb_host(self, hw):
+        return ((self.group_img_end_host.astype(np.int64) * hw) // 64).astype(np.int32)
+
+    def _units_host(self, hw, pair):
+        """per node: first / end M tile (128 pixels) overlapping its slot range -- neighbours may share a tile
+        where an image is smaller than 32 pixels -- and the running count of work units (tiles, or pairs of tiles)"""
+        ends = self.group_img_end_host.astype(np.int64)
+        starts = np.concatenate(([0], ends[:-1]))
+        t0 = (starts * hw) // 128
+        t1 = -((-ends * hw) // 128)
+        t1 = np.where(ends > starts, t1, t0)                    # empty nodes walk nothing
+        n = t1 - t0
+        units = (n + 1) // 2 if pair else n
+        return np.stack([t0, t1, np.cumsum(units)]).astype(np.int32)
+
+    def m_units(self, hw, pair):
+        """(device [3, num_node]: tile start, tile end, running unit end; total units) for the conv GEMMs"""
+        host = self._units_host(hw, pair)
+        key = (hw, bool(pair))
+        if key not in self._units:
+            if self.static and getattr(self, '_frozen', False):
+                raise RuntimeError('static batch plan has no buffer for hw={}'.format(hw))
+            self._units[key] = torch.from_numpy(host).to(self.device)
+        total = int(host[2, -1])
         if self.static:      # a captured graph launches a fixed unit count: the bound for any labelling (extra units are no-ops)
-            total = (self.B_pad * hw // 128 + self.num_node + 1) // 2
-        return self._pair_end[hw], total
+            tiles = self.B_pad * hw // 128 + self.num_node
+            total = (tiles + self.num_node + 1) // 2 if pair else tiles
+        return self._units[key], total
 
     def update(self, label_host):
         """refresh the device buffers in place for a new batch of the same size"""
-        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad, self.pad)
+        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad)
         if int(np.asarray(label_host).size) != self.B:
             raise ValueError('Not valid batch size for this static plan')
         self._frozen = True
         self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
         self.perm.copy_(torch.from_numpy(perm), non_blocking=False)
         self.group_img_end.copy_(torch.from_numpy(ends))
-        for cache, unit in ((self._mtile_end, 128), (self._kb_end, 64)):
-            for hw, t in cache.items():
-                t.copy_(torch.from_numpy(((ends.astype(np.int64) * hw) // unit).astype(np.int32)))
-        for hw, t in self._pair_end.items():
-            t.copy_(torch.from_numpy(self._pair_ends_host(hw)))
+        for hw, t in self._kb_end.items():
+            t.copy_(torch.from_numpy(self._kb_host(hw)))
+        for (hw, pair), t in self._units.items():
+            t.copy_(torch.from_numpy(self._units_host(hw, pair)))
 
 
 class _Layer(object):
@@ -221,8 +228,8 @@ class CodecEngine(object):
                 return bn
         return 64
 
-    def _use_pair(self, n_mtiles, hw, co, pad=PAD):
-        """CTA pairs (256-column N tiles): pair units are formed inside each node (BatchPlan.pair_end), a node
+    def _use_pair(self, n_mtiles, hw, co):
+        """CTA pairs (256-column N tiles): pair units are formed inside each node (BatchPlan.m_units), a node
         with an odd number of M tiles leaves half of its last unit idle"""
         if self.cta_pair == 'off':
             return False
@@ -384,15 +391,15 @@ class CodecEngine(object):
             ly.name, ly.cin, ly.co, ly.h, ly.w = name, cin, co, h, w
             ly.next_mode, ly.next_f32 = nmode, nf32
             ly.in_order, ly.out_order, ly.is_enc, ly.idx, ly.prefs = io, oo, is_enc, idx, prefs
-            ly.pair = self._use_pair(n_mtiles, h * w, co, plan.pad)
+            ly.pair = self._use_pair(n_mtiles, h * w, co)
             ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.groups = len(prefs)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
-            ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
-            ly.pair_end, ly.pair_units = (None, (n_mtiles + 1) // 2)
-            if ly.pair and ly.groups > 1:
-                ly.pair_end, ly.pair_units = plan.pair_end(h * w)
+            # work units of the M dimension: per-node tile ranges (device) for grouped layers, plain tiles otherwise
+            ly.units, ly.n_units = None, ((n_mtiles + 1) // 2 if ly.pair else n_mtiles)
+            if ly.groups > 1:
+                ly.units, ly.n_units = plan.m_units(h * w, ly.pair)
             layers.append(ly)
 
         self._repack = False
@@ -461,14 +468,16 @@ class CodecEngine(object):
             a.w_hi, a.w_lo, a.w_inv_scale = P(ly.hi), P(ly.lo), P(ly.inv)
             a.h_out_hi, a.h_out_lo = P(cur[0]), P(cur[1])
             a.next_hi, a.next_lo = P(nxt[0]), P(nxt[1])
-            a.group_mtile_end = P(ly.mtile_end)
+            a.group_mtile_start = ly.units[0].data_ptr() if ly.units is not None else None
+            a.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
+            a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
+            a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups = ly.groups
             a.has_state = 1 if t > 0 else 0
             a.next_mode, a.next_f32 = ly.next_mode, ly.next_f32
             a.split, a.precise, a.block_n = self.split, self.precise, ly.block_n
             a.cta_pair = int(ly.pair)
-            a.group_pair_end, a.n_pair_units = P(ly.pair_end), ly.pair_units
             # algorithmic FLOPs of this launch: real images only, hidden conv skipped on zero state
             k = 9 * (ly.cin + (ly.co if t > 0 else 0))
             flops = 2.0 * Bn * ly.h * ly.w * 4 * ly.co * k
@@ -553,15 +562,15 @@ class CodecEngine(object):
             n_mtiles = Bp * h * w // 128
             ly = _Layer()
             ly.name, ly.cin, ly.co, ly.h, ly.w, ly.next_mode, ly.next_f32 = name, cin, co, h, w, nmode, nf32
-            ly.pair = self._use_pair(n_mtiles, h * w, co, plan.pad)
+            ly.pair = self._use_pair(n_mtiles, h * w, co)
             ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.groups = len(dec_pref)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, DEC_IDX[name]) for p in dec_pref], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
-            ly.mtile_end = plan.mtile_end(h * w) if ly.groups > 1 else None
-            ly.pair_end, ly.pair_units = (None, (n_mtiles + 1) // 2)
-            if ly.pair and ly.groups > 1:
-                ly.pair_end, ly.pair_units = plan.pair_end(h * w)
+            # work units of the M dimension: per-node tile ranges (device) for grouped layers, plain tiles otherwise
+            ly.units, ly.n_units = None, ((n_mtiles + 1) // 2 if ly.pair else n_mtiles)
+            if ly.groups > 1:
+                ly.units, ly.n_units = plan.m_units(h * w, ly.pair)
             layers.append(ly)
         self._repack = False      # (the encoder planes stay stale: _stale is cleared only by a full forward)
         w_d0 = stack([p + '.0.cell.cell.main.weight' for p in dec_pref])
@@ -593,12 +602,14 @@ class CodecEngine(object):
                 g.w_hi, g.w_lo, g.w_inv_scale = P(ly.hi), P(ly.lo), P(ly.inv)
                 g.h_out_hi, g.h_out_lo = P(cur[0]), P(cur[1])
                 g.next_hi, g.next_lo = P(nxt[0]), P(nxt[1])
-                g.group_mtile_end = P(ly.mtile_end)
+                g.group_mtile_start = ly.units[0].data_ptr() if ly.units is not None else None
+                g.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
+                g.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
+                g.group_img_end, g.n_units = P(plan.group_img_end), ly.n_units
                 g.B_pad, g.H, g.W, g.Cin, g.Co = Bp, ly.h, ly.w, ly.cin, ly.co
                 g.n_groups, g.has_state = ly.groups, 1 if t > 0 else 0
                 g.next_mode, g.next_f32 = ly.next_mode, ly.next_f32
                 g.split, g.precise, g.block_n, g.cta_pair = self.split, self.precise, ly.block_n, int(ly.pair)
-                g.group_pair_end, g.n_pair_units = P(ly.pair_end), ly.pair_units
                 B.check(L.drasic_convlstm_fwd(g, stream), 'convlstm_fwd (decode)')
                 x = nxt
             th = B.TailHeadArgs()
@@ -755,11 +766,13 @@ class CodecEngine(object):
             a.w_inv_scale, a.dg_inv_scale = P(inv), P(inv_dg)
             a.dx_out = P(dx_of[ly.name][0])
             a.dhrec_out = P(wb['dh_rec']) if t > 0 else None
-            a.group_mtile_end = P(ly.mtile_end)
+            a.group_mtile_start = ly.units[0].data_ptr() if ly.units is not None else None
+            a.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
+            a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
+            a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.gsplit
             a.cta_pair = int(ly.pair)
-            a.group_pair_end, a.n_pair_units = P(ly.pair_end), ly.pair_units
             fl = 2.0 * Bn * ly.h * ly.w * 36 * ly.co * (ly.cin + (ly.co if t > 0 else 0))
             self._timed('dgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_data(a, stream), 'convlstm_bwd_data'))
             w = B.WgradArgs()

@@ -15,7 +15,7 @@
  * Channels may be stored in "quad" order (DRASIC_ORDER_QUAD), the order in which the fused
  * pixel (un)shuffle stores are contiguous: physical p = q*(C/4) + c  <->  logical channel c*4 + q.
  * The batch is node-sorted and padded: slot s holds original image perm[s] (or -1), every node's
- * slot range is a multiple of 8 slots, group_img_end[g] is the exclusive end slot of node g.
+ * slot range is a multiple of 4 slots (the total a multiple of 8), group_img_end[g] is the exclusive end slot of node g.
  */
 #ifndef DRASIC_B200_H_
 #define DRASIC_B200_H_
@@ -75,7 +75,7 @@ typedef struct {
   void* gates_out;                      /* nullable: activated gates [B_pad,H,W,4,Co] saved for backward (fp16; fp32 when gates_f32) */
   void* h_out_hi; void* h_out_lo;       /* new h (must not alias h_hi/h_lo) */
   void* next_hi; void* next_lo;         /* consumer copy; fp32 tensor in next_hi when next_f32 */
-  const int* group_mtile_end;           /* device [n_groups]: exclusive end M-tile (128 pixels) per node */
+  const int* group_mtile_end;           /* device [n_groups]: exclusive end M-tile (128 pixels) per node, see below */
   int B_pad, H, W, Cin, Co;
   int n_groups;
   int has_state;                        /* 0 on iteration 0: h = c = 0 (cell.py:118-129) */
@@ -85,9 +85,14 @@ typedef struct {
   int block_n;                          /* N tile: 256, 128 or 64 (must match the packing) */
   int gates_f32;                        /* dtype of gates_out */
   int cta_pair;                         /* 1: CTA pairs (cta_group::2) on 256-pixel x 256-column tiles; needs block_n == 256 */
-  const int* group_pair_end;            /* cta_pair with n_groups > 1: device [n_groups], running ends of the pair units
-                                           (node g owns ceil(tiles_g / 2) of them; a pair never straddles two nodes) */
-  int n_pair_units;                     /* cta_pair: total pair units = group_pair_end[n_groups-1], or ceil(M tiles / 2) */
+  /* Work units of the M dimension.  n_groups > 1: device arrays of n_groups ints -- node g walks the M tiles
+   * [group_mtile_start[g], group_mtile_end[g]) (neighbouring ranges may share a tile: a node's slots are a multiple
+   * of 4 images, a 4x4-layer tile holds 8) as units numbered up to group_unit_end[g] (single tiles, or with
+   * cta_pair two consecutive tiles of the node, an odd last one alone), and stores only the rows of the slots
+   * [group_img_end[g-1], group_img_end[g]).  n_units: total units = group_unit_end[n_groups-1], or with one
+   * group the M tiles (cta_pair: ceil(M tiles / 2)). */
+  const int* group_mtile_start; const int* group_unit_end; const int* group_img_end;
+  int n_units;
 } drasic_convlstm_args;
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream);
 
@@ -181,7 +186,8 @@ typedef struct {
   const int* group_mtile_end;
   int B_pad, H, W, Cin, Co, n_groups, dx_mode, split;
   int cta_pair;                           /* as in drasic_convlstm_args */
-  const int* group_pair_end; int n_pair_units;
+  const int* group_mtile_start; const int* group_unit_end; const int* group_img_end;   /* as in drasic_convlstm_args */
+  int n_units;
 } drasic_dgrad_args;
 int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream);
 

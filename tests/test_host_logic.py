@@ -15,14 +15,22 @@ from engine.codec import BatchPlan, PAD
 def test_batch_plan_sorts_pads_and_keeps_order():
     label = np.array([2, 0, 2, 2, 0, 3, 2])
     p = BatchPlan(label, 4, 'cpu')
-    assert p.B == 7 and p.B_pad == 3 * PAD                 # node 1 is empty: no slots
-    assert list(p.group_img_end_host) == [8, 8, 16, 24]
-    assert list(p.perm_host[:2]) == [1, 4] and list(p.perm_host[8:12]) == [0, 2, 3, 6] and p.perm_host[16] == 5
-    assert (p.perm_host[[2, 7, 12, 15, 17, 23]] == -1).all()
+    assert PAD == 4 and p.B == 7 and p.B_pad == 16             # 4 + 0 + 4 + 4 slots, total rounded up to 8
+    assert list(p.group_img_end_host) == [4, 4, 8, 16]          # node 1 is empty: no slots; the last node owns the alignment slots
+    assert list(p.perm_host[:2]) == [1, 4] and list(p.perm_host[4:8]) == [0, 2, 3, 6] and p.perm_host[8] == 5
+    assert (p.perm_host[[2, 3, 9, 11, 12, 15]] == -1).all()
     valid = p.perm_host[p.perm_host >= 0]
     assert sorted(valid.tolist()) == list(range(7))
-    assert list(p.mtile_end(16).numpy()) == [1, 1, 2, 3]   # 4x4 layer: 8 images per 128-pixel tile
-    assert list(p.mtile_end(256).numpy()) == [16, 16, 32, 48]
+    # 4x4 layer (8 images per 128-pixel tile): nodes 0 and 2 share tile 0, node 3 walks tile 1
+    u, total = p.m_units(16, False)
+    assert u.numpy().tolist() == [[0, 0, 0, 1], [1, 0, 1, 2], [1, 1, 2, 3]] and total == 3
+    u, total = p.m_units(16, True)
+    assert u.numpy()[2].tolist() == [1, 1, 2, 3] and total == 3   # every node: one half-filled pair
+    # 16x16 layer: two tiles per image, ranges are disjoint
+    u, total = p.m_units(256, False)
+    assert u.numpy().tolist() == [[0, 8, 8, 16], [8, 8, 16, 32], [8, 8, 16, 32]] and total == 32
+    assert p.m_units(256, True)[1] == 16
+    assert list(p.kb_end(16).numpy()) == [1, 1, 2, 4]           # wgrad K blocks of 64 pixels = 4 images at 4x4
 
 
 def test_batch_plan_rejects_bad_labels_like_the_reference():
@@ -34,7 +42,8 @@ def test_batch_plan_large_ragged():
     rng = np.random.RandomState(2)
     label = rng.randint(0, 8, size=1000)
     p = BatchPlan(label, 8, 'cpu')
-    assert p.B_pad % PAD == 0 and p.B_pad >= 1000
+    assert p.B_pad % 8 == 0 and p.B_pad >= 1000 and p.B_pad <= 1000 + 3 * 8 + 7
+    assert (p.group_img_end_host % PAD == 0).all() and p.group_img_end_host[-1] == p.B_pad
     for j in range(8):
         lo = 0 if j == 0 else p.group_img_end_host[j - 1]
         idx = p.perm_host[lo:p.group_img_end_host[j]]
