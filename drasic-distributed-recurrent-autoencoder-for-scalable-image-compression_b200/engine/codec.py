@@ -27,7 +27,7 @@ ENC_IDX = {'E1': 2, 'E2': 4, 'E3': 6}   # nn.Sequential indices, dist_codec.py:7
 DEC_IDX = {'D1': 1, 'D2': 3, 'D3': 5}   # dist_codec.py:88-104
 
 
-def plan_arrays(label_host, num_node, pad_total=None):
+def plan_arrays(label_host, num_node, pad_total=None, pad=None):
     """node-sort one batch: (perm [B_pad] slot -> original index or -1, exclusive end slot per node)"""
     label_host = np.asarray(label_host).astype(np.int64).reshape(-1)
     if label_host.size and (label_host.min() < 0 or label_host.max() >= num_node):
@@ -35,7 +35,8 @@ def plan_arrays(label_host, num_node, pad_total=None):
         raise IndexError('label out of range for num_node={}'.format(num_node))
     order = np.argsort(label_host, kind='stable')              # keeps the reference's within-node order
     counts = np.bincount(label_host, minlength=num_node)
-    padded = (counts + PAD - 1) // PAD * PAD
+    pad = PAD if pad is None else int(pad)
+    padded = (counts + pad - 1) // pad * pad
     ends = np.cumsum(padded)
     need = (int(ends[-1]) + TOTAL_PAD - 1) // TOTAL_PAD * TOTAL_PAD
     B_pad = need if pad_total is None else int(pad_total)
@@ -64,10 +65,13 @@ class BatchPlan(object):
     """Node-sorted, padded slot layout of one batch.  With `static_hw` the plan owns fixed device
     buffers (worst-case slot count) that update() refreshes in place -- what a captured CUDA graph reads."""
 
-    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None):
+    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None, pad=None):
+        """pad: slots per node are a multiple of this; PAD (4) when backward will run (wgrad K blocks of 4 images
+        at the 4x4 layers must not mix two nodes), 1 for inference (shared M tiles are handled by row masks)"""
         self.num_node, self.device = num_node, device
         self.pad_total = pad_total
-        perm, ends, counts = plan_arrays(label_host, num_node, pad_total)
+        self.pad = PAD if pad is None else int(pad)
+        perm, ends, counts = plan_arrays(label_host, num_node, pad_total, self.pad)
         self.B, self.B_pad = int(np.asarray(label_host).size), int(perm.size)
         self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
         self.perm = torch.from_numpy(perm).to(device)
@@ -119,7 +123,7 @@ class BatchPlan(object):
 
     def update(self, label_host):
         """refresh the device buffers in place for a new batch of the same size"""
-        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad)
+        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad, self.pad)
         if int(np.asarray(label_host).size) != self.B:
             raise ValueError('Not valid batch size for this static plan')
         self._frozen = True
@@ -352,7 +356,7 @@ class CodecEngine(object):
         if plan is None:
             if label_host is None:
                 label_host = label.detach().cpu().numpy()      # the one host sync per forward
-            plan = BatchPlan(label_host, self.M, dev)
+            plan = BatchPlan(label_host, self.M, dev, pad=PAD if save_for_backward else 1)
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
@@ -542,7 +546,7 @@ class CodecEngine(object):
         T, Bn = int(bits.shape[0]), int(bits.shape[1])
         if label_host is None:
             label_host = label.detach().cpu().numpy()
-        plan = BatchPlan(label_host, self.M, dev)
+        plan = BatchPlan(label_host, self.M, dev, pad=1)
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0

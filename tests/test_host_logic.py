@@ -33,6 +33,21 @@ def test_batch_plan_sorts_pads_and_keeps_order():
     assert list(p.kb_end(16).numpy()) == [1, 1, 2, 4]           # wgrad K blocks of 64 pixels = 4 images at 4x4
 
 
+def test_inference_plan_packs_nodes_back_to_back():
+    """pad=1 (no backward): no per-node padding; tiles shared by neighbouring nodes are walked by both"""
+    label = np.array([2, 0, 2, 2, 0, 3, 2])
+    p = BatchPlan(label, 4, 'cpu', pad=1)
+    assert p.B_pad == 8 and list(p.group_img_end_host) == [2, 2, 6, 8]
+    assert list(p.perm_host) == [1, 4, 0, 2, 3, 6, 5, -1]
+    u, total = p.m_units(64, False)                              # 8x8 layer: 2 images per tile, all boundaries aligned
+    assert u.numpy().tolist() == [[0, 1, 1, 3], [1, 1, 3, 4], [1, 1, 3, 4]] and total == 4
+    u, total = p.m_units(16, False)                              # 4x4 layer: one tile holds all 8 slots, three nodes walk it
+    assert u.numpy().tolist() == [[0, 0, 0, 0], [1, 0, 1, 1], [1, 1, 2, 3]] and total == 3
+    q = BatchPlan(np.array([0, 1, 1]), 2, 'cpu', pad=1)          # odd boundary inside an 8x8 tile
+    u, total = q.m_units(64, False)
+    assert u.numpy().tolist() == [[0, 0], [1, 4], [1, 5]] and total == 5
+
+
 def test_batch_plan_rejects_bad_labels_like_the_reference():
     with pytest.raises(IndexError):
         BatchPlan(np.array([0, 4]), 4, 'cpu')
