@@ -193,8 +193,15 @@ def run_ours(args):
     B = args.batch
     # each rank codes its own shard of the global batch (samples are independent: no data-path collective)
     img_h, label_h = synth_batch(B, 1000 + rank)
+    from engine.dist import allreduce_gradients, owned_nodes, reduce_source_sharded
+    by_source = args.shard == 'source' and world > 1
+    if by_source:
+        # SURVEY 8(e) partitioning for M >= G: this rank holds the samples (and trains the encoders) of its own nodes
+        mine = owned_nodes(M_NODES, rank, world)
+        if not mine:
+            raise SystemExit('--shard source needs at least one node per rank ({} nodes, {} ranks)'.format(M_NODES, world))
+        label_h = torch.tensor(mine)[label_h % len(mine)]
     img, label = img_h.to(dev), label_h.to(dev)
-    from engine.dist import allreduce_gradients
     params = [p for p in model.parameters()]
     opt = torch.optim.Adam(params, lr=1e-3, fused=True) if train else None    # train_model.py:161
 
@@ -209,7 +216,10 @@ def run_ours(args):
             opt.zero_grad(set_to_none=True)
             out = model(inp)                                          # train_model.py:113
             out['loss'].backward()                                    # :115  (backward-through-time kernels)
-            allreduce_gradients(params, B, world * B)                 # replaces DataParallel's reduce (:60)
+            if by_source:
+                reduce_source_sharded(model, B, world * B, rank, world)   # joint decoder only
+            else:
+                allreduce_gradients(params, B, world * B)             # replaces DataParallel's reduce (:60)
             opt.step()                                                # :116
         else:
             with torch.no_grad():
@@ -311,7 +321,9 @@ def run_ours(args):
                    'global_batch': world * B, 'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8,
                    'precision': args.precision, 'cuda_graph': args.graph,
                    'cta_pair': 'cta_group::2 pairs on every gate / dgrad / wgrad GEMM (pair units formed inside each node)',
-                   'parallelism': ('dp{}: batch sharded, one NCCL all-reduce of gradients per step'.format(world) if train
+                   'parallelism': (('dp{}: sharded by source (rank r owns nodes r mod N), one NCCL all-reduce of the joint '
+                                    "decoder's gradients per step" if by_source else
+                                    'dp{}: batch sharded, one NCCL all-reduce of gradients per step').format(world) if train
                                    else 'batch-sharded replicas x{} (no collective)'.format(world)),
                    'l2': 'per-step working set (activations+state, ~1 MB/image) exceeds the 126 MB L2'},
         'e2e': {'value': world * B / e2e_ms * 1e3, 'unit': 'images/s',
@@ -398,6 +410,9 @@ def main():
     ap.add_argument('--graph', action='store_true',
                     help='replay one captured CUDA graph per step instead of launching eagerly (measured slower: the '
                          'loop is GPU-bound at >100 us per launch and a static graph needs worst-case node padding)')
+    ap.add_argument('--shard', default='batch', choices=['batch', 'source'],
+                    help="N>1 training: 'batch' = every rank sees all nodes, all gradients all-reduced; 'source' = rank r "
+                         "owns nodes j = r mod N and their samples, only the joint decoder's gradients are all-reduced")
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-fast', action='store_true', help='skip the secondary fast-precision measurement')
     args = ap.parse_args()

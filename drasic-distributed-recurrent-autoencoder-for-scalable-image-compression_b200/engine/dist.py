@@ -6,7 +6,15 @@ only exchange step of a training iteration is one all-reduce (sum) of the parame
 replacement of nn.DataParallel's per-step broadcast / scatter / gather / reduce_add
 (train_model.py:59-60,114).  The reference loss is a mean over the global batch (dist_codec.py:58), so a
 rank holding n_local of N_global samples contributes its mean-loss gradient with weight n_local/N_global.
-Evaluation needs no collective at all."""
+Evaluation needs no collective at all.
+
+With M >= world sources the batch can instead be sharded *by source* (`source_shard`): rank r holds every
+sample of the nodes j with j % world == r, so an encoder's gradient exists on exactly one rank and only the
+shared decoder's gradients (99 MB of the 326 MB at M=8) are all-reduced (`reduce_source_sharded`); the
+per-node parameters of the other ranks' nodes stay untouched locally and are refreshed from their owners
+before a checkpoint or an evaluation on the whole model (`sync_node_parameters`)."""
+import re
+
 import torch
 import torch.distributed as dist
 
@@ -60,3 +68,69 @@ def allreduce_scalar_mean(value, n_local, n_global, group=None):
     t = value.detach().clone() * (float(n_local) / float(n_global))
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+# ---------------------------------------------------------------- sharding by source
+def owned_nodes(num_node, rank, world):
+    """nodes whose encoder (and, for sep_codec, decoder) lives on this rank"""
+    return [j for j in range(num_node) if j % world == rank]
+
+
+def source_shard(label, rank, world):
+    """indices (ascending) of the samples whose node is owned by rank"""
+    return torch.nonzero(label % world == rank).reshape(-1)
+
+
+_NODE_KEY = re.compile(r'^(?:module\.)?model\.(encoder|decoder)\.(\d+)\.')
+
+
+def split_parameters(model):
+    """(shared, per_node): per_node[j] are the parameters only node j's samples touch -- its encoder
+    (model.encoder.{j}, dist_codec.py:50) and, where decoders are per node too (sep_codec.py:51), its decoder;
+    shared is everything else (dist_codec's joint decoder)."""
+    core = model.module if hasattr(model, 'module') else model
+    node_decoders = isinstance(core.model['decoder'], torch.nn.ModuleList)
+    shared, per_node = [], {}
+    for name, p in model.named_parameters():
+        m = _NODE_KEY.match(name)
+        if m and (m.group(1) == 'encoder' or node_decoders):
+            per_node.setdefault(int(m.group(2)), []).append(p)
+        else:
+            shared.append(p)
+    return shared, per_node
+
+
+def reduce_source_sharded(model, n_local, n_global, rank=None, world=None, group=None):
+    """Gradient exchange of a source-sharded step: all-reduce the shared parameters' gradients, weight the owned
+    nodes' gradients by n_local / N_global (the loss is a mean over the global batch), and leave the other
+    nodes' parameters without a gradient so the optimizer skips them.  Returns the number of collectives."""
+    if not dist.is_available() or not dist.is_initialized():
+        return 0
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    shared, per_node = split_parameters(model)
+    n = allreduce_gradients(shared, n_local, n_global, group=group)
+    w = float(n_local) / float(n_global)
+    for j, ps in per_node.items():
+        for p in ps:
+            if j % world != rank:
+                p.grad = None
+            elif p.grad is not None and world > 1:
+                p.grad.mul_(w)
+    return n
+
+
+def sync_node_parameters(model, group=None):
+    """broadcast every node's parameters from the rank that owns (trains) them"""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    world = dist.get_world_size(group)
+    _, per_node = split_parameters(model)
+    for j in sorted(per_node):
+        flat = torch.cat([p.data.reshape(-1) for p in per_node[j]])
+        dist.broadcast(flat, src=dist.get_global_rank(group, j % world) if group is not None else j % world, group=group)
+        off = 0
+        with torch.no_grad():
+            for p in per_node[j]:
+                p.copy_(flat[off:off + p.numel()].view_as(p))      # in place on the parameter: bumps its _version
+                off += p.numel()

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from engine.dist import allreduce_gradients, allreduce_scalar_mean, shard_range
+from engine.dist import (allreduce_gradients, allreduce_scalar_mean, owned_nodes, reduce_source_sharded, shard_range,
+                         source_shard, split_parameters, sync_node_parameters)
 
 
 def test_shard_range_covers_batch():
@@ -66,4 +67,87 @@ def test_weighted_gradient_allreduce_matches_single_process(n_local):
     with mp.Manager() as mgr:
         results = mgr.dict()
         mp.spawn(_worker, args=(world, port, n_local, results), nprocs=world, join=True)
+        assert results[0] and results[1]
+
+
+class _ToyCodec(torch.nn.Module):
+    """the reference's parameter tree in miniature: per-node encoders, a joint (or per-node) decoder"""
+
+    def __init__(self, num_node, node_decoders):
+        super().__init__()
+        enc = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(3, 4)) for _ in range(num_node)])
+        if node_decoders:
+            dec = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(4, 3)) for _ in range(num_node)])
+        else:
+            dec = torch.nn.Sequential(torch.nn.Linear(4, 3))
+        self.model = torch.nn.ModuleDict({'encoder': enc, 'decoder': dec})
+        self.node_decoders = node_decoders
+
+    def forward(self, x, label):
+        out = torch.zeros_like(x)
+        for j in range(len(self.model['encoder'])):
+            idx = torch.nonzero(label == j).reshape(-1)
+            if idx.numel() == 0:
+                continue
+            dec = self.model['decoder'][j] if self.node_decoders else self.model['decoder']
+            out = out.index_copy(0, idx, dec(torch.tanh(self.model['encoder'][j](x[idx]))))
+        return (out - x).abs().mean()
+
+
+def test_source_shard_helpers():
+    assert owned_nodes(8, 1, 4) == [1, 5] and owned_nodes(3, 2, 8) == [2] and owned_nodes(3, 5, 8) == []
+    label = torch.tensor([3, 0, 1, 2, 1, 0, 3])
+    assert source_shard(label, 1, 2).tolist() == [0, 2, 4, 6] and source_shard(label, 0, 2).tolist() == [1, 3, 5]
+    shared, per_node = split_parameters(_ToyCodec(3, False))
+    assert len(shared) == 2 and sorted(per_node) == [0, 1, 2] and all(len(v) == 2 for v in per_node.values())
+    shared, per_node = split_parameters(_ToyCodec(3, True))
+    assert shared == [] and all(len(v) == 4 for v in per_node.values())
+
+
+def _source_worker(rank, world, port, node_decoders, results):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        M = 5
+        torch.manual_seed(3)
+        m = _ToyCodec(M, node_decoders)
+        ref = _ToyCodec(M, node_decoders)
+        ref.load_state_dict(m.state_dict())
+        g = torch.Generator().manual_seed(4)
+        x_all = torch.randn(23, 3, generator=g)
+        lab_all = torch.randint(0, M, (23,), generator=g)
+        idx = source_shard(lab_all, rank, world)
+        loss = m(x_all[idx], lab_all[idx])
+        loss.backward()
+        n_coll = reduce_source_sharded(m, idx.numel(), 23)
+        ref(x_all, lab_all).backward()
+        ok = (n_coll >= 1) != node_decoders                      # sep_codec shares nothing: no collective
+        for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+            node = int(k.split('.')[2]) if (k.startswith('model.encoder') or node_decoders) else None
+            if node is None or node % world == rank:
+                ok = ok and torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-7)
+            else:
+                ok = ok and p.grad is None
+        # one SGD step on the owned / shared parameters, then the owners publish their nodes
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.grad is not None:
+                    p -= 0.1 * p.grad
+            for q in ref.parameters():
+                q -= 0.1 * q.grad
+        sync_node_parameters(m)
+        for p, q in zip(m.parameters(), ref.parameters()):
+            ok = ok and torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('node_decoders', [False, True])
+def test_source_sharded_step_matches_single_process(node_decoders):
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_source_worker, args=(world, port, node_decoders, results), nprocs=world, join=True)
         assert results[0] and results[1]
