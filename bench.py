@@ -302,12 +302,12 @@ def run_ours(args):
     mma_per_mac = 3 if args.precision == 'parity' else 1
     flop_per_img = FLOP_PER_IMG_FWD * (3 if train else 1)
     # DRAM bytes per gate-kernel launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full capture
-    # committed as profiles/r1_ncu_full_eval_parity_B1024_summary.csv: one iteration t >= 1 moves
-    # E1 826 + E2 408 + E3 163 + D1 305 + D2 1190 + D3 794 MB = 3686 MB over 6 launches
+    # committed as profiles/r1_ncu_full_gates_parity_final_summary.csv (eval forward, 1024 slots): one iteration t >= 1 moves
+    # E1 795 + E2 400 + E3 155 + D1 315 + D2 1192 + D3 763 MB = 3620 MB over 6 launches
     traffic, traffic_note = None, 'no ncu capture for this configuration'
     if args.precision == 'parity' and B == 1024:
-        traffic = 3686e6 / 6
-        traffic_note = ('forward gate kernels only, average per launch, from profiles/r1_ncu_full_eval_parity_B1024_summary.csv; '
+        traffic = 3620e6 / 6
+        traffic_note = ('forward gate kernels only, average per launch, from profiles/r1_ncu_full_gates_parity_final_summary.csv; '
                         'compulsory bytes of the same six launches: 3.1 GB (x, h hi+lo in; c in/out; h, consumer copy out; weights) -> 1.19x')
     sd = {k: v for k, v in model.named_parameters()}
     line = {
