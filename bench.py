@@ -308,7 +308,7 @@ def run_ours(args):
     if args.precision == 'parity' and B == 1024:
         traffic = 3620e6 / 6
         traffic_note = ('forward gate kernels only, average per launch, from profiles/r1_ncu_full_gates_parity_final_summary.csv; '
-                        'compulsory bytes of the same six launches: 3.1 GB (x, h hi+lo in; c in/out; h, consumer copy out; weights) -> 1.19x')
+                        'compulsory bytes of the same six launches: 3.1 GB (x, h hi+lo in; c in/out; h, consumer copy out; weights) -> 1.17x')
     sd = {k: v for k, v in model.named_parameters()}
     line = {
         'metric': METRIC, 'value': world * B / ms * 1e3, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,

@@ -24,75 +24,8 @@ __device__ __forceinline__ int find_group_b(const int* ends, int n_groups, int i
   return g;
 }
 
-// ------------------------------------------------------------------ LSTM pointwise backward
+// ------------------------------------------------------------------ LSTM cell backward -> scaled fp16 planes
 // forward (cell.py:133-139): i,f,o = sigmoid, g = tanh; c = f*c_prev + i*g; h = o*tanh(c)
-__global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdParams p) {
-  const int Co = p.Co;
-  const size_t n_vec = p.n_pix * Co / 8;
-  float amax = 0.0f;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < n_vec; v += stride) {
-    const size_t e0 = v * 8;
-    const size_t pix = e0 / Co;
-    const int ch = static_cast<int>(e0 - pix * Co);
-    auto ld8 = [](const float* src, float (&dst)[8]) {
-      const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
-      dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
-    };
-    float gi[8], gf[8], gg[8], go[8];
-    if (p.gates_f32) {
-      const float* gp = reinterpret_cast<const float*>(p.gates) + pix * (4 * Co) + ch;
-      ld8(gp, gi); ld8(gp + Co, gf); ld8(gp + 2 * Co, gg); ld8(gp + 3 * Co, go);
-    } else {
-      const __half* gp = reinterpret_cast<const __half*>(p.gates) + pix * (4 * Co) + ch;
-      auto ldh = [](const __half* src, float (&dst)[8]) {
-        alignas(16) __half t[8];
-        *reinterpret_cast<uint4*>(t) = *reinterpret_cast<const uint4*>(src);
-        for (int i = 0; i < 8; ++i) dst[i] = __half2float(t[i]);
-      };
-      ldh(gp, gi); ldh(gp + Co, gf); ldh(gp + 2 * Co, gg); ldh(gp + 3 * Co, go);
-    }
-    float ct[8], cp[8], dh[8], dcv[8];
-    ld8(p.c_t + e0, ct);
-    if (p.c_prev) ld8(p.c_prev + e0, cp);
-    else for (int i = 0; i < 8; ++i) cp[i] = 0.0f;
-    ld8(p.dh_above + e0, dh);
-    if (p.dh_rec) {
-      float r[8];
-      ld8(p.dh_rec + e0, r);
-      for (int i = 0; i < 8; ++i) dh[i] += r[i];
-    }
-    if (p.has_dc) ld8(p.dc + e0, dcv);
-    else for (int i = 0; i < 8; ++i) dcv[i] = 0.0f;
-    float di[8], df[8], dg[8], dob[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float ig = gi[i], fg = gf[i], cg = gg[i], og = go[i];
-      const float tc = tanhf(ct[i]);
-      const float dct = fmaf(dh[i] * og, 1.0f - tc * tc, dcv[i]);
-      dob[i] = dh[i] * tc * og * (1.0f - og);
-      di[i] = dct * cg * ig * (1.0f - ig);
-      df[i] = dct * cp[i] * fg * (1.0f - fg);
-      dg[i] = dct * ig * (1.0f - cg * cg);
-      dcv[i] = dct * fg;
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(di[i]), fabsf(df[i])), fmaxf(fabsf(dg[i]), fabsf(dob[i]))));
-    }
-    auto st8 = [](float* dst, const float (&src)[8]) {
-      reinterpret_cast<float4*>(dst)[0] = make_float4(src[0], src[1], src[2], src[3]);
-      reinterpret_cast<float4*>(dst)[1] = make_float4(src[4], src[5], src[6], src[7]);
-    };
-    float* dgp = p.dgates + pix * (4 * Co) + ch;
-    st8(dgp, di);
-    st8(dgp + Co, df);
-    st8(dgp + 2 * Co, dg);
-    st8(dgp + 3 * Co, dob);
-    st8(p.dc + e0, dcv);
-  }
-  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-  if ((threadIdx.x & 31) == 0 && amax > 0.0f) atomicMax(p.amax_bits, __float_as_uint(amax));
-}
-
-// ------------------------------------------------------------------ fused: cell backward -> scaled fp16 planes
 __device__ __forceinline__ int shift_for(float amax, int target_exp) {
   if (!(amax > 0.0f) || !isfinite(amax)) return 0;
   int e;
@@ -182,34 +115,6 @@ __global__ void __launch_bounds__(256, 3) lstm_bwd_fused_kernel(const LstmBwdFus
   if (!p.verify) {
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((threadIdx.x & 31) == 0 && amax > 0.0f) atomicMax(p.amax_bits, __float_as_uint(amax));
-  }
-}
-
-// ------------------------------------------------------------------ fp32 -> scaled fp16 planes
-__global__ void __launch_bounds__(256) convert_scale_kernel(const ConvertParams p) {
-  const float amax = __uint_as_float(*p.amax_bits);
-  int shift = 0;
-  if (amax > 0.0f && isfinite(amax)) {
-    int e;
-    frexpf(amax, &e);   // amax * 2^(14-e) in [2^13, 2^14): 4x head-room below the fp16 maximum
-    shift = 14 - e;
-  }
-  const float scale = ldexpf(1.0f, shift);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.inv_scale_out = ldexpf(1.0f, -shift);
-  const size_t n_vec = p.n / 8;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < n_vec; v += stride) {
-    const float4 a = reinterpret_cast<const float4*>(p.src)[2 * v], b = reinterpret_cast<const float4*>(p.src)[2 * v + 1];
-    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    alignas(16) __half h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float s = x[i] * scale;
-      h[i] = __float2half_rn(s);
-      l[i] = __float2half_rn(s - __half2float(h[i]));
-    }
-    reinterpret_cast<uint4*>(p.hi)[v] = *reinterpret_cast<const uint4*>(h);
-    if (p.lo) reinterpret_cast<uint4*>(p.lo)[v] = *reinterpret_cast<const uint4*>(l);
   }
 }
 
@@ -654,16 +559,8 @@ inline int grid_for(size_t work_items, int threads) {
 
 }  // namespace
 
-int launch_lstm_bwd(const LstmBwdParams& p, cudaStream_t stream) {
-  lstm_bwd_kernel<<<grid_for(p.n_pix * p.Co / 8, 256), 256, 0, stream>>>(p);
-  return static_cast<int>(cudaGetLastError());
-}
 int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream) {
   lstm_bwd_fused_kernel<<<grid_for(p.n_pix * p.Co / 8, 256), 256, 0, stream>>>(p);
-  return static_cast<int>(cudaGetLastError());
-}
-int launch_convert_scale(const ConvertParams& p, cudaStream_t stream) {
-  convert_scale_kernel<<<grid_for(p.n / 8, 256), 256, 0, stream>>>(p);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,

@@ -6,23 +6,7 @@
 
 namespace drasic {
 
-// LSTM cell pointwise backward (modules/cell.py:133-139 differentiated), one launch per (layer, t)
-struct LstmBwdParams {
-  const void* gates;       // [P, 4, Co] activated gates saved by the forward (fp16, or fp32 when gates_f32)
-  int gates_f32;
-  const float* c_t;        // [P, Co]
-  const float* c_prev;     // nullable (t == 0)
-  const float* dh_above;   // [P, Co] gradient from the consumer of h_t
-  const float* dh_rec;     // nullable (t == T-1): gradient from the hidden conv of step t+1
-  float* dc;               // [P, Co] in/out carry: dL/dc_t from step t+1 in, dL/dc_{t-1} out
-  int has_dc;              // 0 at t == T-1 (carry is zero)
-  float* dgates;           // [P, 4, Co] fp32 pre-activation gate gradients
-  unsigned int* amax_bits; // max |dgates| as float bits (atomicMax)
-  size_t n_pix;            // P = B_pad*H*W
-  int Co;
-};
-
-// Fused variant: cell backward that writes the scaled fp16 {hi, lo} operand planes of the dgrad / wgrad GEMMs
+// LSTM cell backward (modules/cell.py:133-139 differentiated), one launch per (layer, t): writes the scaled fp16 {hi, lo} operand planes of the dgrad / wgrad GEMMs
 // directly (no fp32 gate-gradient round trip).  The per-tensor power-of-two scale is *predicted* from the
 // amax of the previously processed iteration; the kernel also records the true amax.  A second launch
 // with verify != 0 re-does the tensor with the exact scale only if the prediction left the scaled amax
@@ -40,16 +24,6 @@ struct LstmBwdFusedParams {
   size_t n_pix; int Co; int verify;
 };
 
-// fp32 -> fp16 {hi, lo} planes with an exact power-of-two scale derived from amax
-struct ConvertParams {
-  const float* src;
-  __half* hi;
-  __half* lo;               // nullable
-  const unsigned int* amax_bits;
-  float* inv_scale_out;     // device scalar: 1/scale
-  size_t n;
-};
-
 struct WgradParams {
   CUtensorMap tm_g[2];      // dG planes [B,H,W,4Co] fp16 {hi, lo}, box = 64 ch x 64 pixels
   CUtensorMap tm_x[2];      // layer input planes [B,H,W,Cin], same pixel box (shifted by the tap)
@@ -63,7 +37,7 @@ struct WgradParams {
   int has_h;                // 0 at t == 0
   int n_groups, m_tiles, n_tiles_x, n_tiles_h, k_splits;
   int wide;                 // CTA pairs only: 512-column tiles (n_tiles_* count units of 8 instead of 4)
-  int dbg;                  // diagnostics only (env DRASIC_WGRAD_DBG): 1 = skip the TMA loads, 2 = skip the MMAs
+  int dbg;                  // -DDRASIC_DIAG builds only (env DRASIC_WGRAD_DBG): 1 = skip the TMA loads, 2 = skip the MMAs
 };
 
 struct BottleneckBwdParams {
@@ -111,8 +85,6 @@ struct HeadBwdParams {
   int B_pad, C, H, W, first, propagate, n_enc_groups;
 };
 
-int launch_lstm_bwd(const LstmBwdParams& p, cudaStream_t stream);
-int launch_convert_scale(const ConvertParams& p, cudaStream_t stream);
 int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream);
 int launch_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
                               int out_order, __half* out_hi, __half* out_lo, float* inv_scale_out,

@@ -287,18 +287,6 @@ int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream) {
 }
 
 
-int drasic_lstm_bwd_pointwise(const void* gates, int gates_f32, const float* c_t, const float* c_prev,
-                              const float* dh_above, const float* dh_rec, float* dc, int has_dc,
-                              float* dgates, void* amax_bits, size_t n_pix, int Co, void* stream) {
-  if (!gates || !c_t || !dh_above || !dc || !dgates || !amax_bits || Co % 8 || n_pix == 0)
-    return fail(DRASIC_ERR_INVALID, "lstm_bwd_pointwise: bad argument");
-  drasic::LstmBwdParams p;
-  p.gates = gates; p.gates_f32 = gates_f32; p.c_t = c_t; p.c_prev = c_prev; p.dh_above = dh_above;
-  p.dh_rec = dh_rec; p.dc = dc; p.has_dc = has_dc; p.dgates = dgates;
-  p.amax_bits = static_cast<unsigned int*>(amax_bits); p.n_pix = n_pix; p.Co = Co;
-  return cuda_fail(drasic::launch_lstm_bwd(p, static_cast<cudaStream_t>(stream)), "lstm_bwd_pointwise launch");
-}
-
 int drasic_lstm_bwd_fused(const drasic_lstm_bwd_fused_args* a, void* stream) {
   if (!a || !a->gates || !a->c_t || !a->dh_above || !a->dc_out || !a->dg_hi || !a->prev_amax_bits || !a->amax_bits ||
       !a->inv_scale_out || a->Co % 8 || a->n_pix == 0 || a->dc_in == a->dc_out)
@@ -311,16 +299,6 @@ int drasic_lstm_bwd_fused(const drasic_lstm_bwd_fused_args* a, void* stream) {
   p.amax_bits = static_cast<unsigned int*>(a->amax_bits); p.inv_scale_out = a->inv_scale_out;
   p.n_pix = a->n_pix; p.Co = a->Co; p.verify = a->verify;
   return cuda_fail(drasic::launch_lstm_bwd_fused(p, static_cast<cudaStream_t>(stream)), "lstm_bwd_fused launch");
-}
-
-int drasic_convert_scale(const float* src, void* hi, void* lo, const void* amax_bits,
-                         float* inv_scale_out, size_t n, void* stream) {
-  if (!src || !hi || !amax_bits || !inv_scale_out || n == 0 || n % 8)
-    return fail(DRASIC_ERR_INVALID, "convert_scale: bad argument");
-  drasic::ConvertParams p;
-  p.src = src; p.hi = static_cast<__half*>(hi); p.lo = static_cast<__half*>(lo);
-  p.amax_bits = static_cast<const unsigned int*>(amax_bits); p.inv_scale_out = inv_scale_out; p.n = n;
-  return cuda_fail(drasic::launch_convert_scale(p, static_cast<cudaStream_t>(stream)), "convert_scale launch");
 }
 
 int drasic_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
@@ -409,8 +387,12 @@ int drasic_convlstm_bwd_weight(const drasic_wgrad_args* a, void* stream) {
   const int upt = p.wide ? 8 : 4;
   p.n_tiles_x = (9 * (Cin / 64) + upt - 1) / upt; p.n_tiles_h = (9 * (Co / 64) + upt - 1) / upt; p.k_splits = a->k_splits;
   {
+#ifdef DRASIC_DIAG
     static const int dbg = getenv("DRASIC_WGRAD_DBG") ? atoi(getenv("DRASIC_WGRAD_DBG")) : 0;
     p.dbg = dbg;
+#else
+    p.dbg = 0;
+#endif
   }
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");

@@ -17,6 +17,14 @@
 #include "backward.h"
 #include "ptx.cuh"
 
+// Diagnostic switches (skip the TMA loads / the MMAs ...; results are then wrong by construction) exist only in
+// -DDRASIC_DIAG builds; the shipped library compiles them out.
+#ifdef DRASIC_DIAG
+#define WG_DBG(p) ((p).dbg)
+#else
+#define WG_DBG(p) 0
+#endif
+
 namespace drasic {
 
 namespace {
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           }
           int tap = unit / cpu;
           u_chunk[uu] = unit - tap * cpu;
-          if (p.dbg == 5) tap = 4;
+          if (WG_DBG(p) == 5) tap = 4;
           u_dx[uu] = tap % 3 - 1;
           u_dy[uu] = tap / 3 - 1;
         }
@@ -193,24 +201,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         }
         for (int kb = t.kb_lo; kb < t.kb_hi; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (p.dbg == 1) {
+          if (WG_DBG(p) == 1) {
             ptx::mbar_arrive(&full_bar[stage]);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
           uint32_t xbytes = bytes;   // diagnostics: 3 = no A loads, 4 = no B loads, 5 = centre tap only
-          if (p.dbg == 3) xbytes = (SPLIT ? 2 : 1) * (my_units * BOX_BYTES);
-          if (p.dbg == 4) xbytes = (SPLIT ? 2 : 1) * C::A_BYTES;
+          if (WG_DBG(p) == 3) xbytes = (SPLIT ? 2 : 1) * (my_units * BOX_BYTES);
+          if (WG_DBG(p) == 4) xbytes = (SPLIT ? 2 : 1) * C::A_BYTES;
           if (!PAIR) ptx::mbar_expect_tx(&full_bar[stage], xbytes);
           else if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * xbytes);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
             uint8_t* sa = st + pl * C::A_BYTES;
             uint8_t* sb = st + (SPLIT ? 2 : 1) * C::A_BYTES + pl * C::B_BYTES;
-            if (p.dbg == 3) {
+            if (WG_DBG(p) == 3) {
             } else if (PAIR) ptx::tma_load_5d_pair(sa, &p.tm_g[pl], (full_remote0 + 8u * stage), 0, x0, y0, n0, mt * 2);
             else ptx::tma_load_5d(sa, &p.tm_g[pl], &full_bar[stage], 0, x0, y0, n0, mt * 2);
-            if (p.dbg == 4) continue;
+            if (WG_DBG(p) == 4) continue;
 #pragma unroll
             for (int uu = 0; uu < C::UNITS / 2; ++uu) {   // a pair of 64-channel chunks of the same tap
               if (2 * uu >= my_units) break;
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           ptx::tc_fence_after();
           // descriptors differ from the stage-0 / k-0 ones only in the 14-bit start-address field
           const uint32_t st_off = static_cast<uint32_t>(stage) * (C::STAGE_BYTES >> 4);
-          if (p.dbg < 2)
+          if (WG_DBG(p) < 2)
 #pragma unroll
           for (int grp = 0; grp < (WIDE ? 2 : 1); ++grp) {
             if (grp == 1 && cnt1 == 0) break;

@@ -81,7 +81,7 @@ DX_SAME, DX_INV_DOWN, DX_INV_UP = 0, 1, 2
 # every symbol include/drasic_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes',
            'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
-           'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_pointwise', 'drasic_convert_scale', 'drasic_lstm_bwd_fused',
+           'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_fused',
            'drasic_pack_dgrad_weights', 'drasic_convlstm_bwd_data', 'drasic_convlstm_bwd_weight',
            'drasic_unpack_wgrad', 'drasic_bottleneck_bwd', 'drasic_tail_bwd', 'drasic_head_bwd')
 
@@ -117,10 +117,6 @@ def lib():
     L.drasic_conv1x1_fwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, vp]
     L.drasic_quantize_fwd.restype = C.c_int
     L.drasic_quantize_fwd.argtypes = [vp, vp, vp, C.c_size_t, vp]
-    L.drasic_lstm_bwd_pointwise.restype = C.c_int
-    L.drasic_lstm_bwd_pointwise.argtypes = [vp, ip, vp, vp, vp, vp, vp, ip, vp, vp, C.c_size_t, ip, vp]
-    L.drasic_convert_scale.restype = C.c_int
-    L.drasic_convert_scale.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, vp]
     L.drasic_lstm_bwd_fused.restype = C.c_int
     L.drasic_lstm_bwd_fused.argtypes = [C.POINTER(LstmBwdFusedArgs), vp]
     L.drasic_pack_dgrad_weights.restype = C.c_int

@@ -139,18 +139,12 @@ int drasic_tail_head_fwd(const drasic_tail_head_args* a, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * Backward-through-time: what autograd executes for `output['loss'].backward()` (train_model.py:115)
  * over the loop of models/dist_codec.py:36-65.  Gradients travel as fp32; the tensor-core GEMMs read
- * them as fp16 {hi,lo} planes scaled by an exact per-tensor power of two (drasic_convert_scale).
+ * them as fp16 {hi,lo} planes scaled by an exact per-tensor power of two (drasic_lstm_bwd_fused).
  */
 enum { DRASIC_DX_SAME = 0, DRASIC_DX_INV_DOWN = 1, DRASIC_DX_INV_UP = 2 };
 
-/* LSTM cell pointwise backward (modules/cell.py:133-139 differentiated): dgates fp32 [P,4,Co],
- * dc carry in/out, running max|dgates| (float bits, atomicMax; clear before the launch). */
-int drasic_lstm_bwd_pointwise(const void* gates, int gates_f32, const float* c_t, const float* c_prev,
-                              const float* dh_above, const float* dh_rec, float* dc, int has_dc,
-                              float* dgates, void* amax_bits, size_t n_pix, int Co, void* stream);
-
-/* The two calls above fused (no fp32 gate-gradient round trip): cell backward writing the scaled fp16
- * {hi,lo} planes directly.  The power-of-two scale is predicted from *prev_amax_bits (the amax of the
+/* LSTM cell pointwise backward (modules/cell.py:133-139 differentiated) writing the scaled fp16 {hi,lo}
+ * gate-gradient planes directly (no fp32 round trip); dc carry in/out.  The power-of-two scale is predicted from *prev_amax_bits (the amax of the
  * previously processed iteration; 0 = unknown); the true amax is recorded in *amax_bits (must be zero
  * before the first call).  Call once with verify = 0, then once with verify = 1: the second call returns
  * immediately unless the prediction left the scaled amax outside [2^4, 2^15.9], in which case it redoes
@@ -164,10 +158,6 @@ typedef struct {
 } drasic_lstm_bwd_fused_args;
 int drasic_lstm_bwd_fused(const drasic_lstm_bwd_fused_args* a, void* stream);
 
-/* fp32 -> fp16 {hi,lo} planes scaled by 2^k so that amax lands in [2^13, 2^14); writes 2^-k. n % 8 == 0 */
-int drasic_convert_scale(const float* src, void* hi, void* lo, const void* amax_bits,
-                         float* inv_scale_out, size_t n, void* stream);
-
 /* conv-transpose weights of one cell for the dgrad GEMM: rows = Cin+Co input channels (physical
  * order), K = 9 taps (flipped) x 4Co gate channels.  Planes of (Cin+Co)*36*Co fp16 each. */
 int drasic_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
@@ -180,7 +170,7 @@ typedef struct {
   const void* dg_hi; const void* dg_lo;   /* [B_pad,H,W,4Co] fp16 planes of the gate gradients */
   const void* w_hi; const void* w_lo;     /* from drasic_pack_dgrad_weights, n_groups consecutive cells */
   const float* w_inv_scale;               /* [n_groups] */
-  const float* dg_inv_scale;              /* device scalar from drasic_convert_scale */
+  const float* dg_inv_scale;              /* device scalar from drasic_lstm_bwd_fused */
   float* dx_out;                          /* fp32, layout per dx_mode */
   float* dhrec_out;                       /* nullable: fp32 [B_pad,H,W,Co] gradient w.r.t. h_{t-1} */
   const int* group_mtile_end;
