@@ -203,7 +203,8 @@ def run_ours(args):
         label_h = torch.tensor(mine)[label_h % len(mine)]
     img, label = img_h.to(dev), label_h.to(dev)
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True) if train else None    # train_model.py:161
+    from engine.optim import FusedAdam
+    opt = FusedAdam(params, lr=1e-3) if train else None               # train_model.py:161 (optim.Adam)
 
     def barrier():
         if world > 1:
@@ -240,7 +241,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     eng = model._engine
-    launches = eng.launches
+    launches = eng.launches + (opt.launches if train else 0)
     clocks = sampler.stop() if sampler else None
 
     # ---- per-kernel timing on the launching stream (separate eager pass, CUDA events around every launch)
@@ -329,7 +330,7 @@ def run_ours(args):
         'e2e': {'value': world * B / e2e_ms * 1e3, 'unit': 'images/s',
                 'h2d_bytes_per_step': B * CHANNELS * 32 * 32 * 4 + B * 8,
                 'd2h_bytes_per_step': T_ITER * B * 128 * 4 + 4 + B * 8,
-                'api': 'models.dist_codec() Model.forward (+ loss.backward(), Adam step when training) on pinned host '
+                'api': 'models.dist_codec() Model.forward (+ loss.backward(), engine.optim.FusedAdam step when training) on pinned host '
                        'img/label; loss.item() and the emitted codes read back'},
         'gpu_launches': launches * args.steps,
         'clocks': clocks,

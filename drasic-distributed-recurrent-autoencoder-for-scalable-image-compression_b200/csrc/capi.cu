@@ -9,6 +9,7 @@
 #include "kernels.h"
 #include "pointwise.h"
 #include "backward.h"
+#include "optim.h"
 
 namespace {
 
@@ -459,6 +460,28 @@ int drasic_quantize_fwd(const float* x, const float* u, float* y, size_t n, void
   if (!x || !y) return fail(DRASIC_ERR_INVALID, "quantize_fwd: null pointer");
   if (n == 0) return 0;
   return cuda_fail(drasic::launch_quantize(x, u, y, n, static_cast<cudaStream_t>(stream)), "quantize_fwd launch");
+}
+
+int drasic_adam_step(const drasic_adam_tensor* tensors, int n_tensors, double lr, double beta1, double beta2,
+                     double eps, double weight_decay, double bias_correction1, double bias_correction2,
+                     void* stream) {
+  static_assert(sizeof(drasic_adam_tensor) == sizeof(drasic::AdamTensor), "ABI / kernel struct mismatch");
+  if (n_tensors < 0 || (n_tensors > 0 && !tensors)) return fail(DRASIC_ERR_INVALID, "adam_step: null tensor list");
+  if (!(lr >= 0.0) || !(eps >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) ||
+      !(weight_decay >= 0.0))
+    return fail(DRASIC_ERR_INVALID, "adam_step: lr=%g betas=(%g, %g) eps=%g weight_decay=%g", lr, beta1, beta2, eps, weight_decay);
+  if (!(bias_correction1 > 0.0) || !(bias_correction2 > 0.0))
+    return fail(DRASIC_ERR_INVALID, "adam_step: bias corrections must be positive (step >= 1)");
+  for (int i = 0; i < n_tensors; ++i) {
+    const drasic_adam_tensor& t = tensors[i];
+    if (t.numel < 0 || (t.numel > 0 && (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq)))
+      return fail(DRASIC_ERR_INVALID, "adam_step: tensor %d has a null pointer", i);
+  }
+  drasic::AdamHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
+  h.bias_correction1 = bias_correction1; h.bias_correction2 = bias_correction2;
+  return cuda_fail(drasic::launch_adam(reinterpret_cast<const drasic::AdamTensor*>(tensors), n_tensors, h,
+                                       static_cast<cudaStream_t>(stream)), "adam_step launch");
 }
 
 }  // extern "C"

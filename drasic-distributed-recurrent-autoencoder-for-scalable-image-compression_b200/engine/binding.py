@@ -76,6 +76,10 @@ class HeadBwdArgs(C.Structure):
                [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'propagate', 'n_enc_groups')]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [('param', vp), ('grad', vp), ('exp_avg', vp), ('exp_avg_sq', vp), ('numel', C.c_longlong)]
+
+
 DX_SAME, DX_INV_DOWN, DX_INV_UP = 0, 1, 2
 
 # every symbol include/drasic_b200.h declares (tests check the library exports all of them)
@@ -83,7 +87,7 @@ SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_p
            'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
            'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_fused',
            'drasic_pack_dgrad_weights', 'drasic_convlstm_bwd_data', 'drasic_convlstm_bwd_weight',
-           'drasic_unpack_wgrad', 'drasic_bottleneck_bwd', 'drasic_tail_bwd', 'drasic_head_bwd')
+           'drasic_unpack_wgrad', 'drasic_bottleneck_bwd', 'drasic_tail_bwd', 'drasic_head_bwd', 'drasic_adam_step')
 
 _lib = None
 
@@ -133,6 +137,9 @@ def lib():
     L.drasic_tail_bwd.argtypes = [C.POINTER(TailBwdArgs), vp]
     L.drasic_head_bwd.restype = C.c_int
     L.drasic_head_bwd.argtypes = [C.POINTER(HeadBwdArgs), vp]
+    L.drasic_adam_step.restype = C.c_int
+    L.drasic_adam_step.argtypes = [C.POINTER(AdamTensor), ip, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_double, C.c_double, vp]
     _lib = L
     return L
 

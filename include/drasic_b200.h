@@ -227,6 +227,22 @@ typedef struct {
 int drasic_head_bwd(const drasic_head_bwd_args* a, void* stream);
 
 /*
+ * Optimizer step (train_model.py:116 `optimizer.step()` on the optim.Adam of train_model.py:155-161): Adam with
+ * L2 weight decay folded into the gradient, no amsgrad, over any number of fp32 tensors in ceil(n/64) launches.
+ * `tensors` is a HOST array (the device pointers travel as kernel arguments); param / exp_avg / exp_avg_sq are
+ * updated in place.  bias_correction{1,2} = 1 - beta{1,2}^step for the step being taken (computed by the caller
+ * in double, like torch; the hyper-parameters are doubles for the same reason: 1 - beta is formed in double and
+ * rounded to fp32 once).  All tensors of one call share the step count.
+ */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  long long numel;
+} drasic_adam_tensor;
+int drasic_adam_step(const drasic_adam_tensor* tensors, int n_tensors, double lr, double beta1, double beta2,
+                     double eps, double weight_decay, double bias_correction1, double bias_correction2,
+                     void* stream);
+
+/*
  * Stand-alone cells (called outside the fused loop; NCHW fp32 like the reference).
  * drasic_conv1x1_fwd: ConvCell.forward with kernel_size 1 (modules/cell.py:69-72): y = act(w*x + b);
  *   x [N,Cin,HW], w [Cout,Cin], b nullable [Cout], y [N,Cout,HW].

@@ -26,7 +26,8 @@ model = models.dist_codec().cuda()
 model.train(True)
 g = torch.Generator().manual_seed(1)
 inp = {'img': torch.rand(B, 3, 32, 32, generator=g).cuda(), 'label': torch.randint(0, 8, (B,), generator=g).cuda()}
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+from engine.optim import FusedAdam
+opt = FusedAdam(model.parameters(), lr=1e-3)
 
 
 def step():

@@ -25,7 +25,8 @@ import data
 import metrics
 torch.manual_seed(0)
 model = models.dist_codec().cuda()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+from engine.optim import FusedAdam
+opt = FusedAdam(model.parameters(), lr=1e-3)
 loader = data.make_data_loader(data.fetch_dataset('CIFAR10', 'label'))
 model.train(True)
 first = last = None

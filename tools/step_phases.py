@@ -25,7 +25,8 @@ g = torch.Generator().manual_seed(1)
 inp = {'img': torch.rand(B, 3, 32, 32, generator=g).cuda(), 'label': torch.randint(0, 8, (B,), generator=g)}
 if len(sys.argv) <= 2 or sys.argv[2] != 'cpu_label':
     inp['label'] = inp['label'].cuda()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+from engine.optim import FusedAdam
+opt = FusedAdam(model.parameters(), lr=1e-3)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
 
