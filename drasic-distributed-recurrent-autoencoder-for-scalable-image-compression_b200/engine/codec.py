@@ -65,23 +65,42 @@ class BatchPlan(object):
     """Node-sorted, padded slot layout of one batch.  With `static_hw` the plan owns fixed device
     buffers (worst-case slot count) that update() refreshes in place -- what a captured CUDA graph reads."""
 
-    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None, pad=None):
+    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None, pad=None, hws=None):
         """pad: slots per node are a multiple of this; PAD (4) when backward will run (wgrad K blocks of 4 images
-        at the 4x4 layers must not mix two nodes), 1 for inference (shared M tiles are handled by row masks)"""
+        at the 4x4 layers must not mix two nodes), 1 for inference (shared M tiles are handled by row masks).
+        hws: pixels per image of the layers that will read this plan; their unit / K-block tables travel to the
+        device together with perm and the node ends in ONE asynchronous copy from pinned memory (a table asked for
+        later costs a synchronising copy of its own)."""
         self.num_node, self.device = num_node, device
         self.pad_total = pad_total
         self.pad = PAD if pad is None else int(pad)
         perm, ends, counts = plan_arrays(label_host, num_node, pad_total, self.pad)
         self.B, self.B_pad = int(np.asarray(label_host).size), int(perm.size)
         self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
-        self.perm = torch.from_numpy(perm).to(device)
-        self.group_img_end = torch.from_numpy(ends).to(device)
         self._kb_end, self._units = {}, {}
         self.static = static_hw is not None
-        for hw in static_hw or ():
-            self.kb_end(hw)
+        pre = tuple(dict.fromkeys(static_hw if static_hw is not None else (hws or ())))
+        parts = [perm, ends]
+        for hw in pre:
+            parts.append(self._kb_host(hw))
+            parts.extend(self._units_host(hw, pair).reshape(-1) for pair in (False, True))
+        flat = np.concatenate(parts).astype(np.int32, copy=False)
+        on_gpu = torch.device(device).type == 'cuda'
+        host = torch.empty(flat.size, dtype=torch.int32, pin_memory=on_gpu)
+        host.numpy()[:] = flat
+        buf = host.to(device, non_blocking=True) if on_gpu else host
+        M, off = num_node, 0
+
+        def take(n):
+            nonlocal off
+            off += n
+            return buf[off - n:off]
+        self.perm = take(perm.size)
+        self.group_img_end = take(M)
+        for hw in pre:
+            self._kb_end[hw] = take(M)
             for pair in (False, True):
-                self.m_units(hw, pair)
+                self._units[(hw, pair)] = take(3 * M).view(3, M)
 
     def kb_end(self, hw):
         """exclusive end K block (64 pixels) of each node, for the wgrad GEMM (node ranges are multiples of 4
@@ -356,7 +375,8 @@ class CodecEngine(object):
         if plan is None:
             if label_host is None:
                 label_host = label.detach().cpu().numpy()      # the one host sync per forward
-            plan = BatchPlan(label_host, self.M, dev, pad=PAD if save_for_backward else 1)
+            plan = BatchPlan(label_host, self.M, dev, pad=PAD if save_for_backward else 1,
+                             hws=((H // 2) * (W // 2), (H // 4) * (W // 4), (H // 8) * (W // 8)))
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
@@ -546,7 +566,7 @@ class CodecEngine(object):
         T, Bn = int(bits.shape[0]), int(bits.shape[1])
         if label_host is None:
             label_host = label.detach().cpu().numpy()
-        plan = BatchPlan(label_host, self.M, dev, pad=1)
+        plan = BatchPlan(label_host, self.M, dev, pad=1, hws=(hc * wc * 16, hc * wc * 4, hc * wc))
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
@@ -864,7 +884,7 @@ class CodecEngine(object):
             grads[pref + '.0.cell.cell.main.weight'] = dw_d0[j].reshape(sd[pref + '.0.cell.cell.main.weight'].shape)
             grads[pref + '.7.cell.cell.main.weight'] = dw_d4[j].reshape(sd[pref + '.7.cell.cell.main.weight'].shape)
         if g_loss is not None:
-            grads = {k: v * g_loss for k, v in grads.items()}
+            torch._foreach_mul_(list(grads.values()), g_loss)      # chain rule for d(anything)/d(loss), in place
         return grads
 
     @staticmethod

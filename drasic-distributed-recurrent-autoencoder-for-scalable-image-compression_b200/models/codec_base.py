@@ -1,6 +1,8 @@
 """Shared implementation of the two codec Models (reference models/dist_codec.py:10-65 and
 models/sep_codec.py:10-66): the architecture spec builders and the fused forward that hands the whole
 T-iteration residual loop to engine.CodecEngine."""
+from collections.abc import Sequence
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -9,7 +11,6 @@ import torch.nn.functional as F
 import config
 from engine.codec import CodecEngine, GraphedCodec
 from modules.cell import ConvCell, ConvLSTMCell, PixelShuffleCell
-from utils import apply_fn
 from .utils import make_model
 
 
@@ -49,6 +50,34 @@ _DEC_KINDS = (ConvCell, ConvLSTMCell, PixelShuffleCell, ConvLSTMCell, PixelShuff
               PixelShuffleCell, ConvCell)
 
 
+class CodeList(Sequence):
+    """output['code'] of the reference (dist_codec.py:42,61-63): a list of T cumulative packed-code arrays.  The
+    reference fills it with one device->host copy per iteration; here the arrays are built from ONE copy at the
+    first access (len() needs none), so a training step that never looks at them -- only metrics.BPP does,
+    metrics.py:84-89 -- has no host synchronisation between its forward and its backward."""
+
+    def __init__(self, n, make):
+        self._n, self._make, self._items = n, make, None
+
+    def _get(self):
+        if self._items is None:
+            self._items = self._make()
+            self._make = None
+        return self._items
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __repr__(self):
+        return 'CodeList({})'.format('pending' if self._items is None else repr(self._items))
+
+
 class _LoopFunction(torch.autograd.Function):
     """The whole T-iteration loop as one autograd node: forward launches the fused kernels, backward
     (backward-through-time) is provided by the engine when it has been built with training support."""
@@ -56,7 +85,7 @@ class _LoopFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, img, label, noise, *params):
         ctx.model = model
-        ctx.names = [k for k, _ in model.named_parameters()]
+        ctx.names = model._index()[0]
         if config.PARAM.get('cuda_graph', False) and config.PARAM.get('node_iters') is None:
             # one graph holds forward AND backward-through-time; backward() only hands the gradients out
             out, ctx.grads = model._run_graphed(img, label, noise, with_backward=True)
@@ -85,6 +114,30 @@ class CodecModel(nn.Module):
         self.model = make_model(config.PARAM['model'])
         self._engine = None
         self._engine_key = None
+        self._tree = None
+
+    def _index(self):
+        """(parameter names, parameters, modules with free_hidden) of the module tree, walked once: the tree has
+        ~1800 modules and three walks per step cost more host time than issuing a small batch's kernels.  The
+        Parameter objects survive .to() / load_state_dict(); both drop the index anyway."""
+        if self._tree is None:
+            named = list(self.named_parameters())
+            cells = [m for m in self.modules() if m is not self and hasattr(m, 'free_hidden')]
+            self._tree = ([k for k, _ in named], [p for _, p in named], cells)
+        return self._tree
+
+    def _apply(self, fn, *args, **kwargs):
+        self._tree = None
+        return super(CodecModel, self)._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._tree = None
+        return super(CodecModel, self).load_state_dict(*args, **kwargs)
+
+    def _free_hidden(self):
+        """apply_fn(self, 'free_hidden') (dist_codec.py:64) over the indexed cells"""
+        for m in self._index()[2]:
+            m.free_hidden()
 
     # ---- reference API -------------------------------------------------------------------------
     def pack(self, code):
@@ -144,7 +197,7 @@ class CodecModel(nn.Module):
         key = (tuple(img.shape), config.PARAM['num_iter'], self.training, with_backward, config.PARAM['loss_fn'])
         g = self._graphs.get(key)
         if g is None:
-            sd = {k: v for k, v in self.named_parameters()}
+            sd = dict(zip(*self._index()[:2]))
             g = GraphedCodec(self._engine, sd, img.shape[0], tuple(img.shape[2:]), config.PARAM['num_iter'],
                              training=self.training, with_backward=with_backward, loss_kind=config.PARAM['loss_fn'])
             self._graphs[key] = g
@@ -152,7 +205,7 @@ class CodecModel(nn.Module):
 
     def _run_engine(self, img, label, noise, save_for_backward=False):
         self._ensure_engine()
-        sd = {k: v for k, v in self.named_parameters()}
+        sd = dict(zip(*self._index()[:2]))
         return self._engine.forward(sd, img, label, config.PARAM['num_iter'], training=self.training,
                                     noise=noise, loss_kind=config.PARAM['loss_fn'],
                                     save_for_backward=save_for_backward, node_iters=config.PARAM.get('node_iters'))
@@ -177,17 +230,17 @@ class CodecModel(nn.Module):
                 res = self._run_engine(input['img'], input['label'], None)
         finally:
             self.train(was_training)
-            apply_fn(self, 'free_hidden')
+            self._free_hidden()
         return {'bits': res['bits'], 'size': tuple(input['img'].shape[2:]), 'label': input['label']}
 
     def decode(self, bits, label, size=(32, 32)):
         """Decoder-only reconstruction from a bitstream prefix bits[:t] (t <= T): list of t cumulative
         reconstructions, bit-identical to forward()['img'][:t] for the same weights."""
         self._ensure_engine()
-        sd = {k: v for k, v in self.named_parameters()}
+        sd = dict(zip(*self._index()[:2]))
         with torch.no_grad():
             res = self._engine.decode(sd, bits, label, tuple(size))
-        apply_fn(self, 'free_hidden')
+        self._free_hidden()
         return [res['recon'][t] for t in range(res['recon'].shape[0])]
 
     @staticmethod
@@ -205,7 +258,7 @@ class CodecModel(nn.Module):
         if config.PARAM['loss_fn'] not in ('bce', 'mse', 'mae'):
             raise ValueError('Not valid loss function')
         img, label = input['img'], input['label']
-        params = [p for p in self.parameters()]
+        params = self._index()[1]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         mse = None
         use_graph = config.PARAM.get('cuda_graph', False) and config.PARAM.get('node_iters') is None
@@ -220,16 +273,23 @@ class CodecModel(nn.Module):
             recon, codes, bits = res['recon'], res['codes'], res['bits']
             mse = (res['loss_acc'][:, 1] / float(img.numel())).float()   # per-iteration MSE, stays on the device
         T = recon.shape[0]
-        output = {'loss': loss, 'img': [recon[t] for t in range(T)], 'code': [], 'code_pm1': codes, 'bits': bits}
+        output = {'loss': loss, 'img': [recon[t] for t in range(T)], 'code_pm1': codes, 'bits': bits}
         if mse is not None:
             output['mse'] = mse                                     # metrics.psnr_per_iteration(output)
         if config.PARAM.get('pack_mode', 'reference') == 'bits':
-            b = bits.cpu().numpy()                                  # one D2H per forward
-            output['code'] = [np.ascontiguousarray(b[:t + 1].transpose(1, 2, 0).reshape(-1, t + 1)) for t in range(T)]
+            def make():
+                b = bits.cpu().numpy()                              # one D2H per forward
+                return [np.ascontiguousarray(b[:t + 1].transpose(1, 2, 0).reshape(-1, t + 1)) for t in range(T)]
         else:
-            c = codes.detach().cpu().numpy().astype(np.int8)        # one D2H per forward (reference: one per iteration)
-            per_iter = [np.packbits(c[t]).reshape(-1, 1) for t in range(T)]
-            for t in range(T):
-                output['code'].append(per_iter[t] if t == 0 else np.concatenate((output['code'][t - 1], per_iter[t]), axis=1))
-        apply_fn(self, 'free_hidden')                               # dist_codec.py:64
+            def make():
+                c = codes.detach().cpu().numpy().astype(np.int8)    # one D2H per forward (reference: one per iteration)
+                per_iter = [np.packbits(c[t]).reshape(-1, 1) for t in range(T)]
+                out = []
+                for t in range(T):
+                    out.append(per_iter[t] if t == 0 else np.concatenate((out[t - 1], per_iter[t]), axis=1))
+                return out
+        output['code'] = CodeList(T, make)                          # materialised at the first access
+        if use_graph:
+            output['code']._get()                                   # a graph's output buffers are rewritten by its next replay
+        self._free_hidden()                                         # dist_codec.py:64
         return output

@@ -60,7 +60,7 @@ def apply_fn(module, fn):
 def recur(fn, input, *args):
     if isinstance(input, (torch.Tensor, np.ndarray)):
         return fn(input, *args)
-    if isinstance(input, list):
+    if isinstance(input, list) or (isinstance(input, container_abcs.Sequence) and not isinstance(input, (str, bytes, tuple))):
         return [recur(fn, v, *args) for v in input]
     if isinstance(input, dict):
         return {k: recur(fn, v, *args) for k, v in input.items()}

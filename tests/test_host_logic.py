@@ -226,3 +226,35 @@ def test_caller_shims_torch2_scheduler_data_and_logger(tmp_path):
     with pytest.raises(ValueError):
         lg.append({'x': 'str'}, 'test')
     pickle.loads(pickle.dumps(lg))
+
+
+def test_code_list_is_materialised_once_and_only_on_access():
+    """output['code'] (dist_codec.py:42,61-63) is built from one device->host copy at the first access"""
+    from models.codec_base import CodeList
+    import utils
+    calls = []
+
+    def make():
+        calls.append(1)
+        return [np.full((4, t + 1), 255, dtype=np.uint8) for t in range(3)]
+    c = CodeList(3, make)
+    assert len(c) == 3 and calls == [] and 'pending' in repr(c)
+    assert c[-1].nbytes == 12 and calls == [1]
+    assert [a.shape for a in c] == [(4, 1), (4, 2), (4, 3)] and len(list(reversed(c))) == 3 and calls == [1]
+    assert utils.recur(lambda a: a.nbytes, c) == [4, 8, 12]              # metrics.BPP's walk (metrics.py:43)
+    assert np.concatenate(c, axis=1).shape == (4, 6)                      # C-level consumers iterate it correctly
+    with pytest.raises(ValueError):
+        utils.recur(lambda a: a, 'abc')
+
+
+def test_module_tree_index_follows_the_parameters():
+    m = build_model('dist_codec', 'CIFAR10', 2, 2, seed=5, device='cpu')
+    names, params, cells = m._index()
+    assert names == [k for k, _ in m.named_parameters()] and all(a is b for a, b in zip(params, m.parameters()))
+    assert len(cells) >= 9 and all(hasattr(c, 'free_hidden') for c in cells)
+    assert m._index() is m._index()
+    m.load_state_dict(m.state_dict())
+    assert m._tree is None
+    m._index()
+    m.double()
+    assert m._tree is None and all(a is b for a, b in zip(m._index()[1], m.parameters()))
