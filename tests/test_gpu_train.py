@@ -333,3 +333,57 @@ def test_single_source_pairs_on_the_4x4_layers():
     with torch.no_grad():
         out_e = m({'img': img.cuda(), 'label': label.cuda()})
     assert np.array_equal(out_e['code_pm1'].cpu().numpy(), torch.stack(ref_e['code_pm1']).numpy())
+
+
+@pytest.mark.parametrize('prev_amax,redo', [(0.0, True), (1e-9, True), (3e4, True), (0.02, False)])
+def test_cell_backward_scale_prediction_and_verify_pass(prev_amax, redo):
+    """drasic_lstm_bwd_fused through the C ABI: cell backward (cell.py:133-139 differentiated by autograd on the CPU)
+    into fp16 planes whose power-of-two scale is predicted from another tensor's amax.  Whatever the prediction
+    (unknown, far too small, far too large, right), after the verify pass planes * inv_scale are the fp32 gate
+    gradients to fp16-split precision, and the carry and the true amax are exact."""
+    from engine import binding as B
+    L = B.lib()
+    P, Co = 8192, 128                                   # 512 blocks of work: the verify launch runs on a capped grid
+    g = torch.Generator().manual_seed(90)
+    pre = (torch.randn(P, 4, Co, generator=g) * 1.5).requires_grad_(True)
+    c_prev = torch.randn(P, Co, generator=g).requires_grad_(True)
+    i, f, o = torch.sigmoid(pre[:, 0]), torch.sigmoid(pre[:, 1]), torch.sigmoid(pre[:, 3])
+    gg = torch.tanh(pre[:, 2])
+    c_t = f * c_prev + i * gg
+    h = o * torch.tanh(c_t)
+    dh_above, dh_rec = torch.randn(P, Co, generator=g) * 1e-2, torch.randn(P, Co, generator=g) * 1e-2
+    dc_in = torch.randn(P, Co, generator=g) * 1e-2
+    (h * (dh_above + dh_rec)).sum().backward(retain_graph=True, inputs=[pre, c_prev])
+    d_pre, d_cprev = pre.grad.clone(), c_prev.grad.clone()
+    pre.grad = c_prev.grad = None
+    (c_t * dc_in).sum().backward(inputs=[pre, c_prev])
+    d_pre += pre.grad
+    d_cprev += c_prev.grad
+    gates = torch.stack([i, f, gg, o], 1).detach().cuda().contiguous()       # activated gates, fp32
+    dev = dict(device='cuda')
+    hi, lo = torch.zeros(P, 4, Co, dtype=torch.float16, **dev), torch.zeros(P, 4, Co, dtype=torch.float16, **dev)
+    dc_out = torch.zeros(P, Co, **dev)
+    prev = torch.tensor([prev_amax], dtype=torch.float32, **dev).view(torch.int32)
+    amax = torch.zeros(1, dtype=torch.int32, **dev)
+    inv = torch.zeros(1, **dev)
+    t = [x.detach().cuda().contiguous() for x in (c_t, c_prev, dh_above, dh_rec, dc_in)]
+    a = B.LstmBwdFusedArgs()
+    a.gates, a.c_t, a.c_prev, a.dh_above, a.dh_rec, a.dc_in = [B.ptr(x) for x in [gates] + t]
+    a.dc_out, a.dg_hi, a.dg_lo = B.ptr(dc_out), B.ptr(hi), B.ptr(lo)
+    a.prev_amax_bits, a.amax_bits, a.inv_scale_out = B.ptr(prev), B.ptr(amax), B.ptr(inv)
+    a.n_pix, a.Co, a.gates_f32 = P, Co, 1
+    stream = torch.cuda.current_stream().cuda_stream
+    a.verify = 0
+    B.check(L.drasic_lstm_bwd_fused(a, stream), 'lstm_bwd_fused')
+    inv_first = float(inv)
+    a.verify = 1
+    B.check(L.drasic_lstm_bwd_fused(a, stream), 'lstm_bwd_fused')
+    torch.cuda.synchronize()
+    true_amax = float(d_pre.abs().max())
+    assert abs(float(amax.view(torch.float32)) - true_amax) <= 1e-5 * true_amax
+    assert (float(inv) != inv_first) == redo
+    scaled = true_amax / float(inv)
+    assert 16.0 <= scaled <= 60000.0                     # the planes sit inside fp16's normal range
+    got = (hi.float() + lo.float()) * inv
+    assert (got.cpu() - d_pre).abs().max().item() <= 2e-6 * true_amax + 1e-9
+    assert (dc_out.cpu() - d_cprev).abs().max().item() <= 1e-6 * float(d_cprev.abs().max())
