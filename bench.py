@@ -176,7 +176,6 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     from oracle import drasic_oracle as O          # used only by the cpu_baseline leg at the end
-    from engine.codec import CodecEngine
     import config
     config.init()
     config.PARAM.update(device='cuda', data_name='CIFAR10', precision=args.precision, pack_mode='reference',

@@ -3,7 +3,6 @@ loops run end to end against this package.  The reference's `data
 wrappers with downloaders and an anytree class hierarchy) is outside the coding loop and not rebuilt; what
 the loop consumes is a stream of {'img': [C,32,32] in [0,1], 'label': node id} samples, produced here
 deterministically.  `subset` keeps the reference's meaning of "which annotation becomes the node id"."""
-import numpy as np
 import torch
 from torch.utils.data import DataLoader, Dataset
 from torch.utils.data.dataloader import default_collate

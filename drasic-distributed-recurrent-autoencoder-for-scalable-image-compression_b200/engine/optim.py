@@ -5,7 +5,6 @@ optimizer `make_optimizer` builds at train_model.py:155-161 (optim.Adam with lr 
 Drop-in for torch.optim.Adam on the codec's parameters: same constructor arguments, same update rule, and the
 same per-parameter state ('step', 'exp_avg', 'exp_avg_sq'), so `optimizer.state_dict()` checkpoints written by
 either (train_model.py:90, utils.py:173-180) load into the other."""
-import ctypes as C
 
 import torch
 

@@ -6,7 +6,6 @@ loop and are not provided here."""
 import numpy as np
 import torch
 
-import config
 from utils import recur
 
 

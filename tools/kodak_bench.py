@@ -3,7 +3,6 @@
 usage: python tools/kodak_bench.py [precision]"""
 import os
 import sys
-import time
 
 import torch
 
