@@ -1,14 +1,14 @@
-"""Quantization module (reference modules/quantization.py:5-12): binarize with the module's training flag."""
-import torch.nn as nn
+"""Quantization module (reference modules/quantization.py:5-12): the binarizer as an nn.Module, stochastic while
+the module is in training mode and a deterministic sign otherwise.  `noise` (optional uniforms) makes the
+stochastic draw an explicit input, which is how the parity tests reproduce the reference's samples."""
+from torch import nn
 
-from functions import Quantize as QuantizeFunction
+import functions
 
 __all__ = ['Quantization']
 
 
 class Quantization(nn.Module):
-    def __init__(self):
-        super(Quantization, self).__init__()
-
     def forward(self, input, noise=None):
-        return QuantizeFunction.apply(input, self.training, noise)
+        stochastic = bool(self.training)
+        return functions.Quantize.apply(input, stochastic, noise)
