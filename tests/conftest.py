@@ -13,6 +13,10 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a real B200 (run with -m gpu on the GPU box)')
+    # a fresh checkout has no libdrasic_b200.so (built artefacts are not tracked): compile it once (nvcc needs no GPU)
+    if not os.path.exists(os.path.join(PKG, 'libdrasic_b200.so')):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope='session')
