@@ -258,3 +258,46 @@ def test_module_tree_index_follows_the_parameters():
     m._index()
     m.double()
     assert m._tree is None and all(a is b for a, b in zip(m._index()[1], m.parameters()))
+
+
+def test_batch_plan_invariants_property():
+    """any labelling, any padding unit: perm is a bijection onto the batch, every slot lies in exactly one node's
+    range, node order is kept inside a node, every tile a node's pixels touch is walked by that node, and wgrad
+    K blocks never straddle two nodes when the plan is a training plan (pad 4)"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 10).flatmap(lambda m: st.tuples(st.just(m), st.lists(st.integers(0, m - 1), min_size=1, max_size=70))),
+           st.sampled_from([1, 4]))
+    def check(case, pad):
+        M, labels = case
+        label = np.array(labels)
+        p = BatchPlan(label, M, 'cpu', pad=pad, hws=(256, 64, 16))
+        assert p.B_pad % 8 == 0 and p.B_pad >= label.size
+        valid = p.perm_host[p.perm_host >= 0]
+        assert sorted(valid.tolist()) == list(range(label.size))
+        ends = p.group_img_end_host
+        assert (np.diff(np.concatenate(([0], ends))) >= 0).all() and ends[-1] == p.B_pad
+        for j in range(M):
+            lo = 0 if j == 0 else ends[j - 1]
+            idx = p.perm_host[lo:ends[j]]
+            idx = idx[idx >= 0]
+            assert (label[idx] == j).all() and (np.diff(idx) > 0).all() and idx.size == (label == j).sum()
+            if pad == 4:
+                assert lo % 4 == 0 and ends[j] % 4 == 0
+        for hw in (256, 64, 16):
+            for pair in (False, True):
+                u, total = p.m_units(hw, pair)
+                u = u.numpy()
+                assert total == u[2, -1] and (np.diff(np.concatenate(([0], u[2]))) >= 0).all()
+                for j in range(M):
+                    lo = 0 if j == 0 else ends[j - 1]
+                    if ends[j] > lo:
+                        assert u[0, j] * 128 <= lo * hw and u[1, j] * 128 >= ends[j] * hw    # tiles cover the node's pixels
+                        n = u[1, j] - u[0, j]
+                        got = u[2, j] - (u[2, j - 1] if j else 0)
+                        assert got == ((n + 1) // 2 if pair else n)
+            kb = p.kb_end(hw).numpy()
+            if pad == 4:
+                assert (kb * 64 == ends.astype(np.int64) * hw).all()                           # K blocks end exactly at node ends
+    check()
