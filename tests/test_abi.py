@@ -63,3 +63,38 @@ def test_invalid_arguments_map_to_value_error():
     assert L.drasic_pack_lstm_weights(None, None, 128, 128, 0, 0, 256, None, None, None, None, None) == -1
     assert L.drasic_quantize_fwd(None, None, None, 4, None) == -1
     assert L.drasic_conv1x1_fwd(None, None, None, None, 1, 1, 1, 1, 1, None) == -1
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/drasic_b200.h compiles as C (no C++ or torch types in the signatures) and a C program links the
+    library through it; bad arguments come back as DRASIC_ERR_INVALID with a message, without touching a device"""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'use_abi.c'
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "drasic_b200.h"
+int main(void) {
+  drasic_convlstm_args a;
+  drasic_adam_tensor t;
+  memset(&a, 0, sizeof a);
+  memset(&t, 0, sizeof t);
+  t.numel = 4;
+  if (drasic_version() != 1) return 1;
+  if (drasic_convlstm_fwd(&a, NULL) != -1) return 2;
+  if (strlen(drasic_last_error()) == 0) return 3;
+  if (drasic_adam_step(&t, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0.1, 0.001, NULL) != -1) return 4;
+  if (drasic_adam_step(&t, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0.1, 0.001, NULL) != 0) return 5;
+  printf("%d %d\n", (int)sizeof a, (int)sizeof t);
+  return 0;
+}
+''')
+    exe = tmp_path / 'use_abi'
+    libdir = os.path.dirname(B.LIB_PATH)
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                    '-L', libdir, '-ldrasic_b200', '-Wl,-rpath,' + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(B.ConvLSTMArgs) and int(out[1]) == ctypes.sizeof(B.AdamTensor)
