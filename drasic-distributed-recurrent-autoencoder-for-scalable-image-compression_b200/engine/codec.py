@@ -56,9 +56,9 @@ def plan_arrays(label_host, num_node, pad_total=None, pad=None):
     return perm, ends.astype(np.int32), counts
 
 
-def worst_case_pad(B, num_node):
-    """slot count that fits any assignment of B samples to num_node nodes"""
-    return (B + (PAD - 1) * min(num_node, B) + TOTAL_PAD - 1) // TOTAL_PAD * TOTAL_PAD
+def worst_case_pad(B, num_node, pad=PAD):
+    """slot count that fits any assignment of B samples to num_node nodes whose ranges are multiples of `pad`"""
+    return (B + (pad - 1) * min(num_node, B) + TOTAL_PAD - 1) // TOTAL_PAD * TOTAL_PAD
 
 
 class BatchPlan(object):
@@ -913,7 +913,9 @@ class GraphedCodec(object):
             if training else None
         hws = sorted({(H // d) * (W // d) for d in (2, 4, 8)})
         label0 = np.arange(self.B) % engine.M
-        self.plan = BatchPlan(label0, engine.M, dev, pad_total=worst_case_pad(self.B, engine.M), static_hw=hws)
+        pad = PAD if with_backward else 1     # inference plans pack the nodes back to back: no worst-case slack at all
+        self.plan = BatchPlan(label0, engine.M, dev, pad_total=worst_case_pad(self.B, engine.M, pad), static_hw=hws,
+                              pad=pad)
         self.graph = None
         self.out = self.grads = None
         side = torch.cuda.Stream(device=dev)
