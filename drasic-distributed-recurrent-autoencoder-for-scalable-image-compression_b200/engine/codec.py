@@ -189,7 +189,10 @@ class CodecEngine(object):
         if cta_pair not in ('auto', 'on', 'off'):
             raise ValueError('Not valid cta_pair')
         self.cta_pair = cta_pair  # CTA pairs (cta_group::2) for the gate / dgrad / wgrad GEMMs
-        self.wgrad_pair_mode = int(os.environ.get('DRASIC_WGRAD_PAIR', '2'))   # 1: 256-column, 2: 512-column pair tiles
+        # wgrad pair tiles: 1 = 256 columns (default), 2 = 512 columns where a node has >= 256 K blocks.  The wide tiles
+        # move fewer bytes per MMA but leave 9..180 work units for 74 CTA pairs; measured per step at B=1024 they are
+        # slower on every layer (D1 7.8 vs 4.9 ms, E1 10.0 vs 8.5, D2 20.1 vs 17.9, D3 8.7 vs 8.5)
+        self.wgrad_pair_mode = int(os.environ.get('DRASIC_WGRAD_PAIR', '1'))
         self.gsplit = 1 if grad_precision == 'parity' else 0
         self.C, self.code, self.M, self.separate = num_channel, code_size, num_node, separate
         self.split = 1 if precision == 'parity' else 0

@@ -387,3 +387,30 @@ def test_cell_backward_scale_prediction_and_verify_pass(prev_amax, redo):
     got = (hi.float() + lo.float()) * inv
     assert (got.cpu() - d_pre).abs().max().item() <= 2e-6 * true_amax + 1e-9
     assert (dc_out.cpu() - d_cprev).abs().max().item() <= 1e-6 * float(d_cprev.abs().max())
+
+
+def test_wgrad_wide_pair_tiles_agree_with_the_default_tiles():
+    """the opt-in 512-column wgrad pair tiles (DRASIC_WGRAD_PAIR=2; used where a node has >= 256 K blocks) give the
+    same weight gradients as the default 256-column tiles, and both match the oracle's autograd"""
+    M, B_, T = 1, 72, 2
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=21)
+    g = torch.Generator().manual_seed(22)
+    img = torch.rand(B_, 3, 32, 32, generator=g)
+    label = torch.zeros(B_, dtype=torch.long)
+    noise = torch.rand(T, B_, 8, 4, 4, generator=g)
+    grads = {}
+    for mode in (1, 2):
+        m.zero_grad()
+        m.train(True)
+        if m._engine is not None:
+            m._engine.wgrad_pair_mode = mode
+        out = m({'img': img.cuda(), 'label': label.cuda()}, noise=noise.cuda())
+        m._engine.wgrad_pair_mode = mode          # (the engine exists after the first forward)
+        out['loss'].backward()
+        grads[mode] = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    ref = O.codec_forward(sd, img, label, T, M, training=True, noise=[n for n in noise])
+    ref['loss'].backward()
+    for k in grads[1]:
+        assert rel_err(grads[2][k].cpu(), grads[1][k].cpu()) < 2e-4, k       # fp32 accumulation order only
+        assert rel_err(grads[2][k].cpu(), sd[k].grad) < GRAD_TOL['fp16'], k
