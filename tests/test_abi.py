@@ -98,3 +98,43 @@ int main(void) {
                     '-L', libdir, '-ldrasic_b200', '-Wl,-rpath,' + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == ctypes.sizeof(B.ConvLSTMArgs) and int(out[1]) == ctypes.sizeof(B.AdamTensor)
+
+
+def header_structs():
+    """{typedef name: [(kind, field name)]} parsed from the header; kind is 'ptr', 'int', 'float', 'size_t' or 'll'"""
+    text = open(os.path.join(ROOT, 'include', 'drasic_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    out = {}
+    for body, name in re.findall(r'typedef\s+struct\s*\{(.*?)\}\s*(drasic_[a-z0-9_]+)\s*;', text, flags=re.S):
+        fields = []
+        for decl in body.split(';'):
+            decl = ' '.join(decl.split())
+            if not decl:
+                continue
+            m = re.match(r'^(const\s+)?(void|float|double|int|uint8_t|size_t|long long|unsigned int)\s*(.*)$', decl)
+            assert m, decl
+            base = m.group(2)
+            for item in m.group(3).split(','):
+                item = item.strip()
+                ptr = item.startswith('*')
+                fname = item.lstrip('* ').strip()
+                kind = 'ptr' if ptr else {'int': 'int', 'float': 'float', 'size_t': 'size_t', 'long long': 'll'}[base]
+                fields.append((kind, fname))
+        out[name] = fields
+    return out
+
+
+def test_binding_structs_follow_the_header_field_for_field():
+    structs = header_structs()
+    pairs = {'drasic_convlstm_args': B.ConvLSTMArgs, 'drasic_bottleneck_args': B.BottleneckArgs,
+             'drasic_tail_head_args': B.TailHeadArgs, 'drasic_lstm_bwd_fused_args': B.LstmBwdFusedArgs,
+             'drasic_dgrad_args': B.DgradArgs, 'drasic_wgrad_args': B.WgradArgs,
+             'drasic_bottleneck_bwd_args': B.BottleneckBwdArgs, 'drasic_tail_bwd_args': B.TailBwdArgs,
+             'drasic_head_bwd_args': B.HeadBwdArgs, 'drasic_adam_tensor': B.AdamTensor}
+    assert sorted(structs) == sorted(pairs)
+    ctype_of = {'ptr': ctypes.c_void_p, 'int': ctypes.c_int, 'float': ctypes.c_float, 'size_t': ctypes.c_size_t,
+                'll': ctypes.c_longlong}
+    for name, cls in pairs.items():
+        want = [(f, ctype_of[k]) for k, f in structs[name]]
+        got = [(f, t) for f, t in cls._fields_]
+        assert got == want, name
