@@ -138,3 +138,30 @@ def test_binding_structs_follow_the_header_field_for_field():
         want = [(f, ctype_of[k]) for k, f in structs[name]]
         got = [(f, t) for f, t in cls._fields_]
         assert got == want, name
+
+
+def test_binding_prototypes_follow_the_header():
+    """argument count and kind of every ctypes prototype against the header's declaration"""
+    text = open(os.path.join(ROOT, 'include', 'drasic_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = re.findall(r'\b(int|size_t|const char\*)\s+(drasic_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', text)
+    assert len(protos) == len(B.SYMBOLS)
+    L = B.lib()
+    scalar = {'int': ctypes.c_int, 'size_t': ctypes.c_size_t, 'float': ctypes.c_float, 'double': ctypes.c_double}
+    restype = {'int': ctypes.c_int, 'size_t': ctypes.c_size_t, 'const char*': ctypes.c_char_p}
+    for ret, name, args in protos:
+        fn = getattr(L, name)
+        assert fn.restype is restype[ret], name
+        params = [] if args.strip() in ('', 'void') else [' '.join(a.split()) for a in args.split(',')]
+        got = list(fn.argtypes or [])
+        assert len(got) == len(params), name
+        for p, t in zip(params, got):
+            if '*' in p:
+                m = re.search(r'(drasic_[a-z0-9_]+)\s*\*', p)
+                if m:       # pointer to an argument struct
+                    assert issubclass(t, ctypes._Pointer) and ctypes.sizeof(t._type_) > 0, (name, p)
+                else:
+                    assert t is ctypes.c_void_p, (name, p)
+            else:
+                base = re.match(r'^(?:const\s+)?(int|size_t|float|double)\b', p).group(1)
+                assert t is scalar[base], (name, p)
