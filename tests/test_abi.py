@@ -165,3 +165,20 @@ def test_binding_prototypes_follow_the_header():
             else:
                 base = re.match(r'^(?:const\s+)?(int|size_t|float|double)\b', p).group(1)
                 assert t is scalar[base], (name, p)
+
+
+def test_library_is_sm100a_tensor_core_and_tma_code():
+    """the shipped library really is tcgen05 / TMA code for sm_100a: its SASS holds UTCHMMA (tcgen05.mma), LDTM
+    (tcgen05.ld), UTMALDG (cp.async.bulk.tensor), UBLKCP (cp.async.bulk), SYNCS (mbarriers), the two-CTA variants and
+    cluster barriers -- and no legacy HMMA (mma.sync) anywhere"""
+    import shutil
+    import subprocess
+    tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(tool):
+        pytest.skip('no cuobjdump')
+    sass = subprocess.run([tool, '-sass', B.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    assert 'arch = sm_100a' in sass and 'arch = sm_90' not in sass
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UBLKCP', 'SYNCS', 'UCGABAR_ARV', 'UTCBAR'):
+        assert mnemonic in sass, mnemonic
+    assert '.2CTA' in sass                                   # cta_group::2 MMAs / TMA loads of the CTA-pair kernels
+    assert not re.search(r'\bHMMA\b', sass)
