@@ -176,3 +176,16 @@ def test_fixtures_regenerate_bit_identically_from_the_reference(golden_dir, tmp_
         assert sorted(a.files) == sorted(b.files), f
         for k in a.files:
             assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), (f, k)
+
+
+def test_oracle_agrees_with_the_live_reference_on_fresh_cases(golden_dir):
+    """tests/golden/live_check.py: the reference's own modules (imported from /root/reference in a process of
+    their own) against the oracle on seeds and shapes no fixture holds -- eval codes / z / reconstructions / loss
+    for dist and sep codecs, and a training pass (the reference's uniforms, loss, every parameter gradient)"""
+    import subprocess
+    import sys
+    if not os.path.isdir('/root/reference/src'):
+        pytest.skip('the reference tree exists only in the build container')
+    r = subprocess.run([sys.executable, os.path.join(golden_dir, 'live_check.py')], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and 'live check passed' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
