@@ -47,6 +47,10 @@ class FusedAdam(torch.optim.Optimizer):
         L = B.lib()
         self.launches = 0
         for group in self.param_groups:
+            # options a loaded torch.optim.Adam state_dict may carry that this kernel does not implement
+            for opt in ('amsgrad', 'maximize', 'decoupled_weight_decay', 'differentiable'):
+                if group.get(opt):
+                    raise ValueError('Not valid optimizer option for FusedAdam: {}'.format(opt))
             beta1, beta2 = group['betas']
             buckets = {}      # (device, step count) -> [(param, grad, exp_avg, exp_avg_sq)]
             for p in group['params']:
