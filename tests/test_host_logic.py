@@ -301,3 +301,22 @@ def test_batch_plan_invariants_property():
             if pad == 4:
                 assert (kb * 64 == ends.astype(np.int64) * hw).all()                           # K blocks end exactly at node ends
     check()
+
+
+def test_wgrad_k_split_picker():
+    """_pick_k_splits: within the K blocks a node offers, aim for >= 3 waves of work on the persistent grid and
+    prefer the split whose last wave is fullest"""
+    from engine.codec import _pick_k_splits
+    assert 1 <= _pick_k_splits(tiles=1000, units=74, k_max=64) <= 4       # plenty of tiles already: only wave balance
+    for tiles, units, k_max in [(9, 74, 32), (18, 74, 16), (90, 74, 16), (180, 74, 65), (45, 148, 8), (1, 74, 1), (7, 74, 2)]:
+        k = _pick_k_splits(tiles, units, k_max)
+        assert 1 <= k <= k_max
+        n = tiles * k
+        waves = -(-n // units)
+        # no admissible split with at least as many waves fills its last wave better
+        k_lo = max(1, min(k_max, (3 * units + tiles - 1) // tiles))
+        assert k >= k_lo or k == k_max
+        eff = n / float(waves * units)
+        for other in range(k_lo, max(k_lo, min(k_max, 4 * k_lo)) + 1):
+            m = tiles * other
+            assert m / float(-(-m // units) * units) <= eff + 1e-3 or other > k
