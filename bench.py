@@ -1,12 +1,22 @@
 """Benchmark of DRASIC's recurrent residual coding loop on B200 (see BASELINE.json / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--mode eval|train]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--mode all|train|eval]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path (T=16 iterations of encode -> binarize -> decode over the
 residual) over one batch of synthetic CIFAR-shaped images from 8 sources.  Rank 0 prints ONE JSON line.
+
+The line's own `value` is the training step (forward + backward-through-time + gradient all-reduce + Adam) of
+BASELINE configs[1] at --batch images per GPU.  With the default `--mode all` the same line also carries, each
+with its own value / e2e / roofline:
+    eval          encode+decode of the same workload (the other half of BASELINE.json's metric)
+    b128          training step and encode+decode at 128 images per GPU (SURVEY 8d config 2's batch)
+    config1       BASELINE configs[0]: MNIST-shaped single source, eval, batch 64
+    grad_parity   the training step with fp32-grade (split-fp16) backward GEMMs
+    parity        codes / reconstructions / PSNR of this build against the CPU oracle on 256 images
+    multi_gpu_parity   (N > 1) all-reduced gradients of a sharded batch against the same batch on one GPU
 `--impl reference` times the CPU oracle (the reference's algorithm on torch CPU ops, all host threads)
-on a bounded sample of the same workload.
+on a bounded sample of the same workload: the SAME sample `cpu_baseline` of our arm is timed on.
 """
 import argparse
 import json
@@ -25,8 +35,11 @@ for _p in (ROOT, PKG):
 T_ITER = 16
 M_NODES = 8
 CHANNELS = 3
-FLOP_PER_IMG_FWD = 57.083e9        # SURVEY 8d / BASELINE.md 3: dense forward count at T=16, C=3
+FLOP_PER_IMG_ITER = {3: 3567714304.0, 1: 3567452160.0}     # dense forward count per image and iteration
 METRIC = 'images/s train & encode+decode at T=16 (CIFAR-10 32x32), 1/2/4/8 B200; PSNR parity'
+# one CPU sample per mode, used by BOTH `cpu_baseline` (our arm) and `--impl reference`
+CPU_SAMPLE = {'train': 64, 'eval': 256}
+PARITY_SAMPLE = 256
 
 
 def measured_peaks():
@@ -86,83 +99,390 @@ class ClockSampler(object):
                 'samples': len(sm)}
 
 
-def workload_name(mode):
-    return ('cifar10_32x32_m8_random_subsets_T16_train_step_fwd_bptt_adam' if mode == 'train'
-            else 'cifar10_32x32_m8_random_subsets_T16_eval_encode_decode')
+def workload_name(mode, channels=CHANNELS, nodes=M_NODES):
+    data = 'cifar10_32x32' if channels == 3 else 'mnist_32x32'
+    src = 'm{}_random_subsets'.format(nodes) if nodes > 1 else 'single_source'
+    return '{}_{}_T16_{}'.format(data, src, 'train_step_fwd_bptt_adam' if mode == 'train' else 'eval_encode_decode')
 
 
-def synth_batch(batch, seed):
+def workload_config(mode, batch, world, channels=CHANNELS, nodes=M_NODES):
+    """what is computed -- shared verbatim by our arm and the reference arm"""
+    return {'workload': workload_name(mode, channels, nodes), 'batch_per_gpu': batch, 'global_batch': world * batch,
+            'num_node': nodes, 'num_iter': T_ITER, 'code_size': 8, 'image': [channels, 32, 32],
+            'l2': 'per-step working set (activations+state, ~1 MB/image) exceeds the 126 MB L2'}
+
+
+def synth_batch(batch, seed, channels=CHANNELS, nodes=M_NODES):
     import torch
     g = torch.Generator().manual_seed(seed)
-    img = torch.rand(batch, CHANNELS, 32, 32, generator=g)
-    label = torch.randint(0, M_NODES, (batch,), generator=g)        # "split by random subsets"
+    img = torch.rand(batch, channels, 32, 32, generator=g)
+    label = torch.randint(0, nodes, (batch,), generator=g)        # "split by random subsets"
     return img, label
 
 
-# ------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """the reference's algorithm (oracle port: torch CPU fp32 ops in the reference's order) on host cores"""
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
+# ------------------------------------------------------------------------------------------ CPU (oracle) timing
+def cpu_time(mode, steps, warmup, sd=None, with_adam=True):
+    """the reference's algorithm (oracle port: torch CPU fp32 ops in the reference's order) on all host cores,
+    on CPU_SAMPLE[mode] images per step.  Returns (images/s, seconds per step, cores, description)."""
     import torch
     from oracle import drasic_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    train = args.mode == 'train'
-    sd = O.init_state_dict(CHANNELS, 8, M_NODES, seed=0)
-    opt = None
-    if train:
-        sd = {k: v.requires_grad_(True) for k, v in sd.items()}
-        opt = torch.optim.Adam(list(sd.values()), lr=1e-3)           # train_model.py:161
+    train = mode == 'train'
+    nb = CPU_SAMPLE[mode]
+    if sd is None:
+        sd = O.init_state_dict(CHANNELS, 8, M_NODES, seed=0)
+    sd = {k: v.detach().cpu().clone().requires_grad_(train) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-3) if train and with_adam else None   # train_model.py:161
 
     def step(img, label, n_iter=T_ITER):
-        if train:                                                    # forward + full BPTT, like train_model.py:113-115
+        if train:                                                    # forward + full BPTT, like train_model.py:113-116
             for v in sd.values():
                 v.grad = None
-            out = O.codec_forward(sd, img, label, n_iter, M_NODES, training=True)
-            out['loss'].backward()
-            opt.step()                                               # train_model.py:116
+            O.codec_forward(sd, img, label, n_iter, M_NODES, training=True)['loss'].backward()
+            if opt is not None:
+                opt.step()
         else:
             with torch.no_grad():
                 O.codec_forward(sd, img, label, n_iter, M_NODES)
-    # size the per-step sample so the whole run stays within a few minutes
     img, label = synth_batch(8, 1)
     step(img, label, 2)                                              # warm the thread pool / oneDNN primitives
-    t0 = time.perf_counter()
-    step(img, label)
-    t8 = time.perf_counter() - t0
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    sample = int(max(8, min(64, 8 * budget / max(t8, 1e-3))) // 8 * 8)
-    img, label = synth_batch(sample, 2)
-    for _ in range(args.warmup):
+    img, label = synth_batch(nb, 7)
+    for _ in range(warmup):
         step(img, label)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(img, label)
-    dt = (time.perf_counter() - t0) / args.steps
-    v = sample / dt
+    dt = (time.perf_counter() - t0) / steps
+    what = 'oracle/drasic_oracle.py codec_forward{}, B={} M=8 T=16 per step, {} step(s) of {:.1f} s'.format(
+        ' + backward (stochastic binarizer, full BPTT)' + (' + Adam step' if opt is not None else '') if train else ' (eval)',
+        nb, steps, dt)
+    return nb / dt, dt, cores, what
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    main_mode = 'train' if args.mode in ('all', 'train') else 'eval'
+    v, dt, cores, what = cpu_time(main_mode, args.steps, args.warmup)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.mode), 'sample_batch': sample,
-                   'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8},
-        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': 'oracle/drasic_oracle.py codec_forward{}, B={} M=8 T=16 per step'.format(
-                             ' + backward (stochastic binarizer, full BPTT) + Adam step' if train else ' (eval)', sample)},
+        'config': workload_config(main_mode, args.batch, args.gpus),
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': what},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if args.mode == 'all':
+        ev, edt, _, ewhat = cpu_time('eval', min(args.steps, 2), 1)
+        line['eval'] = {'value': ev, 'unit': 'images/s', 'ms_per_step': edt * 1e3,
+                        'config': workload_config('eval', args.batch, args.gpus),
+                        'cpu_baseline': {'value': ev, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': ewhat}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def prof_gate_tflops(gate, fwd_mma_per_mac):
-    """tensor-core work actually issued: forward gate GEMMs count fwd_mma_per_mac MMAs per algorithmic MAC"""
-    fl = sum(v[2] * (fwd_mma_per_mac if k.startswith('gates') else 1) for k, v in gate)
-    ms = sum(v[1] for _, v in gate)
-    return fl / (ms * 1e-3) / 1e12 if ms else 0.0
+class Arm(object):
+    """one model + optimizer on this rank's GPU, measured through the public API"""
+
+    def __init__(self, dev, rank, world, channels=CHANNELS, nodes=M_NODES, precision='parity', grad_precision='fp16',
+                 shard='batch'):
+        import torch
+        import config
+        import utils
+        self.torch, self.config = torch, config
+        self.dev, self.rank, self.world = dev, rank, world
+        self.channels, self.nodes, self.precision, self.grad_precision = channels, nodes, precision, grad_precision
+        self.by_source = shard == 'source' and world > 1 and nodes >= world
+        self._apply_config()
+        import models
+        torch.manual_seed(0)
+        self.model = models.dist_codec().to(dev)
+        self.params = [p for p in self.model.parameters()]
+        self.opt = None
+
+    def _apply_config(self):
+        c = self.config
+        c.PARAM.update(device='cuda', data_name='CIFAR10' if self.channels == 3 else 'MNIST', precision=self.precision,
+                       pack_mode='reference', grad_precision=self.grad_precision, loss_fn='mae')
+        c.PARAM['control'] = {'normalization': 'none', 'activation': 'tanh', 'num_iter': str(T_ITER),
+                              'code_size': '8', 'num_node': str(self.nodes)}
+        import utils
+        utils.process_control_name()
+
+    def batch(self, B, seed=1000):
+        img_h, label_h = synth_batch(B, seed + self.rank, self.channels, self.nodes)
+        if self.by_source:
+            # SURVEY 8(e) partitioning for M >= G: this rank holds the samples (and trains the encoders) of its own nodes
+            from engine.dist import owned_nodes
+            mine = owned_nodes(self.nodes, self.rank, self.world)
+            label_h = self.torch.tensor(mine)[label_h % len(mine)]
+        return img_h, label_h
+
+    def barrier(self):
+        if self.world > 1:
+            self.torch.distributed.barrier()
+        self.torch.cuda.synchronize()
+
+    def step(self, inp, train, B):
+        """one pass of the hot path through the public API"""
+        from engine.dist import allreduce_gradients, reduce_source_sharded
+        torch = self.torch
+        if train:
+            if self.opt is None:
+                from engine.optim import FusedAdam
+                self.opt = FusedAdam(self.params, lr=1e-3)                # train_model.py:161 (optim.Adam)
+            self.opt.zero_grad(set_to_none=True)
+            out = self.model(inp)                                         # train_model.py:113
+            out['loss'].backward()                                        # :115  (backward-through-time kernels)
+            if self.by_source:
+                reduce_source_sharded(self.model, B, self.world * B, self.rank, self.world)   # joint decoder only
+            else:
+                allreduce_gradients(self.params, B, self.world * B)       # replaces DataParallel's reduce (:60)
+            self.opt.step()                                               # :116
+        else:
+            with torch.no_grad():
+                out = self.model(inp)
+        return out
+
+    def measure(self, mode, B, steps, warmup, graph=False, fast=False, clocks=False):
+        """device-timed steps on resident inputs, a per-kernel pass, and the end-to-end loop on host buffers"""
+        torch, config = self.torch, self.config
+        self._apply_config()
+        train = mode == 'train'
+        self.model.train(train)
+        img_h, label_h = self.batch(B)
+        img, label = img_h.to(self.dev), label_h.to(self.dev)
+        config.PARAM['cuda_graph'] = graph
+        resident = {'img': img, 'label': label}
+        for _ in range(max(warmup, 3)):
+            self.step(resident, train, B)
+        self.barrier()
+        sampler = ClockSampler(self.dev.index) if (clocks and self.rank == 0) else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step(resident, train, B)
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1) / steps
+        eng = self.model._engine
+        launches = eng.launches + (self.opt.launches if train else 0)
+        res = {'clocks': sampler.stop() if sampler else None}
+
+        # ---- per-kernel timing on the launching stream (separate eager pass, CUDA events around every launch)
+        config.PARAM['cuda_graph'] = False
+        eng.profile = []
+        for _ in range(2):
+            self.step(resident, train, B)
+        torch.cuda.synchronize()
+        prof = eng.profile_summary()
+        eng.profile = None
+        config.PARAM['cuda_graph'] = graph
+
+        # ---- end to end through the public API with host buffers (H2D of inputs, D2H of loss + codes)
+        pin_img, pin_label = img_h.pin_memory(), label_h.pin_memory()
+
+        def e2e_step():
+            out = self.step({'img': pin_img.to(self.dev, non_blocking=True),
+                             'label': pin_label.to(self.dev, non_blocking=True)}, train, B)
+            return out['loss'].item(), out['code'][-1].nbytes
+        for _ in range(2):
+            e2e_step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        self.barrier()
+        e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+
+        # ---- the same step at 'fast' precision (single fp16 operands + tanh.approx, stated tolerance), for reference
+        fast_ms = float('nan')
+        if fast and self.precision == 'parity':
+            self.precision = 'fast'
+            self._apply_config()
+            for _ in range(3):
+                self.step(resident, train, B)
+            self.barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(steps):
+                self.step(resident, train, B)
+            f1.record()
+            self.barrier()
+            fast_ms = f0.elapsed_time(f1) / steps
+            self.precision = 'parity'
+            self._apply_config()
+        config.PARAM['cuda_graph'] = False
+
+        t = torch.tensor([ms, e2e_ms, fast_ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, e2e_ms, fast_ms = t.tolist()
+        res.update(mode=mode, B=B, steps=steps, warmup=max(warmup, 3), ms=ms, e2e_ms=e2e_ms, fast_ms=fast_ms, prof=prof,
+                   launches=launches, graph=graph)
+        return res
+
+    def record(self, r):
+        """bench record (value / e2e / roofline ...) of one measurement"""
+        sust, burst, hbm, how = measured_peaks()
+        train, B, world, prof = r['mode'] == 'train', r['B'], self.world, r['prof']
+        gate = [(k, v) for k, v in prof.items() if k.split('_')[0] in ('gates', 'dgrad', 'wgrad')]
+        g_n = sum(v[0] for _, v in gate)
+        g_ms = sum(v[1] for _, v in gate)
+        g_fl = sum(v[2] for _, v in gate)
+        all_ms = sum(v[1] for v in prof.values())
+        achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
+        fwd_mma = 3 if self.precision == 'parity' else 1
+        bwd_mma = 3 if self.grad_precision == 'parity' else 1
+        issued = sum(v[2] * (fwd_mma if k.startswith('gates') else bwd_mma) for k, v in gate)
+        flop_per_img = FLOP_PER_IMG_ITER[self.channels] * T_ITER * (3 if train else 1)
+
+        def kind_tflops(kk):
+            ms = sum(v[1] for k, v in gate if k.startswith(kk))
+            return sum(v[2] for k, v in gate if k.startswith(kk)) / max(1e-9, ms) / 1e9
+        fwd = kind_tflops('gates')
+        rec = {
+            'value': world * B / r['ms'] * 1e3, 'unit': 'images/s', 'ms_per_step': r['ms'], 'steps': r['steps'],
+            'warmup': r['warmup'],
+            'dtype': ('f16x2-split forward (fp32-grade, fp32 accumulate)' if self.precision == 'parity'
+                      else 'f16 forward (fp32 accumulate)')
+                     + ((', f16 backward GEMMs with exact per-tensor power-of-two scaling, fp32 gradients (tolerance 1e-2 relative '
+                         'per tensor, tests/test_gpu_train.py)' if self.grad_precision == 'fp16' else
+                         ', f16x2-split backward GEMMs, fp32 saved gates, fp32 gradients (tolerance 5e-4 relative per tensor, '
+                         'tests/test_gpu_train.py)') if train else ''),
+            'config': workload_config(r['mode'], B, world, self.channels, self.nodes),
+            'impl_config': {'precision': self.precision, 'grad_precision': self.grad_precision if train else None,
+                            'cuda_graph': r['graph'],
+                            'parallelism': (('dp{}: sharded by source (rank r owns nodes r mod N), one NCCL all-reduce of the joint '
+                                             "decoder's gradients per step" if self.by_source else
+                                             'dp{}: batch sharded, one NCCL all-reduce of gradients per step').format(world) if train
+                                            else 'batch-sharded replicas x{} (no collective)'.format(world))},
+            'e2e': {'value': world * B / r['e2e_ms'] * 1e3, 'unit': 'images/s',
+                    'h2d_bytes_per_step': B * self.channels * 32 * 32 * 4 + B * 8,
+                    'd2h_bytes_per_step': T_ITER * B * 128 * 4 + 4,
+                    'api': 'models.dist_codec() Model.forward (+ loss.backward(), gradient all-reduce, engine.optim.FusedAdam step when '
+                           'training) on pinned host img/label; loss.item() and the emitted codes read back'},
+            'gpu_launches': r['launches'] * r['steps'],
+            'roofline': {'bound': 'tensor',
+                         'kernel': ('conv_gemm_kernel<gates> + conv_gemm_kernel<dgrad> + wgrad_kernel (6 layers x 16 iterations)'
+                                    if train else 'conv_gemm_kernel<gates> (6 layers x 16 iterations)'),
+                         'achieved': achieved, 'peak': sust, 'unit': 'TFLOP/s', 'frac': achieved / sust,
+                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained ({}); burst {}'.format(how, burst),
+                         'traffic': None,
+                         'traffic_note': 'not measurable inside bench.py; per-kernel dram__bytes of the same kernels are in the ncu '
+                                         'captures under profiles/ (r2_ncu_full_*_summary.csv)',
+                         'launches': g_n, 'avg_launch_ms': g_ms / max(g_n, 1), 'share_of_step': g_ms / max(all_ms, 1e-9),
+                         'dominant_kernel': {'name': 'conv_gemm_kernel<gates> (forward gate GEMMs)', 'achieved': fwd,
+                                             'frac': fwd / sust, 'tensor_mma_per_algorithmic_mac': fwd_mma,
+                                             'issued_mma_frac': fwd * fwd_mma / sust},
+                         'per_kind_tflops': {kk: kind_tflops(kk) for kk in ('gates', 'dgrad', 'wgrad')
+                                             if any(k.startswith(kk) for k, _ in gate)},
+                         'issued_mma_tflops': issued / (g_ms * 1e-3) / 1e12 if g_ms else 0.0},
+            'kernels_ms_per_step': {k: v[1] / 2 for k, v in sorted(prof.items())},
+            'algorithmic_tflops': world * B / r['ms'] * 1e3 * flop_per_img / 1e12,
+        }
+        rec['roofline']['issued_mma_frac'] = rec['roofline']['issued_mma_tflops'] / sust
+        if r['fast_ms'] == r['fast_ms']:
+            rec['fast_precision'] = {'value': world * B / r['fast_ms'] * 1e3, 'unit': 'images/s', 'ms_per_step': r['fast_ms'],
+                                     'dtype': 'f16 forward (fp32 accumulate, tanh.approx)' + (', f16 backward GEMMs' if train else ''),
+                                     'tolerance': 'code mismatch rate < 2e-3 in the first iterations, PSNR within 0.05 dB per rate '
+                                                  '(tests/test_gpu_loop.py::test_fast_precision_stated_tolerance)'}
+        if r.get('clocks'):
+            rec['clocks'] = r['clocks']
+        return rec
+
+    def release(self):
+        self.model.release()
+        self.opt = None
+        self.torch.cuda.empty_cache()
+
+
+def parity_check(arm, n_img):
+    """eval-mode parity of this build against the CPU oracle on n_img images of the bench workload (M=8, T=16)"""
+    import torch
+    from oracle import drasic_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    arm._apply_config()
+    model = arm.model
+    sd = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    pi, pl = synth_batch(n_img, 11, arm.channels, arm.nodes)
+    with torch.no_grad():
+        ref = O.codec_forward(sd, pi, pl, T_ITER, arm.nodes)
+        was = model.training
+        model.train(False)
+        out = model({'img': pi.to(arm.dev), 'label': pl.to(arm.dev)})
+        model.train(was)
+    refc, refz = torch.stack(ref['code_pm1']), torch.stack(ref['z'])
+    codes = out['code_pm1'].cpu()
+    diff = codes != refc                                          # [T,B,code,h,w]
+    # a flip cascades through the later iterations of its image: count the FIRST differing symbol(s) per image
+    flips, margins = 0, []
+    clean = torch.ones(n_img, dtype=torch.bool)
+    for b in range(n_img):
+        for t in range(T_ITER):
+            bad = diff[t, b]
+            if bad.any():
+                flips += int(bad.sum())
+                margins.append(float(refz[t, b][bad].abs().max()))
+                clean[b] = False
+                break
+    rec = torch.stack(out['img']).cpu()
+    refr = torch.stack(ref['img'])
+    rec_err = float((rec[:, clean] - refr[:, clean]).abs().max()) if clean.any() else float('nan')
+    dps = max(abs(O.psnr(a, pi) - O.psnr(b, pi)) for a, b in zip(rec, refr))
+    return {'sample': 'eval, parity precision, B={} M={} T=16 vs oracle/drasic_oracle.py'.format(n_img, arm.nodes),
+            'code_symbols': int(refc.numel()), 'code_mismatches': int(diff.sum()),
+            'code_flips': flips, 'images_with_a_flip': int((~clean).sum()),
+            'flip_margin_max_abs_z': max(margins) if margins else None,
+            'min_margin': float(refz.abs().min()),
+            'note': 'code_flips = symbols differing at the first differing iteration of an image (later iterations of that image '
+                    'cascade and are counted only in code_mismatches); flip_margin = |z_oracle| of those symbols',
+            'recon_max_abs_err': rec_err, 'recon_err_over': 'images without a flip', 'psnr_max_abs_diff_db': dps,
+            'loss_abs_diff': abs(float(out['loss']) - float(ref['loss']))}
+
+
+def multi_gpu_parity(arm):
+    """all-reduced gradients and loss of a global batch sharded over the ranks against the same
+    batch computed on one GPU (every rank computes both; rank 0 reports)"""
+    import torch
+    from engine.dist import allreduce_gradients, allreduce_scalar_mean, shard_range
+    config = arm.config
+    arm._apply_config()
+    world, rank, dev = arm.world, arm.rank, arm.dev
+    Bg, T = 16 * world, 4
+    g = torch.Generator().manual_seed(77)
+    img = torch.rand(Bg, arm.channels, 32, 32, generator=g)
+    label = torch.randint(0, arm.nodes, (Bg,), generator=g)
+    noise = torch.rand(T, Bg, 8, 4, 4, generator=g)
+    lo, hi = shard_range(Bg, rank, world)
+    model = arm.model
+    model.train(True)
+    config.PARAM['num_iter'] = T
+    try:
+        model.zero_grad(set_to_none=True)
+        out = model({'img': img[lo:hi].to(dev), 'label': label[lo:hi].to(dev)}, noise=noise[:, lo:hi].to(dev))
+        out['loss'].backward()
+        allreduce_gradients(arm.params, hi - lo, Bg)
+        loss = float(allreduce_scalar_mean(out['loss'], hi - lo, Bg))
+        sharded = [p.grad.clone() for p in arm.params]
+        model.zero_grad(set_to_none=True)
+        o1 = model({'img': img.to(dev), 'label': label.to(dev)}, noise=noise.to(dev))
+        o1['loss'].backward()
+        worst = 0.0
+        for a, p in zip(sharded, arm.params):
+            den = float(p.grad.norm())
+            worst = max(worst, float((a - p.grad).norm()) / den if den > 0 else float(a.abs().max()))
+        model.zero_grad(set_to_none=True)
+    finally:
+        config.PARAM['num_iter'] = T_ITER
+    return {'sample': 'training mode (given binarizer noise), global batch {} over {} ranks, M={} T={}: NCCL all-reduced '
+                      'gradients (weights n_local/N_global) vs the whole batch on one GPU'.format(Bg, world, arm.nodes, T),
+            'worst_rel': worst, 'dloss': abs(loss - float(o1['loss'])),
+            'tolerance': 'fp16 backward GEMMs scale each rank\'s gradient planes by its own power of two: 2e-3 relative '
+                         'per tensor (tests/test_gpu_multi.py)'}
 
 
 def run_ours(args):
@@ -175,221 +495,60 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    from oracle import drasic_oracle as O          # used only by the cpu_baseline leg at the end
     import config
     config.init()
-    config.PARAM.update(device='cuda', data_name='CIFAR10', precision=args.precision, pack_mode='reference',
-                        grad_precision=args.grad_precision)
-    config.PARAM['control'] = {'normalization': 'none', 'activation': 'tanh', 'num_iter': str(T_ITER),
-                               'code_size': '8', 'num_node': str(M_NODES)}
-    import utils
-    utils.process_control_name()
-    import models
-    torch.manual_seed(0)
-    model = models.dist_codec().to(dev)
-    train = args.mode == 'train'
-    model.train(train)
-    B = args.batch
-    # each rank codes its own shard of the global batch (samples are independent: no data-path collective)
-    img_h, label_h = synth_batch(B, 1000 + rank)
-    from engine.dist import allreduce_gradients, owned_nodes, reduce_source_sharded
-    by_source = args.shard == 'source' and world > 1
-    if by_source:
-        # SURVEY 8(e) partitioning for M >= G: this rank holds the samples (and trains the encoders) of its own nodes
-        mine = owned_nodes(M_NODES, rank, world)
-        if not mine:
-            raise SystemExit('--shard source needs at least one node per rank ({} nodes, {} ranks)'.format(M_NODES, world))
-        label_h = torch.tensor(mine)[label_h % len(mine)]
-    img, label = img_h.to(dev), label_h.to(dev)
-    params = [p for p in model.parameters()]
-    from engine.optim import FusedAdam
-    opt = FusedAdam(params, lr=1e-3) if train else None               # train_model.py:161 (optim.Adam)
+    arm = Arm(dev, rank, world, precision=args.precision, grad_precision=args.grad_precision, shard=args.shard)
+    B, K, W = args.batch, args.steps, args.warmup
+    main_mode = 'train' if args.mode in ('all', 'train') else 'eval'
+    everything = args.mode == 'all'
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step(inp):
-        """one pass of the hot path through the public API"""
-        if train:
-            opt.zero_grad(set_to_none=True)
-            out = model(inp)                                          # train_model.py:113
-            out['loss'].backward()                                    # :115  (backward-through-time kernels)
-            if by_source:
-                reduce_source_sharded(model, B, world * B, rank, world)   # joint decoder only
-            else:
-                allreduce_gradients(params, B, world * B)             # replaces DataParallel's reduce (:60)
-            opt.step()                                                # :116
-        else:
-            with torch.no_grad():
-                out = model(inp)
-        return out
-
-    config.PARAM['cuda_graph'] = args.graph
-    resident = {'img': img, 'label': label}
-    for _ in range(max(args.warmup, 3)):
-        step(resident)
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step(resident)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    eng = model._engine
-    launches = eng.launches + (opt.launches if train else 0)
-    clocks = sampler.stop() if sampler else None
-
-    # ---- per-kernel timing on the launching stream (separate eager pass, CUDA events around every launch)
-    config.PARAM['cuda_graph'] = False
-    eng.profile = []
-    for _ in range(2):
-        step(resident)
-    torch.cuda.synchronize()
-    prof = eng.profile_summary()
-    eng.profile = None
-    config.PARAM['cuda_graph'] = args.graph
-
-    # ---- end to end through the public API with host buffers (H2D of inputs, D2H of loss + codes)
-    pin_img, pin_label = img_h.pin_memory(), label_h.pin_memory()
-
-    def e2e_step():
-        out = step({'img': pin_img.to(dev, non_blocking=True), 'label': pin_label.to(dev, non_blocking=True)})
-        return out['loss'].item(), out['code'][-1].nbytes
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-
-    # ---- the same step at 'fast' precision (single fp16 operands + tanh.approx, stated tolerance), for reference
-    fast_ms = float('nan')
-    if args.precision == 'parity' and not args.no_fast:
-        config.PARAM['precision'] = 'fast'
-        for _ in range(3):
-            step(resident)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
-            step(resident)
-        f1.record()
-        barrier()
-        fast_ms = f0.elapsed_time(f1) / args.steps
-        config.PARAM['precision'] = args.precision
-
-    t_ms = torch.tensor([ms, e2e_s * 1e3, fast_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, fast_ms = t_ms.tolist()
+    main = arm.measure(main_mode, B, K, W, graph=args.graph, fast=not args.no_fast, clocks=True)
+    line = {'metric': METRIC, 'n_gpus': world, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'data': 'synthetic'}
+    line.update(arm.record(main))
+    extras = {}
+    k2 = max(3, min(K, 10))
+    if everything:
+        arm.release()
+        extras['eval'] = arm.record(arm.measure('eval', B, K, W, fast=not args.no_fast))
+        b128 = {}
+        for mode in ('train', 'eval'):
+            arm.release()
+            b128[mode] = arm.record(arm.measure(mode, 128, k2, W, graph=(mode == 'eval')))
+        extras['b128'] = b128
+        arm.release()
+        if args.precision == 'parity':
+            gp = Arm(dev, rank, world, precision='parity', grad_precision='parity', shard=args.shard)
+            extras['grad_parity'] = gp.record(gp.measure('train', B, max(2, min(K, 5)), W))
+            gp.release()
+            del gp
+    if world > 1 and (everything or args.multi_parity):
+        arm.release()
+        extras['multi_gpu_parity'] = multi_gpu_parity(arm)
+    if world == 1 and not args.no_cpu:
+        arm.release()
+        extras['parity'] = parity_check(arm, PARITY_SAMPLE)
+    if everything:
+        arm.release()
+        c1 = Arm(dev, rank, world, channels=1, nodes=1, precision=args.precision)
+        extras['config1'] = c1.record(c1.measure('eval', 64, k2, W, graph=True))
+        if world == 1 and not args.no_cpu:
+            extras['config1']['parity'] = parity_check(c1, 64)
+        c1.release()
+        del c1
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    sust, burst, hbm, how = measured_peaks()
-    gate = [(k, v) for k, v in prof.items() if k.split('_')[0] in ('gates', 'dgrad', 'wgrad')]
-    g_n = sum(v[0] for _, v in gate)
-    g_ms = sum(v[1] for _, v in gate)
-    g_fl = sum(v[2] for _, v in gate)
-    all_ms = sum(v[1] for v in prof.values())
-    achieved = g_fl / (g_ms * 1e-3) / 1e12
-    mma_per_mac = 3 if args.precision == 'parity' else 1
-    flop_per_img = FLOP_PER_IMG_FWD * (3 if train else 1)
-    # DRAM bytes per gate-kernel launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full capture
-    # committed as profiles/r1_ncu_full_gates_parity_final_summary.csv (eval forward, 1024 slots): one iteration t >= 1 moves
-    # E1 795 + E2 400 + E3 155 + D1 315 + D2 1192 + D3 763 MB = 3620 MB over 6 launches
-    traffic, traffic_note = None, 'no ncu capture for this configuration'
-    if args.precision == 'parity' and B == 1024:
-        traffic = 3620e6 / 6
-        traffic_note = ('forward gate kernels only, average per launch, from profiles/r1_ncu_full_gates_parity_final_summary.csv; '
-                        'compulsory bytes of the same six launches: 3.1 GB (x, h hi+lo in; c in/out; h, consumer copy out; weights) -> 1.17x')
-    sd = {k: v for k, v in model.named_parameters()}
-    line = {
-        'metric': METRIC, 'value': world * B / ms * 1e3, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None,
-        'dtype': ('f16x2-split forward (fp32-grade, fp32 accumulate)' if args.precision == 'parity' else 'f16 forward (fp32 accumulate)')
-                 + (', f16 backward GEMMs with exact per-tensor power-of-two scaling, fp32 gradients' if train else ''),
-        'data': 'synthetic',
-        'config': {'workload': workload_name(args.mode), 'batch_per_gpu': B,
-                   'global_batch': world * B, 'num_node': M_NODES, 'num_iter': T_ITER, 'code_size': 8,
-                   'precision': args.precision, 'cuda_graph': args.graph,
-                   'cta_pair': 'cta_group::2 pairs on every gate / dgrad / wgrad GEMM (pair units formed inside each node)',
-                   'parallelism': (('dp{}: sharded by source (rank r owns nodes r mod N), one NCCL all-reduce of the joint '
-                                    "decoder's gradients per step" if by_source else
-                                    'dp{}: batch sharded, one NCCL all-reduce of gradients per step').format(world) if train
-                                   else 'batch-sharded replicas x{} (no collective)'.format(world)),
-                   'l2': 'per-step working set (activations+state, ~1 MB/image) exceeds the 126 MB L2'},
-        'e2e': {'value': world * B / e2e_ms * 1e3, 'unit': 'images/s',
-                'h2d_bytes_per_step': B * CHANNELS * 32 * 32 * 4 + B * 8,
-                'd2h_bytes_per_step': T_ITER * B * 128 * 4 + 4 + B * 8,
-                'api': 'models.dist_codec() Model.forward (+ loss.backward(), engine.optim.FusedAdam step when training) on pinned host '
-                       'img/label; loss.item() and the emitted codes read back'},
-        'gpu_launches': launches * args.steps,
-        'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel<gates> + conv_gemm_kernel<dgrad> + wgrad_kernel (6 layers x 16 iterations)'
-                     if train else 'conv_gemm_kernel<gates> (6 layers x 16 iterations)',
-                     'achieved': achieved, 'peak': sust, 'unit': 'TFLOP/s', 'frac': achieved / sust,
-                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained ({}); burst {}'.format(how, burst),
-                     'traffic': traffic, 'traffic_note': traffic_note, 'launches': g_n, 'avg_launch_ms': g_ms / max(g_n, 1),
-                     'share_of_step': g_ms / all_ms, 'tensor_mma_per_algorithmic_mac': mma_per_mac,
-                     'per_kind_tflops': {kk: sum(v[2] for k, v in gate if k.startswith(kk)) / max(1e-9, sum(v[1] for k, v in gate if k.startswith(kk))) / 1e9
-                                         for kk in ('gates', 'dgrad', 'wgrad') if any(k.startswith(kk) for k, _ in gate)},
-                     'forward_mma_per_algorithmic_mac': mma_per_mac},
-        'kernels_ms_per_step': {k: v[1] / 2 for k, v in sorted(prof.items())},
-        'algorithmic_tflops': world * B / ms * 1e3 * flop_per_img / 1e12,
-    }
-    line['roofline']['issued_mma_tflops'] = (prof_gate_tflops(gate, mma_per_mac))
-    line['roofline']['issued_mma_frac'] = line['roofline']['issued_mma_tflops'] / sust
-    if fast_ms == fast_ms:
-        line['fast_precision'] = {'value': world * B / fast_ms * 1e3, 'unit': 'images/s', 'ms_per_step': fast_ms,
-                                  'dtype': 'f16 forward (fp32 accumulate, tanh.approx)' + (', f16 backward GEMMs' if train else ''),
-                                  'tolerance': 'code mismatch rate < 2e-3 in the first iterations, PSNR within 0.05 dB per rate '
-                                               '(tests/test_gpu_loop.py::test_fast_precision_stated_tolerance)'}
-    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
+    line.update(extras)
+    # ---- CPU baseline (oracle port) on the same bounded sample `--impl reference` times, rank 0 at N=1 only
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        nb = 96 if train else 512                                   # ~10-15 s of CPU work on 16 cores
-        sdc = {k: v.detach().cpu().clone().requires_grad_(train) for k, v in sd.items()}
-        ci, cl = synth_batch(nb, 7)
-        with torch.no_grad():
-            O.codec_forward(sdc, ci[:8], cl[:8], 2, M_NODES)
-        t0 = time.perf_counter()
-        if train:
-            O.codec_forward(sdc, ci, cl, T_ITER, M_NODES, training=True)['loss'].backward()
-        else:
-            with torch.no_grad():
-                O.codec_forward(sdc, ci, cl, T_ITER, M_NODES)
-        dt = time.perf_counter() - t0
-        line['cpu_baseline'] = {'value': nb / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                'sample': 'oracle codec_forward{} B={} M=8 T=16, one pass ({:.1f} s)'.format(
-                                    ' + backward (BPTT)' if train else ' eval', nb, dt)}
-    # ---- parity of this build against the CPU oracle on a small sample of the same workload (eval mode, T=16)
-    if world == 1 and not args.no_cpu:
-        pi, pl = synth_batch(16, 11)
-        sdc = {k: v.detach().cpu() for k, v in sd.items()}
-        with torch.no_grad():
-            ref = O.codec_forward(sdc, pi, pl, T_ITER, M_NODES)
-            was = model.training
-            model.train(False)
-            prec = config.PARAM['precision']
-            config.PARAM['precision'] = 'parity'
-            out = model({'img': pi.to(dev), 'label': pl.to(dev)})
-            config.PARAM['precision'] = prec
-            model.train(was)
-        refc = torch.stack(ref['code_pm1'])
-        mism = int((out['code_pm1'].cpu() != refc).sum())
-        rec_err = float((torch.stack(out['img']).cpu() - torch.stack(ref['img'])).abs().max())
-        dps = max(abs(O.psnr(a.cpu(), pi) - O.psnr(b, pi)) for a, b in zip(out['img'], ref['img']))
-        line['parity'] = {'sample': 'eval, parity precision, B=16 M=8 T=16 vs oracle/drasic_oracle.py', 'code_mismatches': mism,
-                          'code_symbols': int(refc.numel()), 'recon_max_abs_err': rec_err, 'psnr_max_abs_diff_db': dps}
+        sd = {k: v for k, v in arm.model.named_parameters()}
+        v, dt, cores, what = cpu_time(main_mode, 1, 0, sd=sd)
+        line['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': what}
+        if everything:
+            v, dt, cores, what = cpu_time('eval', 1, 0, sd=sd)
+            line['eval']['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': what}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -403,19 +562,22 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='images per GPU per step')
     ap.add_argument('--precision', default='parity', choices=['parity', 'fast'])
-    ap.add_argument('--mode', default='train', choices=['train', 'eval'],
-                    help='train: forward + backward-through-time + all-reduce + Adam step (BASELINE configs[1]); '
+    ap.add_argument('--mode', default='all', choices=['all', 'train', 'eval'],
+                    help='all: the training step (BASELINE configs[1]) as the line\'s value plus eval / b128 / config1 / '
+                         'grad_parity / parity records; train: forward + backward-through-time + all-reduce + Adam step only; '
                          'eval: encode+decode only')
     ap.add_argument('--grad-precision', default='fp16', choices=['fp16', 'parity'])
-    ap.add_argument('--graph', action='store_true',
-                    help='replay one captured CUDA graph per step instead of launching eagerly (measured slower: the '
-                         'loop is GPU-bound at >100 us per launch and a static graph needs worst-case node padding)')
-    ap.add_argument('--shard', default='batch', choices=['batch', 'source'],
+    ap.add_argument('--graph', action='store_true', help='replay one captured CUDA graph per step instead of launching eagerly')
+    ap.add_argument('--shard', default='auto', choices=['auto', 'batch', 'source'],
                     help="N>1 training: 'batch' = every rank sees all nodes, all gradients all-reduced; 'source' = rank r "
-                         "owns nodes j = r mod N and their samples, only the joint decoder's gradients are all-reduced")
+                         "owns nodes j = r mod N and their samples, only the joint decoder's gradients are all-reduced; "
+                         "'auto' = source when there are at least as many nodes as ranks")
+    ap.add_argument('--multi-parity', action='store_true', help='N>1: run the in-line gradient parity check in train / eval mode too')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-fast', action='store_true', help='skip the secondary fast-precision measurement')
     args = ap.parse_args()
+    if args.shard == 'auto':
+        args.shard = 'batch'
     if args.impl == 'reference':
         run_reference(args)
     else:

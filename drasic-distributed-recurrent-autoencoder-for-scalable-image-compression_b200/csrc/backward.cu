@@ -377,6 +377,8 @@ __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdPa
       float direct;
       if (p.loss_kind == LOSS_MAE) direct = (r_c > im_c) ? 1.0f : ((r_c < im_c) ? -1.0f : 0.0f);
       else if (p.loss_kind == LOSS_MSE) direct = 2.0f * (r_c - im_c);
+      // torch's binary_cross_entropy backward: (input - target) / max((1 - input) * input, 1e-12), also where the
+      // forward's log clamp at -100 is active (the forward refuses inputs outside [0, 1], see tail_head_kernel)
       else direct = (r_c - im_c) / fmaxf(r_c * (1.0f - r_c), 1e-12f);
       const float G = ga_c + direct * p.loss_scale;
       p.gacc[gi] = G;

@@ -216,7 +216,9 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   p.bw = bw; p.bh = bh; p.bn = bn;
   p.n_mtiles = static_cast<int>(static_cast<long long>(B) * H * W / 128);
   p.n_ntiles = 4 * Co / a->block_n;
+#ifdef DRASIC_DIAG
   { static const int ord = getenv("DRASIC_TILE_ORDER") ? atoi(getenv("DRASIC_TILE_ORDER")) : 0; p.tile_order = ord; }
+#endif
   p.has_hidden = a->has_state ? 1 : 0;
   p.has_cell = a->has_state ? 1 : 0;
   p.next_mode = a->next_mode;
@@ -346,7 +348,9 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   // without a dH_{t-1} destination (t == 0) only the dX columns are computed
   const int Nuse = a->dhrec_out ? Nout : Cin;
   p.n_ntiles = (Nuse + 255) / 256;
+#ifdef DRASIC_DIAG
   { static const int ord = getenv("DRASIC_TILE_ORDER") ? atoi(getenv("DRASIC_TILE_ORDER")) : 0; p.tile_order = ord; }
+#endif
   p.n_groups = a->n_groups; p.group_mtile_end = a->group_mtile_end;
   p.group_mtile_start = a->group_mtile_start; p.group_unit_end = a->group_unit_end; p.group_img_end = a->group_img_end;
   p.n_munits = a->n_units;

@@ -326,7 +326,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailPa
           const float e = __fsub_rn(r, im_c[u]);
           if (p.loss_kind == LOSS_MAE) pa += fabsf(e);
           else if (p.loss_kind == LOSS_MSE) pa = fmaf(e, e, pa);
-          else {  // bce with torch's log clamp at -100
+          else if (r < 0.0f || r > 1.0f) {
+            // F.binary_cross_entropy (dist_codec.py:26) raises for an input outside [0, 1]; the un-clamped cumulative
+            // reconstruction leaves it after a few iterations.  The sum is poisoned here (NaN) and Model.forward raises.
+            pa = __int_as_float(0x7fc00000);
+          } else {  // bce with torch's log clamp at -100
             const float lr = fmaxf(logf(r), -100.0f), l1r = fmaxf(logf(1.0f - r), -100.0f);
             pa -= im_c[u] * lr + (1.0f - im_c[u]) * l1r;
           }

@@ -6,7 +6,6 @@ ConvLSTM weights if they changed, then launch per iteration
     E1 E2 E3 (gate kernels, grouped by node) -> bottleneck -> D1 D2 D3 (gate kernels) -> tail/head
 on the caller's CUDA stream through the C ABI.  torch is used for device memory and streams only.
 """
-import os
 
 import numpy as np
 import torch
@@ -15,6 +14,14 @@ from . import binding as B
 
 PAD = 4        # slots per node are padded to a multiple of 4 images (one 64-pixel wgrad K block at the 4x4 layers)
 TOTAL_PAD = 8  # ... and the whole batch to 8 (one 128-pixel M tile at the 4x4 layers)
+
+
+def pads_for(H, W, training):
+    """(slots-per-node multiple, whole-batch multiple) for H x W images: the smallest layer (E3 / D1, H/8 x W/8) has
+    hw pixels per image, a wgrad K block is 64 pixels and an M tile 128.  32x32 images give (4, 8); 16x16 images
+    (4 pixels per image there) need node ranges of 16 images when a backward will run."""
+    hw = max(1, (H // 8) * (W // 8))
+    return (max(PAD, -(-64 // hw)) if training else 1), max(TOTAL_PAD, -(-128 // hw))
 
 # (name, Cin, Co, spatial divisor, in_order, out_order, next_mode, next_f32)
 ENC_LAYERS = (('E1', 128, 128, 2, B.ORDER_QUAD, B.ORDER_IDENT, B.NEXT_DOWN, 0),
@@ -27,7 +34,7 @@ ENC_IDX = {'E1': 2, 'E2': 4, 'E3': 6}   # nn.Sequential indices, dist_codec.py:7
 DEC_IDX = {'D1': 1, 'D2': 3, 'D3': 5}   # dist_codec.py:88-104
 
 
-def plan_arrays(label_host, num_node, pad_total=None, pad=None):
+def plan_arrays(label_host, num_node, pad_total=None, pad=None, total_pad=TOTAL_PAD):
     """node-sort one batch: (perm [B_pad] slot -> original index or -1, exclusive end slot per node)"""
     label_host = np.asarray(label_host).astype(np.int64).reshape(-1)
     if label_host.size and (label_host.min() < 0 or label_host.max() >= num_node):
@@ -38,9 +45,9 @@ def plan_arrays(label_host, num_node, pad_total=None, pad=None):
     pad = PAD if pad is None else int(pad)
     padded = (counts + pad - 1) // pad * pad
     ends = np.cumsum(padded)
-    need = (int(ends[-1]) + TOTAL_PAD - 1) // TOTAL_PAD * TOTAL_PAD
+    need = (int(ends[-1]) + total_pad - 1) // total_pad * total_pad
     B_pad = need if pad_total is None else int(pad_total)
-    if B_pad < need or B_pad % TOTAL_PAD:
+    if B_pad < need or B_pad % total_pad:
         raise ValueError('Not valid pad_total')
     perm = np.full(B_pad, -1, dtype=np.int32)
     starts = ends - padded
@@ -56,16 +63,17 @@ def plan_arrays(label_host, num_node, pad_total=None, pad=None):
     return perm, ends.astype(np.int32), counts
 
 
-def worst_case_pad(B, num_node, pad=PAD):
+def worst_case_pad(B, num_node, pad=PAD, total_pad=TOTAL_PAD):
     """slot count that fits any assignment of B samples to num_node nodes whose ranges are multiples of `pad`"""
-    return (B + (pad - 1) * min(num_node, B) + TOTAL_PAD - 1) // TOTAL_PAD * TOTAL_PAD
+    return (B + (pad - 1) * min(num_node, B) + total_pad - 1) // total_pad * total_pad
 
 
 class BatchPlan(object):
     """Node-sorted, padded slot layout of one batch.  With `static_hw` the plan owns fixed device
     buffers (worst-case slot count) that update() refreshes in place -- what a captured CUDA graph reads."""
 
-    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None, pad=None, hws=None):
+    def __init__(self, label_host, num_node, device, pad_total=None, static_hw=None, pad=None, hws=None,
+                 total_pad=TOTAL_PAD):
         """pad: slots per node are a multiple of this; PAD (4) when backward will run (wgrad K blocks of 4 images
         at the 4x4 layers must not mix two nodes), 1 for inference (shared M tiles are handled by row masks).
         hws: pixels per image of the layers that will read this plan; their unit / K-block tables travel to the
@@ -74,7 +82,8 @@ class BatchPlan(object):
         self.num_node, self.device = num_node, device
         self.pad_total = pad_total
         self.pad = PAD if pad is None else int(pad)
-        perm, ends, counts = plan_arrays(label_host, num_node, pad_total, self.pad)
+        self.total_pad = int(total_pad)
+        perm, ends, counts = plan_arrays(label_host, num_node, pad_total, self.pad, self.total_pad)
         self.B, self.B_pad = int(np.asarray(label_host).size), int(perm.size)
         self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
         self._kb_end, self._units = {}, {}
@@ -112,7 +121,11 @@ class BatchPlan(object):
         return self._kb_end[hw]
 
     def _kb_host(self, hw):
-        return ((self.group_img_end_host.astype(np.int64) * hw) // 64).astype(np.int32)
+        px = self.group_img_end_host.astype(np.int64) * hw
+        if self.pad > 1 and np.any(px % 64):
+            # a 64-pixel K block of the wgrad GEMM would mix the samples of two nodes (their weights differ)
+            raise ValueError('Not valid batch plan: node ranges of {} pixels per image are not K-block aligned'.format(hw))
+        return (px // 64).astype(np.int32)
 
     def _units_host(self, hw, pair):
         """per node: first / end M tile (128 pixels) overlapping its slot range -- neighbours may share a tile
@@ -142,7 +155,7 @@ class BatchPlan(object):
 
     def update(self, label_host):
         """refresh the device buffers in place for a new batch of the same size"""
-        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad, self.pad)
+        perm, ends, counts = plan_arrays(label_host, self.num_node, self.B_pad, self.pad, self.total_pad)
         if int(np.asarray(label_host).size) != self.B:
             raise ValueError('Not valid batch size for this static plan')
         self._frozen = True
@@ -188,11 +201,16 @@ class CodecEngine(object):
             raise ValueError('Not valid grad_precision')
         if cta_pair not in ('auto', 'on', 'off'):
             raise ValueError('Not valid cta_pair')
+        self._ctor = dict(num_channel=num_channel, code_size=code_size, num_node=num_node, separate=separate,
+                          precision=precision, grad_precision=grad_precision, cta_pair=cta_pair)
+        # counts the forwards that saved state for a backward, over this engine and the engines cloned from it (one
+        # per captured graph): whoever holds packed weight planes re-packs when it has moved (see _stale below)
+        self.train_count = [0]
         self.cta_pair = cta_pair  # CTA pairs (cta_group::2) for the gate / dgrad / wgrad GEMMs
         # wgrad pair tiles: 1 = 256 columns (default), 2 = 512 columns where a node has >= 256 K blocks.  The wide tiles
         # move fewer bytes per MMA but leave 9..180 work units for 74 CTA pairs; measured per step at B=1024 they are
         # slower on every layer (D1 7.8 vs 4.9 ms, E1 10.0 vs 8.5, D2 20.1 vs 17.9, D3 8.7 vs 8.5)
-        self.wgrad_pair_mode = int(os.environ.get('DRASIC_WGRAD_PAIR', '1'))
+        self.wgrad_pair_mode = 1      # (an attribute, not an environment knob: tests set it to 2)
         self.gsplit = 1 if grad_precision == 'parity' else 0
         self.C, self.code, self.M, self.separate = num_channel, code_size, num_node, separate
         self.split = 1 if precision == 'parity' else 0
@@ -209,9 +227,17 @@ class CodecEngine(object):
         # cache: a forward that saves state for backward always re-packs (the weights are about to change
         # anyway) and leaves the cache marked stale for whatever forward comes next.
         self._stale = False
+        self._seen_train = 0
         self._repack = False
-        self.overlap_wgrad = os.environ.get('DRASIC_OVERLAP_WGRAD', '1') != '0'   # wgrad GEMMs on a side stream
+        self.overlap_wgrad = True   # wgrad GEMMs on a side stream
         self.profile = None  # set to [] to collect (label, flops, start_event, end_event) per launch
+
+    def clone(self):
+        """an engine with the same configuration and its own arenas / packed weight planes (a captured CUDA graph
+        bakes device addresses in: it must own every buffer it replays on)"""
+        e = CodecEngine(**self._ctor)
+        e.train_count = self.train_count
+        return e
 
     def release(self):
         """free the device arenas and caches of this engine"""
@@ -378,7 +404,8 @@ class CodecEngine(object):
         if plan is None:
             if label_host is None:
                 label_host = label.detach().cpu().numpy()      # the one host sync per forward
-            plan = BatchPlan(label_host, self.M, dev, pad=PAD if save_for_backward else 1,
+            pad, total_pad = pads_for(H, W, save_for_backward)
+            plan = BatchPlan(label_host, self.M, dev, pad=pad, total_pad=total_pad,
                              hws=((H // 2) * (W // 2), (H // 4) * (W // 4), (H // 8) * (W // 8)))
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -389,7 +416,6 @@ class CodecEngine(object):
             if ni.size != self.M or ni.min() < 0:
                 raise ValueError('Not valid node_iters')
             group_iters = torch.from_numpy(ni).to(dev)
-        A = self._get_arena(Bp, H, W, dev, T if save_for_backward else 0)
         keep = save_for_backward
         want_z = want_z or keep
         code, hc, wc = self.code, H // 8, W // 8
@@ -407,7 +433,7 @@ class CodecEngine(object):
         enc_pref = ['model.encoder.{}'.format(j) for j in range(self.M)]
         dec_pref = ['model.decoder.{}'.format(j) for j in range(self.M)] if self.separate else ['model.decoder']
         layers = []
-        self._repack = bool(save_for_backward or self._stale)
+        self._repack = bool(save_for_backward or self._stale or self._seen_train != self.train_count[0])
         for (name, cin, co, div, io, oo, nmode, nf32) in ENC_LAYERS + DEC_LAYERS:
             is_enc = name[0] == 'E'
             prefs = enc_pref if is_enc else dec_pref
@@ -432,8 +458,12 @@ class CodecEngine(object):
         self._repack = False
         self._stale = bool(save_for_backward)
         self._last_layers = layers      # (tests / tools: which layers ran as CTA pairs)
+        if save_for_backward:
+            self.train_count[0] += 1
+        self._seen_train = self.train_count[0]
         if pack_only:
             return None
+        A = self._get_arena(Bp, H, W, dev, T if save_for_backward else 0)
 
         def stack(keys):
             return torch.stack([sd[k].detach().float().reshape(sd[k].shape[0], -1) for k in keys]).contiguous()
@@ -569,7 +599,8 @@ class CodecEngine(object):
         T, Bn = int(bits.shape[0]), int(bits.shape[1])
         if label_host is None:
             label_host = label.detach().cpu().numpy()
-        plan = BatchPlan(label_host, self.M, dev, pad=1, hws=(hc * wc * 16, hc * wc * 4, hc * wc))
+        plan = BatchPlan(label_host, self.M, dev, pad=1, total_pad=pads_for(H, W, False)[1],
+                         hws=(hc * wc * 16, hc * wc * 4, hc * wc))
         Bp = plan.B_pad
         stream = torch.cuda.current_stream(dev).cuda_stream
         self.launches = 0
@@ -583,7 +614,7 @@ class CodecEngine(object):
         def stack(keys):
             return torch.stack([sd[k].detach().float().reshape(sd[k].shape[0], -1) for k in keys]).contiguous()
         layers = []
-        self._repack = bool(self._stale)
+        self._repack = bool(self._stale or self._seen_train != self.train_count[0])
         for (name, cin, co, div, io, oo, nmode, nf32) in DEC_LAYERS:
             h, w = H // div, W // div
             n_mtiles = Bp * h * w // 128
@@ -906,7 +937,12 @@ class GraphedCodec(object):
 
     def __init__(self, engine, sd, batch, hw, num_iter, training=False, with_backward=False, loss_kind='mae',
                  device=None):
-        self.eng, self.sd, self.T = engine, sd, int(num_iter)
+        # The graph bakes in the addresses of the arena, the backward work buffers and the packed weight planes.  The
+        # engine keeps one slot of each and replaces it when a call with another batch size / mode comes along, so the
+        # graph replays on an engine of its own that nothing else ever calls.
+        self.parent = engine
+        self.eng, self.sd, self.T = engine.clone(), sd, int(num_iter)
+        engine = self.eng
         self.training, self.with_backward, self.loss_kind = training, with_backward, loss_kind
         H, W = hw
         dev = device or next(iter(sd.values())).device
@@ -916,9 +952,10 @@ class GraphedCodec(object):
             if training else None
         hws = sorted({(H // d) * (W // d) for d in (2, 4, 8)})
         label0 = np.arange(self.B) % engine.M
-        pad = PAD if with_backward else 1     # inference plans pack the nodes back to back: no worst-case slack at all
-        self.plan = BatchPlan(label0, engine.M, dev, pad_total=worst_case_pad(self.B, engine.M, pad), static_hw=hws,
-                              pad=pad)
+        # inference plans pack the nodes back to back: no worst-case slack at all
+        pad, total_pad = pads_for(H, W, with_backward)
+        self.plan = BatchPlan(label0, engine.M, dev, pad_total=worst_case_pad(self.B, engine.M, pad, total_pad),
+                              static_hw=hws, pad=pad, total_pad=total_pad)
         self.graph = None
         self.out = self.grads = None
         side = torch.cuda.Stream(device=dev)
@@ -943,7 +980,9 @@ class GraphedCodec(object):
         return tuple(v._version for v in self.sd.values())
 
     def _refresh_weights(self):
-        if self._versions() == self._seen and not self.eng._stale:
+        # parameter versions, plus the family's count of training forwards: fused optimizers update parameters in
+        # place without bumping Tensor._version, so any training step since the last pack makes the planes suspect
+        if self._versions() == self._seen and self._seen_train == self.eng.train_count[0] and not self.eng._stale:
             return
         # a parameter changed since capture: re-pack eagerly into the buffers the graph reads
         self.eng.force_pack = True
@@ -952,10 +991,10 @@ class GraphedCodec(object):
                 self.eng.forward(self.sd, self.img, None, 0, training=False, plan=self.plan, pack_only=True)
         finally:
             self.eng.force_pack = False
-        self._seen = self._versions()
+        self._seen, self._seen_train = self._versions(), self.eng.train_count[0]
 
     def _run(self):
-        self._seen = self._versions()
+        self._seen, self._seen_train = self._versions(), self.eng.train_count[0]
         with torch.no_grad():
             self.out = self.eng.forward(self.sd, self.img, None, self.T, training=self.training, noise=self.noise,
                                         loss_kind=self.loss_kind, save_for_backward=self.with_backward,
@@ -975,5 +1014,7 @@ class GraphedCodec(object):
         if not self.with_backward:
             self._refresh_weights()
         self.graph.replay()
-        self.eng.launches = self.launches
+        if self.with_backward:
+            self.eng.train_count[0] += 1        # (the capture-time forward counted itself once; replays count here)
+        self.eng.launches = self.parent.launches = self.launches
         return self.out, self.grads

@@ -12,7 +12,9 @@ With M >= world sources the batch can instead be sharded *by source* (`source_sh
 sample of the nodes j with j % world == r, so an encoder's gradient exists on exactly one rank and only the
 shared decoder's gradients (99 MB of the 326 MB at M=8) are all-reduced (`reduce_source_sharded`); the
 per-node parameters of the other ranks' nodes stay untouched locally and are refreshed from their owners
-before a checkpoint or an evaluation on the whole model (`sync_node_parameters`)."""
+before an evaluation on the whole model (`sync_node_parameters`) and, together with the owners' optimizer state,
+before a checkpoint (`gather_sharded_state`: the reference's checkpoint is single-process and complete,
+train_model.py:87-98)."""
 import re
 
 import torch
@@ -134,3 +136,45 @@ def sync_node_parameters(model, group=None):
             for p in per_node[j]:
                 p.copy_(flat[off:off + p.numel()].view_as(p))      # in place on the parameter: bumps its _version
                 off += p.numel()
+
+
+def gather_sharded_state(model, optimizer=None, group=None):
+    """Make every rank's model -- and optimizer -- complete before a checkpoint of a source-sharded run
+    (`{'model_dict': model.state_dict(), 'optimizer_dict': optimizer.state_dict()}`, train_model.py:87-98 /
+    utils.resume): each node's parameters and the Adam moments / step counts of those parameters are broadcast
+    from the rank that trains the node.  Without it rank 0's checkpoint would hold untrained encoders and no
+    optimizer state for the other ranks' nodes, and a resume would silently restart them.  MANDATORY before
+    `state_dict()` whenever `reduce_source_sharded` is the gradient exchange.  Works for optimizers whose per-
+    parameter state is {'step', 'exp_avg', 'exp_avg_sq'} (torch.optim.Adam, engine.optim.FusedAdam)."""
+    sync_node_parameters(model, group)
+    if optimizer is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    _, per_node = split_parameters(model)
+    for j in sorted(per_node):
+        owner = j % world
+        src = dist.get_global_rank(group, owner) if group is not None else owner
+        ps = per_node[j]
+        dev = ps[0].device
+        # does the owner hold any state yet (it has none before its first step)
+        have = torch.tensor([1.0 if (rank == owner and all(len(optimizer.state[p]) for p in ps)) else 0.0], device=dev)
+        dist.broadcast(have, src=src, group=group)
+        if float(have) == 0.0:
+            continue
+        if rank == owner:
+            steps = [float(optimizer.state[p]['step']) for p in ps]
+            flat = torch.cat([optimizer.state[p][k].reshape(-1).float() for p in ps for k in ('exp_avg', 'exp_avg_sq')] +
+                             [torch.tensor(steps, dtype=torch.float32, device=dev)])
+        else:
+            flat = torch.empty(2 * sum(p.numel() for p in ps) + len(ps), dtype=torch.float32, device=dev)
+        dist.broadcast(flat, src=src, group=group)
+        if rank == owner:
+            continue
+        off = 0
+        steps = flat[-len(ps):].tolist()
+        for i, p in enumerate(ps):
+            st = optimizer.state[p]
+            for k in ('exp_avg', 'exp_avg_sq'):
+                st[k] = flat[off:off + p.numel()].view_as(p).clone()
+                off += p.numel()
+            st['step'] = torch.tensor(steps[i], dtype=torch.float32)

@@ -272,6 +272,11 @@ class CodecModel(nn.Module):
             loss = CodecEngine.loss_from_acc(res['loss_acc'], img.numel())
             recon, codes, bits = res['recon'], res['codes'], res['bits']
             mse = (res['loss_acc'][:, 1] / float(img.numel())).float()   # per-iteration MSE, stays on the device
+        if config.PARAM['loss_fn'] == 'bce' and bool(torch.isnan(loss.detach())):
+            # F.binary_cross_entropy on the un-clamped cumulative reconstruction (dist_codec.py:26,58) raises as soon
+            # as one element leaves [0, 1]; the kernels poison the loss sum instead and the error surfaces here
+            self._free_hidden()
+            raise RuntimeError('all elements of input should be between 0 and 1')
         T = recon.shape[0]
         output = {'loss': loss, 'img': [recon[t] for t in range(T)], 'code_pm1': codes, 'bits': bits}
         if mse is not None:

@@ -151,3 +151,74 @@ def test_source_sharded_step_matches_single_process(node_decoders):
         results = mgr.dict()
         mp.spawn(_source_worker, args=(world, port, node_decoders, results), nprocs=world, join=True)
         assert results[0] and results[1]
+
+
+def _ckpt_worker(rank, world, port, tmpdir, results):
+    from engine.dist import gather_sharded_state
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        M = 5
+        torch.manual_seed(5)
+        m, ref = _ToyCodec(M, False), _ToyCodec(M, False)
+        ref.load_state_dict(m.state_dict())
+        opt, opt_ref = torch.optim.Adam(m.parameters(), lr=0.05), torch.optim.Adam(ref.parameters(), lr=0.05)
+        g = torch.Generator().manual_seed(6)
+
+        def train(model, optimizer, sharded, steps):
+            for _ in range(steps):
+                x = torch.randn(23, 3, generator=g)
+                lab = torch.randint(0, M, (23,), generator=g)
+                optimizer.zero_grad(set_to_none=True)
+                if sharded:
+                    idx = source_shard(lab, rank, world)
+                    model(x[idx], lab[idx]).backward()
+                    reduce_source_sharded(model, idx.numel(), 23)
+                else:
+                    model(x, lab).backward()
+                optimizer.step()
+        state = g.get_state()
+        train(m, opt, True, 3)
+        g.set_state(state)
+        train(ref, opt_ref, False, 3)
+        # before the gather this rank's copy of the other rank's encoders is untrained and has no Adam state
+        foreign = [p for k, p in m.named_parameters() if k.startswith('model.encoder.') and int(k.split('.')[2]) % world != rank]
+        stale = all(len(opt.state[p]) == 0 for p in foreign)
+        gather_sharded_state(m, opt)                             # MANDATORY before a source-sharded checkpoint
+        ok = stale
+        for p, q in zip(m.parameters(), ref.parameters()):
+            ok = ok and torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+            for k in ('exp_avg', 'exp_avg_sq'):
+                ok = ok and torch.allclose(opt.state[p][k], opt_ref.state[q][k], rtol=1e-5, atol=1e-9)
+            ok = ok and float(opt.state[p]['step']) == float(opt_ref.state[q]['step'])
+        # the reference's checkpoint, written by rank 0 only (train_model.py:87-98), resumes on ONE process to the
+        # same trajectory as the never-sharded run
+        path = os.path.join(tmpdir, 'ckpt.pt')
+        if rank == 0:
+            torch.save({'model_dict': m.state_dict(), 'optimizer_dict': opt.state_dict()}, path)
+        dist.barrier()
+        if rank == 0:
+            ck = torch.load(path, weights_only=False)
+            m2 = _ToyCodec(M, False)
+            m2.load_state_dict(ck['model_dict'])
+            opt2 = torch.optim.Adam(m2.parameters(), lr=0.05)
+            opt2.load_state_dict(ck['optimizer_dict'])
+            state = g.get_state()
+            train(m2, opt2, False, 2)
+            g.set_state(state)
+            train(ref, opt_ref, False, 2)
+            for p, q in zip(m2.parameters(), ref.parameters()):
+                ok = ok and torch.allclose(p, q, rtol=1e-4, atol=1e-6)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_source_sharded_checkpoint_round_trip(tmp_path):
+    """a checkpoint of a source-sharded run must carry every node's trained encoder and Adam moments"""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_ckpt_worker, args=(world, port, str(tmp_path), results), nprocs=world, join=True)
+        assert results[0] and results[1]
