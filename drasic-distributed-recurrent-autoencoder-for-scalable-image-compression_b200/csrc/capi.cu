@@ -161,6 +161,25 @@ static int pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
   return 0;
 }
 
+// position-major region of a conv GEMM launch (see drasic_convlstm_args): validates, builds the (64 ch, 1, 1, 128
+// images) tensor maps of the planes in `hi` / `lo` and fills the unit bookkeeping
+static int setup_pos_tiles(drasic::GateParams& p, const char* who, const int* pos_order, int pos_imgs, int n_groups,
+                           bool pair, int B, int H, int W, int n_units) {
+  p.pos_units = 0; p.pos_upp = 1; p.pos_tile_base = 0; p.pos_order = nullptr;
+  if (pos_imgs == 0) return 0;
+  const int unit_imgs = pair ? 256 : 128;
+  if (pos_imgs < 0 || pos_imgs > B || pos_imgs % unit_imgs || n_groups != 1 || !pos_order)
+    return fail(DRASIC_ERR_INVALID, "%s: pos_imgs=%d needs one group, a pos_order table and a multiple of %d slots <= B_pad", who, pos_imgs, unit_imgs);
+  p.pos_upp = pos_imgs / unit_imgs;
+  p.pos_units = H * W * p.pos_upp;
+  p.pos_tile_base = static_cast<int>(static_cast<long long>(pos_imgs) * H * W / 128);
+  p.pos_order = pos_order;
+  const int rest = p.n_mtiles - p.pos_tile_base;
+  if (n_units != p.pos_units + (pair ? (rest + 1) / 2 : rest))
+    return fail(DRASIC_ERR_INVALID, "%s: n_units=%d does not match pos_imgs=%d", who, n_units, pos_imgs);
+  return 0;
+}
+
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   if (!a) return fail(DRASIC_ERR_INVALID, "convlstm_fwd: null args");
   const int H = a->H, W = a->W, Cin = a->Cin, Co = a->Co, B = a->B_pad;
@@ -228,6 +247,15 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   p.group_mtile_end = a->group_mtile_end;
   p.group_mtile_start = a->group_mtile_start; p.group_unit_end = a->group_unit_end; p.group_img_end = a->group_img_end;
   p.n_munits = a->n_units;
+  if ((rc = setup_pos_tiles(p, "convlstm_fwd", a->pos_order, a->pos_imgs, a->n_groups, pair, B, H, W, a->n_units))) return rc;
+  if (p.pos_units) {
+    if ((rc = make_act_map(&p.tm_xp[0], a->x_hi, B, H, W, Cin, 1, 1, 128))) return rc;
+    if (a->split && (rc = make_act_map(&p.tm_xp[1], a->x_lo, B, H, W, Cin, 1, 1, 128))) return rc;
+    if (a->has_state) {
+      if ((rc = make_act_map(&p.tm_hp[0], a->h_hi, B, H, W, Co, 1, 1, 128))) return rc;
+      if (a->split && (rc = make_act_map(&p.tm_hp[1], a->h_lo, B, H, W, Co, 1, 1, 128))) return rc;
+    }
+  }
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
   return cuda_fail(drasic::launch_convlstm_gates(p, a->split != 0, a->block_n, pair, sms, static_cast<cudaStream_t>(stream)),
@@ -356,6 +384,11 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   p.n_munits = a->n_units;
   p.w_group_rows = Nout; p.n_out = Nuse; p.n_x = Cin; p.dx_mode = a->dx_mode;
   p.dx_out = a->dx_out; p.dhrec_out = a->dhrec_out;
+  if ((rc = setup_pos_tiles(p, "convlstm_bwd_data", a->pos_order, a->pos_imgs, a->n_groups, pair, B, H, W, a->n_units))) return rc;
+  if (p.pos_units) {
+    if ((rc = make_act_map(&p.tm_xp[0], a->dg_hi, B, H, W, Cg, 1, 1, 128))) return rc;
+    if (a->split && (rc = make_act_map(&p.tm_xp[1], a->dg_lo, B, H, W, Cg, 1, 1, 128))) return rc;
+  }
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
   return cuda_fail(drasic::launch_convlstm_dgrad(p, a->split != 0, pair, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_data launch");

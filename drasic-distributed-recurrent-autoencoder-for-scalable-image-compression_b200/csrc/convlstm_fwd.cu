@@ -103,14 +103,29 @@ __device__ __forceinline__ void tile_split(const GateParams& p, int tile, int m_
 // node has an odd number of tiles the second CTA of its last pair has no tile of its own: it stages the first
 // CTA's pixels again (the cta_group::2 MMA reads both CTAs' shared memory) and stores nothing.
 struct MUnit {
-  int mt;        // M tile this CTA stages
-  int g;         // node (weight group)
+  int g;                // node (weight group)
   int img_lo, img_hi;   // slots whose rows this unit may store
-  bool own;      // false: filler CTA of an odd pair
+  bool own;             // false: filler CTA of an odd pair
+  bool pos;             // position-major tile: row r = image n0 + r at pixel (y0, x0)
+  int n0, y0, x0;       // first image / pixel of the tile this CTA stages
+  uint32_t taps;        // bit t: tap t (dy = t/3 - 1, dx = t%3 - 1) is walked (all nine for pixel-major tiles)
 };
 template <bool PAIR>
-__device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank) {
+__device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank, int tiles_x, int tiles_per_img) {
   MUnit u;
+  if (mu < p.pos_units) {
+    // position-major: both CTAs of a pair sit on the same position (same taps), adjacent blocks of 128 images
+    const int pi = mu / p.pos_upp, it = mu - pi * p.pos_upp;
+    const int pos = __ldg(&p.pos_order[pi]);
+    u.y0 = pos / p.W;
+    u.x0 = pos - u.y0 * p.W;
+    u.n0 = (PAIR ? 2 * it + rank : it) * TILE_M;
+    u.g = 0; u.img_lo = 0; u.img_hi = 0x7fffffff; u.own = true; u.pos = true;
+    const uint32_t mx = (u.x0 > 0 ? 1u : 0u) | 2u | (u.x0 < p.W - 1 ? 4u : 0u);
+    u.taps = (u.y0 > 0 ? mx : 0u) | (mx << 3) | (u.y0 < p.H - 1 ? mx << 6 : 0u);
+    return u;
+  }
+  mu -= p.pos_units;
   int first, end;
   if (p.n_groups > 1) {
     int g = 0;
@@ -122,31 +137,25 @@ __device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank) {
     u.img_lo = g ? p.group_img_end[g - 1] : 0;
     u.img_hi = p.group_img_end[g];
   } else {
-    first = (PAIR ? 2 : 1) * mu;
+    first = p.pos_tile_base + (PAIR ? 2 : 1) * mu;
     end = p.n_mtiles;
     u.g = 0;
     u.img_lo = 0;
     u.img_hi = 0x7fffffff;
   }
   u.own = first + rank < end;
-  u.mt = u.own ? first + rank : first;
-  return u;
-}
-
-struct TileCoord {
-  int n0, y0, x0;
-};
-__device__ __forceinline__ TileCoord tile_coord(const GateParams& p, int mt, int tiles_x, int tiles_per_img) {
-  TileCoord t;
+  const int mt = u.own ? first + rank : first;
+  u.pos = false;
+  u.taps = 0x1ffu;
   if (p.bn > 1) {
-    t.n0 = mt * p.bn; t.y0 = 0; t.x0 = 0;
+    u.n0 = mt * p.bn; u.y0 = 0; u.x0 = 0;
   } else {
-    t.n0 = mt / tiles_per_img;
+    u.n0 = mt / tiles_per_img;
     const int rem = mt % tiles_per_img;
-    t.y0 = (rem / tiles_x) * p.bh;
-    t.x0 = (rem % tiles_x) * p.bw;
+    u.y0 = (rem / tiles_x) * p.bh;
+    u.x0 = (rem % tiles_x) * p.bw;
   }
-  return t;
+  return u;
 }
 
 // ---------------------------------------------------------------- epilogues (one tile row per thread)
@@ -325,6 +334,14 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       ptx::prefetch_tmap(&p.tm_h[0]);
       if (SPLIT) ptx::prefetch_tmap(&p.tm_h[1]);
     }
+    if (p.pos_units) {
+      ptx::prefetch_tmap(&p.tm_xp[0]);
+      if (SPLIT) ptx::prefetch_tmap(&p.tm_xp[1]);
+      if (p.has_hidden) {
+        ptx::prefetch_tmap(&p.tm_hp[0]);
+        if (SPLIT) ptx::prefetch_tmap(&p.tm_hp[1]);
+      }
+    }
   }
   if (warp == 1) {
     if (PAIR) {
@@ -347,7 +364,8 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
   const int total_tiles = m_units * p.n_ntiles;
   const int cx_chunks = p.Cin / BLOCK_K;
   const int ch_chunks = p.Co / BLOCK_K;
-  const int nkb = 9 * cx_chunks + (p.has_hidden ? 9 * ch_chunks : 0);
+  const int chunks_per_tap = cx_chunks + (p.has_hidden ? ch_chunks : 0);
+  const int nkb_full = 9 * chunks_per_tap;
   const int tiles_x = p.W / p.bw;
   const int tiles_per_img = (p.H / p.bh) * tiles_x;
 
@@ -361,49 +379,49 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
         int nt, mu;
         tile_split(p, tile, m_units, nt, mu);
-        const MUnit un = m_unit<PAIR>(p, mu, static_cast<int>(cta_rank));
-        const int mt = un.mt;
-        const TileCoord tc = tile_coord(p, mt, tiles_x, tiles_per_img);
+        const MUnit un = m_unit<PAIR>(p, mu, static_cast<int>(cta_rank), tiles_x, tiles_per_img);
         int wrow = un.g * p.w_group_rows + nt * BLOCK_N;
         if (PAIR) {  // this CTA stages its half of the (possibly narrower, dgrad) N tile
           int width = BLOCK_N;
           if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
           wrow += static_cast<int>(cta_rank) * (width >> 1);
         }
-        // K blocks walk (source x | h, tap, 64-channel chunk); the position advances incrementally
-        bool is_h = false;
-        int tap = 0, cc = 0, chunks = cx_chunks, kcol = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * C::STAGE_BYTES;
-          const CUtensorMap* ta = is_h ? p.tm_h : p.tm_x;
-          uint8_t* sb = st + (SPLIT ? 2 : 1) * A_TILE_BYTES;
-          if (PAIR) {
-            // both CTAs' bytes are accounted on the leader's barrier (its MMA thread consumes both halves)
-            if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            const uint32_t fb = full_remote0 + 8u * stage;
-            ptx::tma_load_4d_pair(st, &ta[0], fb, cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
-            if (SPLIT)
-              ptx::tma_load_4d_pair(st + A_TILE_BYTES, &ta[1], fb, cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
-            ptx::tma_load_2d_pair(sb, &p.tm_w[0], fb, kcol, wrow);
-            if (SPLIT) ptx::tma_load_2d_pair(sb + C::B_TILE_BYTES, &p.tm_w[1], fb, kcol, wrow);
-          } else {
-            ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            ptx::tma_load_4d(st, &ta[0], &full_bar[stage], cc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.n0);
-            if (SPLIT)
-              ptx::tma_load_4d(st + A_TILE_BYTES, &ta[1], &full_bar[stage], cc * BLOCK_K, tc.x0 + dx,
-                               tc.y0 + dy, tc.n0);
-            ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], kcol, wrow);
-            if (SPLIT)
-              ptx::tma_load_2d(sb + C::B_TILE_BYTES, &p.tm_w[1], &full_bar[stage], kcol, wrow);
+        // K blocks walk (source x | h, tap, 64-channel chunk); taps that lie in the zero padding for every row of a
+        // position-major tile are skipped (the MMA issuer counts the same blocks)
+        for (int src = 0; src < (p.has_hidden ? 2 : 1); ++src) {
+          const CUtensorMap* ta = un.pos ? (src ? p.tm_hp : p.tm_xp) : (src ? p.tm_h : p.tm_x);
+          const int chunks = src ? ch_chunks : cx_chunks;
+          const int kbase = src ? 9 * cx_chunks * BLOCK_K : 0;
+          for (int tap = 0; tap < 9; ++tap) {
+            if (!((un.taps >> tap) & 1u)) continue;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            int kcol = kbase + tap * chunks * BLOCK_K;
+            for (int cc = 0; cc < chunks; ++cc, kcol += BLOCK_K) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* st = smem + stage * C::STAGE_BYTES;
+              uint8_t* sb = st + (SPLIT ? 2 : 1) * A_TILE_BYTES;
+              if (PAIR) {
+                // both CTAs' bytes are accounted on the leader's barrier (its MMA thread consumes both halves)
+                if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                const uint32_t fb = full_remote0 + 8u * stage;
+                ptx::tma_load_4d_pair(st, &ta[0], fb, cc * BLOCK_K, un.x0 + dx, un.y0 + dy, un.n0);
+                if (SPLIT)
+                  ptx::tma_load_4d_pair(st + A_TILE_BYTES, &ta[1], fb, cc * BLOCK_K, un.x0 + dx, un.y0 + dy, un.n0);
+                ptx::tma_load_2d_pair(sb, &p.tm_w[0], fb, kcol, wrow);
+                if (SPLIT) ptx::tma_load_2d_pair(sb + C::B_TILE_BYTES, &p.tm_w[1], fb, kcol, wrow);
+              } else {
+                ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                ptx::tma_load_4d(st, &ta[0], &full_bar[stage], cc * BLOCK_K, un.x0 + dx, un.y0 + dy, un.n0);
+                if (SPLIT)
+                  ptx::tma_load_4d(st + A_TILE_BYTES, &ta[1], &full_bar[stage], cc * BLOCK_K, un.x0 + dx,
+                                   un.y0 + dy, un.n0);
+                ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], kcol, wrow);
+                if (SPLIT)
+                  ptx::tma_load_2d(sb + C::B_TILE_BYTES, &p.tm_w[1], &full_bar[stage], kcol, wrow);
+              }
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
           }
-          kcol += BLOCK_K;
-          if (++cc == chunks) {
-            cc = 0;
-            if (++tap == 9) { tap = 0; is_h = true; chunks = ch_chunks; }
-          }
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -421,11 +439,12 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
         // dgrad: the last N tile of a row may be narrower than BLOCK_N (UMMA N is a runtime field)
         int width = BLOCK_N;
-        if (EPI == EPI_DGRAD) {
-          int nt, mu;
-          tile_split(p, tile, m_units, nt, mu);
-          width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
-        }
+        int nt, mu;
+        tile_split(p, tile, m_units, nt, mu);
+        if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
+        // K blocks of this tile: the taps the producer walks x the channel chunks of both sources
+        int nkb = nkb_full;
+        if (mu < p.pos_units) nkb = __popc(m_unit<PAIR>(p, mu, 0, tiles_x, tiles_per_img).taps) * chunks_per_tap;
         const uint32_t idesc = ptx::umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, width);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -483,20 +502,21 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
       int nt, mu;
       tile_split(p, tile, m_units, nt, mu);
-      const MUnit un = m_unit<PAIR>(p, mu, static_cast<int>(cta_rank));
-      const TileCoord tc = tile_coord(p, un.mt, tiles_x, tiles_per_img);
+      const MUnit un = m_unit<PAIR>(p, mu, static_cast<int>(cta_rank), tiles_x, tiles_per_img);
       const int g = un.g;
+      // this thread's row: pixel (yl, xl) of image nl of the box, or image `row` of a position-major tile
+      const int rn = un.n0 + (un.pos ? row : nl), ry = un.y0 + (un.pos ? 0 : yl), rx = un.x0 + (un.pos ? 0 : xl);
       // rows of another node's images (a shared 4x4 tile) and the filler CTA of an odd pair store nothing
-      const bool row_ok = un.own && tc.n0 + nl >= un.img_lo && tc.n0 + nl < un.img_hi;
+      const bool row_ok = un.own && rn >= un.img_lo && rn < un.img_hi;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       if (EPI == EPI_GATES)
-        epilogue_gates<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl, row_ok);
+        epilogue_gates<SPLIT, BLOCK_N>(p, t_row, nt, g, rn, ry, rx, row_ok);
       else
-        epilogue_dgrad<SPLIT, BLOCK_N>(p, t_row, nt, g, tc.n0 + nl, tc.y0 + yl, tc.x0 + xl, row_ok);
+        epilogue_dgrad<SPLIT, BLOCK_N>(p, t_row, nt, g, rn, ry, rx, row_ok);
       // release the accumulator to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();

@@ -62,6 +62,15 @@ struct GateParams {
   const int* group_unit_end;
   const int* group_img_end;
   int n_munits;                // total work units of the M dimension
+  // ---- position-major M tiles (n_groups == 1): the first pos_units units hold ONE pixel position of 128 images
+  // each (TMA box 64 ch x 1 x 1 x 128 images), walked heaviest position first; the (tile, tap) K blocks whose tap
+  // falls into the zero padding for that position are skipped altogether.  The images behind them (fewer than one
+  // unit's worth) are covered by ordinary pixel-major tiles starting at M tile pos_tile_base.
+  CUtensorMap tm_xp[2];
+  CUtensorMap tm_hp[2];
+  int pos_units, pos_upp;      // units in the position-major region; units (image tiles / pairs of them) per position
+  int pos_tile_base;
+  const int* pos_order;        // [H*W] pixel positions (y*W + x), most in-bounds taps first
   // ---- dgrad epilogue (EPI_DGRAD): D[pixels, Nout] = conv3x3^T(dG) ; Cin here = 4*Co of the layer
   int w_group_rows;            // weight-matrix rows per group (4Co for gates, Nout rounded for dgrad)
   int n_out;                   // dgrad: output columns = layer Cin + layer Co

@@ -21,7 +21,8 @@ class ConvLSTMArgs(C.Structure):
                                   'group_mtile_end')] + \
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'has_state', 'next_mode',
                                   'next_f32', 'split', 'precise', 'block_n', 'gates_f32', 'cta_pair')] + \
-               [('group_mtile_start', vp), ('group_unit_end', vp), ('group_img_end', vp), ('n_units', ip)]
+               [('group_mtile_start', vp), ('group_unit_end', vp), ('group_img_end', vp), ('n_units', ip),
+                ('pos_order', vp), ('pos_imgs', ip)]
 
 
 class BottleneckArgs(C.Structure):
@@ -42,7 +43,8 @@ class DgradArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('dg_hi', 'dg_lo', 'w_hi', 'w_lo', 'w_inv_scale', 'dg_inv_scale', 'dx_out',
                                   'dhrec_out', 'group_mtile_end')] + \
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'dx_mode', 'split', 'cta_pair')] + \
-               [('group_mtile_start', vp), ('group_unit_end', vp), ('group_img_end', vp), ('n_units', ip)]
+               [('group_mtile_start', vp), ('group_unit_end', vp), ('group_img_end', vp), ('n_units', ip),
+                ('pos_order', vp), ('pos_imgs', ip)]
 
 
 class WgradArgs(C.Structure):

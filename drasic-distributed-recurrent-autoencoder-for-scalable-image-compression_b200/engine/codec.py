@@ -172,6 +172,15 @@ class _Layer(object):
     pass
 
 
+def position_order(h, w):
+    """pixel positions y*w + x of an h x w plane, most in-bounds 3x3 taps first (interior 9, edges 6, corners 4):
+    the order in which the conv GEMMs walk their position-major tiles, so that the persistent CTAs -- dealt the
+    units round robin -- get the same mix of long and short K loops and finish together"""
+    y, x = np.divmod(np.arange(h * w), w)
+    taps = (3 - (y == 0) - (y == h - 1)) * (3 - (x == 0) - (x == w - 1))
+    return np.argsort(-taps, kind='stable').astype(np.int32)
+
+
 def _pick_k_splits(tiles, units, k_max):
     """K splits of the wgrad GEMM: the persistent grid walks tiles*k work items in waves of `units`;
     pick the split count (at least ~3 waves of work when K allows) whose last wave is fullest."""
@@ -231,6 +240,34 @@ class CodecEngine(object):
         self._repack = False
         self.overlap_wgrad = True   # wgrad GEMMs on a side stream
         self.profile = None  # set to [] to collect (label, flops, start_event, end_event) per launch
+        # position-major M tiles for the layers whose weights are shared by the whole batch (the joint decoder; the
+        # encoder too with a single source): padding taps are never issued (15 % of the MACs of an iteration)
+        self.pos_major = True
+        self._pos_tables = {}
+
+    def _pos_order(self, h, w, dev):
+        key = (h, w, str(dev))
+        if key not in self._pos_tables:
+            self._pos_tables[key] = torch.from_numpy(position_order(h, w)).to(dev)
+        return self._pos_tables[key]
+
+    def _plan_units(self, ly, Bp, plan, dev):
+        """work units of the M dimension of one layer: per-node tile ranges (device tables of the batch plan) for
+        grouped layers; for a layer shared by the whole batch, position-major tiles over as many slots as fill whole
+        units (128 images, 256 with CTA pairs) followed by pixel-major tiles over the rest"""
+        hw = ly.h * ly.w
+        n_mtiles = Bp * hw // 128
+        ly.units, ly.pos_imgs, ly.pos_order = None, 0, None
+        if ly.groups > 1:
+            ly.units, ly.n_units = plan.m_units(hw, ly.pair)
+            return
+        unit_imgs = 256 if ly.pair else 128
+        if self.pos_major:
+            ly.pos_imgs = Bp // unit_imgs * unit_imgs
+        rest = n_mtiles - ly.pos_imgs * hw // 128
+        ly.n_units = hw * (ly.pos_imgs // unit_imgs) + ((rest + 1) // 2 if ly.pair else rest)
+        if ly.pos_imgs:
+            ly.pos_order = self._pos_order(ly.h, ly.w, dev)
 
     def clone(self):
         """an engine with the same configuration and its own arenas / packed weight planes (a captured CUDA graph
@@ -449,10 +486,7 @@ class CodecEngine(object):
             ly.groups = len(prefs)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
-            # work units of the M dimension: per-node tile ranges (device) for grouped layers, plain tiles otherwise
-            ly.units, ly.n_units = None, ((n_mtiles + 1) // 2 if ly.pair else n_mtiles)
-            if ly.groups > 1:
-                ly.units, ly.n_units = plan.m_units(h * w, ly.pair)
+            self._plan_units(ly, Bp, plan, dev)
             layers.append(ly)
 
         self._repack = False
@@ -529,6 +563,7 @@ class CodecEngine(object):
             a.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
             a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
             a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
+            a.pos_order, a.pos_imgs = P(ly.pos_order), ly.pos_imgs
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups = ly.groups
             a.has_state = 1 if t > 0 else 0
@@ -625,10 +660,7 @@ class CodecEngine(object):
             ly.groups = len(dec_pref)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, DEC_IDX[name]) for p in dec_pref], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
-            # work units of the M dimension: per-node tile ranges (device) for grouped layers, plain tiles otherwise
-            ly.units, ly.n_units = None, ((n_mtiles + 1) // 2 if ly.pair else n_mtiles)
-            if ly.groups > 1:
-                ly.units, ly.n_units = plan.m_units(h * w, ly.pair)
+            self._plan_units(ly, Bp, plan, dev)
             layers.append(ly)
         self._repack = False      # (the encoder planes stay stale: _stale is cleared only by a full forward)
         w_d0 = stack([p + '.0.cell.cell.main.weight' for p in dec_pref])
@@ -664,6 +696,7 @@ class CodecEngine(object):
                 g.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
                 g.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
                 g.group_img_end, g.n_units = P(plan.group_img_end), ly.n_units
+                g.pos_order, g.pos_imgs = P(ly.pos_order), ly.pos_imgs
                 g.B_pad, g.H, g.W, g.Cin, g.Co = Bp, ly.h, ly.w, ly.cin, ly.co
                 g.n_groups, g.has_state = ly.groups, 1 if t > 0 else 0
                 g.next_mode, g.next_f32 = ly.next_mode, ly.next_f32
@@ -828,6 +861,7 @@ class CodecEngine(object):
             a.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
             a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
             a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
+            a.pos_order, a.pos_imgs = P(ly.pos_order), ly.pos_imgs
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.gsplit
             a.cta_pair = int(ly.pair)

@@ -93,6 +93,15 @@ typedef struct {
    * group the M tiles (cta_pair: ceil(M tiles / 2)). */
   const int* group_mtile_start; const int* group_unit_end; const int* group_img_end;
   int n_units;
+  /* Position-major M tiles (n_groups == 1 only; pos_imgs == 0 switches them off).  The first pos_imgs slots -- a
+   * multiple of 128, or of 256 with cta_pair -- are tiled as ONE pixel position x 128 images per M tile, so the
+   * (tile, tap) blocks of the 3x3 convolutions (padding=1, cell.py:117,132) that fall entirely into the zero padding
+   * are never issued: (4-|dx|)(4-|dy|)/16 of the taps are in bounds at 4x4, i.e. 30 % of the MACs of those layers are
+   * skipped, 16 % at 8x8, 8 % at 16x16.  pos_order: device [H*W] ints, the pixel positions y*W+x in the order they are
+   * walked (most in-bounds taps first, so the persistent CTAs end together).  The remaining B_pad - pos_imgs slots use
+   * pixel-major tiles; n_units = H*W * pos_imgs/128 (cta_pair: /256) + the units of those tiles. */
+  const int* pos_order;
+  int pos_imgs;
 } drasic_convlstm_args;
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream);
 
@@ -178,6 +187,7 @@ typedef struct {
   int cta_pair;                           /* as in drasic_convlstm_args */
   const int* group_mtile_start; const int* group_unit_end; const int* group_img_end;   /* as in drasic_convlstm_args */
   int n_units;
+  const int* pos_order; int pos_imgs;   /* position-major M tiles, as in drasic_convlstm_args */
 } drasic_dgrad_args;
 int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream);
 

@@ -236,3 +236,36 @@ def test_captured_graphs_own_their_buffers():
         assert rel_err(got[3], t_eager[3]) < 1e-3      # (wgrad accumulates with atomics: run-to-run noise only)
     for got in (e_graph_1, e_graph_2):
         assert torch.equal(got[0], e_eager[0]) and torch.equal(got[1], e_eager[1])
+
+
+@pytest.mark.parametrize('M,B,cta_pair', [(1, 256, 'on'), (1, 264, 'on'), (1, 136, 'off'), (4, 272, 'on')])
+def test_position_major_tiles_are_bit_identical_to_pixel_major(M, B, cta_pair):
+    """The position-major M tiles (one pixel position x 128 images; padding taps never issued) skip only MMAs whose A
+    operand is TMA zero fill, so every output bit equals the pixel-major walk's: forward (codes, reconstructions)
+    and -- up to the atomics' order in wgrad -- the gradients.  M=1: encoder and decoder layers; M=4: the joint
+    decoder only.  B=264 / 136 / 272 leave a pixel-major remainder behind the position-major region."""
+    T = 3
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=37, cta_pair=cta_pair)
+    g = torch.Generator().manual_seed(38)
+    img = torch.rand(B, 3, 32, 32, generator=g)
+    label = torch.randint(0, M, (B,), generator=g)
+    noise = torch.rand(T, B, 8, 4, 4, generator=g)
+    res = {}
+    for pos in (True, False):
+        out = run(m, img, label)                                     # (creates the engine on the first pass)
+        m._engine.pos_major = pos
+        out = run(m, img, label)
+        assert any(ly.pos_imgs > 0 for ly in m._engine._last_layers) == pos
+        tr = train_step(m, img, label, noise)
+        grads = torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+        res[pos] = (out['code_pm1'].clone(), torch.stack(out['img']).clone(), tr['code_pm1'].clone(), tr['loss'].item(), grads)
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    assert torch.equal(res[True][2], res[False][2]) and res[True][3] == res[False][3]
+    assert rel_err(res[True][4], res[False][4]) < 1e-4
+    # and against the oracle on a slice of the batch
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    sub = torch.arange(0, B, B // 24)[:24]
+    with torch.no_grad():
+        ref = O.codec_forward(sd, img[sub], label[sub], T, M)
+    assert torch.equal(res[True][0].cpu()[:, sub], torch.stack(ref['code_pm1']))
+    assert (res[True][1].cpu()[:, sub] - torch.stack(ref['img'])).abs().max().item() < RECON_TOL

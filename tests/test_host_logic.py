@@ -320,3 +320,35 @@ def test_wgrad_k_split_picker():
         for other in range(k_lo, max(k_lo, min(k_max, 4 * k_lo)) + 1):
             m = tiles * other
             assert m / float(-(-m // units) * units) <= eff + 1e-3 or other > k
+
+
+def test_position_order_heaviest_first():
+    """engine.codec.position_order: every position once, in-bounds tap counts non-increasing (9, 6, 4)"""
+    from engine.codec import position_order
+    for h, w in [(4, 4), (8, 8), (16, 16), (2, 2), (4, 6), (1, 1)]:
+        order = position_order(h, w)
+        assert sorted(order.tolist()) == list(range(h * w))
+        y, x = np.divmod(order, w)
+        taps = (3 - (y == 0) - (y == h - 1)) * (3 - (x == 0) - (x == w - 1))
+        assert np.all(np.diff(taps) <= 0)
+    taps44 = sorted(((3 - (p // 4 == 0) - (p // 4 == 3)) * (3 - (p % 4 == 0) - (p % 4 == 3))) for p in range(16))
+    assert sum(taps44) == 100                                      # 100 of 144 (position, tap) pairs are in bounds at 4x4
+
+
+def test_plan_units_position_major():
+    """CodecEngine._plan_units: position-major tiles cover whole units of 128 (pairs: 256) slots, pixel-major the rest"""
+    from engine.codec import CodecEngine, _Layer
+    eng = CodecEngine(3, 8, 1)
+    for Bp, h, w, pair, want_pos, want_units in [(1024, 4, 4, True, 1024, 16 * 4), (1040, 8, 8, True, 1024, 64 * 4 + 4),
+                                                 (128, 4, 4, False, 128, 16), (200, 16, 16, False, 128, 256 + 144),
+                                                 (64, 8, 8, False, 0, 32), (128, 4, 4, True, 0, 8)]:
+        ly = _Layer()
+        ly.h, ly.w, ly.pair, ly.groups = h, w, pair, 1
+        eng._plan_units(ly, Bp, None, 'cpu')
+        assert (ly.pos_imgs, ly.n_units) == (want_pos, want_units), (Bp, h, w, pair, ly.pos_imgs, ly.n_units)
+        assert (ly.pos_order is not None) == (want_pos > 0)
+    eng.pos_major = False
+    ly = _Layer()
+    ly.h, ly.w, ly.pair, ly.groups = 4, 4, True, 1
+    eng._plan_units(ly, 1024, None, 'cpu')
+    assert (ly.pos_imgs, ly.n_units) == (0, 64)
