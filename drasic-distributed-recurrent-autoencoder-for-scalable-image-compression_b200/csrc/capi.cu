@@ -126,6 +126,9 @@ int drasic_device_sms(void) {
   return n;
 }
 
+size_t drasic_stream_k_scratch_bytes(void) { return drasic::SK_MAX_WORKERS * drasic::SK_SLOT_FLOATS * sizeof(float); }
+size_t drasic_stream_k_flag_bytes(void) { return drasic::SK_MAX_WORKERS * sizeof(unsigned int); }
+
 size_t drasic_packed_weight_bytes(int Cin, int Co) {
   return static_cast<size_t>(4) * Co * 9 * (Cin + Co) * 2;
 }
@@ -177,6 +180,51 @@ static int setup_pos_tiles(drasic::GateParams& p, const char* who, const int* po
   const int rest = p.n_mtiles - p.pos_tile_base;
   if (n_units != p.pos_units + (pair ? (rest + 1) / 2 : rest))
     return fail(DRASIC_ERR_INVALID, "%s: n_units=%d does not match pos_imgs=%d", who, n_units, pos_imgs);
+  return 0;
+}
+
+// stream-K schedule of a conv GEMM launch (see GateParams): the classes of work items with equal K-block counts, in
+// the order the kernel numbers the items (position-major units sorted by in-bounds taps, then pixel-major units)
+static int setup_stream_k(drasic::GateParams& p, const char* who, int stream_k, void* scratch, void* flags, int chunks_per_tap,
+                          int max_workers) {
+  p.sk_on = 0;
+  if (!stream_k) return 0;
+  if (!scratch || !flags) return fail(DRASIC_ERR_INVALID, "%s: stream_k needs sk_scratch and sk_flags", who);
+  if (max_workers < 1) return fail(DRASIC_ERR_NO_DEVICE, "%s: stream_k: no co-resident workers on this device", who);
+  int count[10] = {0};
+  if (p.pos_units) {
+    int cy[4] = {0, 0, 0, 0}, cx[4] = {0, 0, 0, 0};     // rows / columns with 1, 2, 3 in-bounds taps along the axis
+    if (p.H == 1) cy[1] = 1; else { cy[2] = 2; cy[3] = p.H - 2; }
+    if (p.W == 1) cx[1] = 1; else { cx[2] = 2; cx[3] = p.W - 2; }
+    for (int ty = 1; ty <= 3; ++ty)
+      for (int tx = 1; tx <= 3; ++tx) count[ty * tx] += cy[ty] * cx[tx];
+  }
+  int k = 0, item = 0;
+  long long kb = 0;
+  for (int taps = 9; taps >= 1; --taps) {
+    if (!count[taps]) continue;
+    p.sk_item0[k] = item; p.sk_kb0[k] = static_cast<int>(kb); p.sk_nkb[k] = taps * chunks_per_tap;
+    const int items = count[taps] * p.pos_upp * p.n_ntiles;
+    item += items; kb += static_cast<long long>(items) * p.sk_nkb[k];
+    ++k;
+  }
+  const int rest = (p.n_munits - p.pos_units) * p.n_ntiles;
+  if (rest > 0) {
+    p.sk_item0[k] = item; p.sk_kb0[k] = static_cast<int>(kb); p.sk_nkb[k] = 9 * chunks_per_tap;
+    item += rest; kb += static_cast<long long>(rest) * p.sk_nkb[k];
+    ++k;
+  }
+  if (k == 0 || kb <= 0 || kb > 0x3fffffffLL || item != p.n_munits * p.n_ntiles)
+    return fail(DRASIC_ERR_INVALID, "%s: stream_k: inconsistent work item count", who);
+  p.sk_item0[k] = item; p.sk_kb0[k] = static_cast<int>(kb);
+  p.sk_classes = k;
+  p.sk_on = 1;
+  long long w = kb / 4;                       // at least four K blocks per worker
+  if (w < 1) w = 1;
+  p.sk_workers = static_cast<int>(w < max_workers ? w : max_workers);
+  p.sk_scratch = static_cast<float*>(scratch);
+  p.sk_flags = static_cast<unsigned int*>(flags);
+  p.tile_order = 0;
   return 0;
 }
 
@@ -258,6 +306,10 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   }
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
+  if (a->stream_k && (rc = setup_stream_k(p, "convlstm_fwd", a->stream_k, a->sk_scratch, a->sk_flags,
+                                          Cin / 64 + (a->has_state ? Co / 64 : 0),
+                                          drasic::conv_gemm_max_workers(a->split != 0, a->block_n, false, pair, sms))))
+    return rc;
   return cuda_fail(drasic::launch_convlstm_gates(p, a->split != 0, a->block_n, pair, sms, static_cast<cudaStream_t>(stream)),
                    "convlstm_fwd launch");
 }
@@ -391,6 +443,9 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   }
   const int sms = num_sms();
   if (sms <= 0) return fail(DRASIC_ERR_NO_DEVICE, "no CUDA device");
+  if (a->stream_k && (rc = setup_stream_k(p, "convlstm_bwd_data", a->stream_k, a->sk_scratch, a->sk_flags, Cg / 64,
+                                          drasic::conv_gemm_max_workers(a->split != 0, 256, true, pair, sms))))
+    return rc;
   return cuda_fail(drasic::launch_convlstm_dgrad(p, a->split != 0, pair, sms, static_cast<cudaStream_t>(stream)), "convlstm_bwd_data launch");
 }
 

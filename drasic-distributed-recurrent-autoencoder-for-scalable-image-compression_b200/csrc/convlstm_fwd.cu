@@ -110,6 +110,11 @@ struct MUnit {
   int n0, y0, x0;       // first image / pixel of the tile this CTA stages
   uint32_t taps;        // bit t: tap t (dy = t/3 - 1, dx = t%3 - 1) is walked (all nine for pixel-major tiles)
 };
+// taps of the 3x3 stencil that are in bounds at pixel (y, x): bit t <-> (dy = t/3 - 1, dx = t%3 - 1)
+__device__ __forceinline__ uint32_t pos_taps(const GateParams& p, int y, int x) {
+  const uint32_t mx = (x > 0 ? 1u : 0u) | 2u | (x < p.W - 1 ? 4u : 0u);
+  return (y > 0 ? mx : 0u) | (mx << 3) | (y < p.H - 1 ? mx << 6 : 0u);
+}
 template <bool PAIR>
 __device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank, int tiles_x, int tiles_per_img) {
   MUnit u;
@@ -121,8 +126,7 @@ __device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank, i
     u.x0 = pos - u.y0 * p.W;
     u.n0 = (PAIR ? 2 * it + rank : it) * TILE_M;
     u.g = 0; u.img_lo = 0; u.img_hi = 0x7fffffff; u.own = true; u.pos = true;
-    const uint32_t mx = (u.x0 > 0 ? 1u : 0u) | 2u | (u.x0 < p.W - 1 ? 4u : 0u);
-    u.taps = (u.y0 > 0 ? mx : 0u) | (mx << 3) | (u.y0 < p.H - 1 ? mx << 6 : 0u);
+    u.taps = pos_taps(p, u.y0, u.x0);
     return u;
   }
   mu -= p.pos_units;
@@ -158,11 +162,92 @@ __device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank, i
   return u;
 }
 
+// ---------------------------------------------------------------- schedule
+// One piece of work of a worker (CTA, or CTA pair): K blocks [kb_lo, kb_hi) of work item (mu, nt).  The static
+// schedule deals whole items round robin; the stream-K schedule gives every worker one contiguous range of the
+// global K-block sequence, so its first and last segments may be parts of items.
+struct Seg {
+  int nt, mu;
+  int kb_lo, kb_hi, nkb;   // nkb: K blocks of the whole item
+  int g0;                  // stream-K: global index of the item's first K block
+};
+struct Walk {
+  int item, stride, total;   // static schedule
+  int g, g_end;              // stream-K
+  int cpt, n_workers;
+  __device__ __forceinline__ static int range_begin(const GateParams& p, int worker, int n_workers) {
+    return static_cast<int>(static_cast<long long>(worker) * p.sk_kb0[p.sk_classes] / n_workers);
+  }
+  __device__ __forceinline__ Walk(const GateParams& p, int worker, int n_workers_, int chunks_per_tap) {
+    cpt = chunks_per_tap;
+    n_workers = n_workers_;
+    item = worker; stride = n_workers_; total = p.n_munits * p.n_ntiles;
+    g = g_end = 0;
+    if (p.sk_on) { g = range_begin(p, worker, n_workers_); g_end = range_begin(p, worker + 1, n_workers_); }
+  }
+  __device__ __forceinline__ bool next(const GateParams& p, Seg& s) {
+    int it;
+    if (p.sk_on) {
+      if (g >= g_end) return false;
+      int k = 0;
+      while (k + 1 < p.sk_classes && g >= p.sk_kb0[k + 1]) ++k;
+      const int off = g - p.sk_kb0[k], n = p.sk_nkb[k];
+      const int q = off / n;
+      it = p.sk_item0[k] + q;
+      s.kb_lo = off - q * n;
+      s.nkb = n;
+      s.kb_hi = min(n, s.kb_lo + (g_end - g));
+      s.g0 = g - s.kb_lo;
+      g += s.kb_hi - s.kb_lo;
+      tile_split(p, it, p.n_munits, s.nt, s.mu);
+      return true;
+    }
+    if (item >= total) return false;
+    it = item;
+    item += stride;
+    tile_split(p, it, p.n_munits, s.nt, s.mu);
+    int taps = 9;
+    if (s.mu < p.pos_units) {
+      const int pos = __ldg(&p.pos_order[s.mu / p.pos_upp]);
+      taps = __popc(pos_taps(p, pos / p.W, pos % p.W));
+    }
+    s.nkb = taps * cpt;
+    s.kb_lo = 0; s.kb_hi = s.nkb; s.g0 = 0;
+    return true;
+  }
+};
+
+// stream-K partial accumulators: slot of CTA `rank` of `worker`, laid out [16-column chunk][row][16] so that a warp
+// (32 consecutive rows) moves 2 KB contiguous per chunk
+__device__ __forceinline__ float* sk_slot(const GateParams& p, int worker, int ranks, int rank) {
+  return p.sk_scratch + (static_cast<size_t>(worker) * ranks + rank) * SK_SLOT_FLOATS;
+}
+__device__ __forceinline__ void sk_add16(float (&v)[16], const float* __restrict__ part, int n_peers, size_t peer_stride,
+                                         int chunk, int row) {
+  for (int pp = 0; pp < n_peers; ++pp) {
+    const float4* src = reinterpret_cast<const float4*>(part + pp * peer_stride + (static_cast<size_t>(chunk) * TILE_M + row) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = __ldcg(src + q);
+      v[4 * q + 0] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    }
+  }
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void epilogue_bar_sync() {   // the four epilogue warps only
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- epilogues (one tile row per thread)
 // ConvLSTM gates: the N tile holds i,f,g,o of SLOTS channels (columns gate*SLOTS + s)
 template <bool SPLIT, int BLOCK_N>
 __device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_row, int nt, int g, int n,
-                                               int y, int x, bool row_ok) {
+                                               int y, int x, bool row_ok, const float* part, int n_peers,
+                                               size_t peer_stride, int row) {
   constexpr int SLOTS = BLOCK_N / 4;  // channels per N tile
   const int H = p.H, W = p.W, Co = p.Co;
   const float inv = __ldg(&p.w_inv_scale[g]);
@@ -176,6 +261,12 @@ __device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_r
     ptx::tmem_ld16(t_row + 3 * SLOTS + j * 16, go);
     ptx::tmem_ld_wait();
     if (!row_ok) continue;   // (the TMEM loads above are warp-collective; everything below is per row)
+    if (n_peers) {           // stream-K: the other workers' parts of this item's K range
+      sk_add16(gi, part, n_peers, peer_stride, 0 * (SLOTS / 16) + j, row);
+      sk_add16(gf, part, n_peers, peer_stride, 1 * (SLOTS / 16) + j, row);
+      sk_add16(gg, part, n_peers, peer_stride, 2 * (SLOTS / 16) + j, row);
+      sk_add16(go, part, n_peers, peer_stride, 3 * (SLOTS / 16) + j, row);
+    }
     const int p0 = nt * SLOTS + j * 16;  // first physical channel of this chunk
     float cv[16];
     if (p.has_cell) {
@@ -257,7 +348,8 @@ __device__ __forceinline__ void epilogue_gates(const GateParams& p, uint32_t t_r
 // dgrad: columns are output channels [dX (n_x) | dH_prev (n_out - n_x)], fp32 stores
 template <bool SPLIT, int BLOCK_N>
 __device__ __forceinline__ void epilogue_dgrad(const GateParams& p, uint32_t t_row, int nt, int g, int n,
-                                               int y, int x, bool row_ok) {
+                                               int y, int x, bool row_ok, const float* part, int n_peers,
+                                               size_t peer_stride, int row) {
   const int H = p.H, W = p.W;
   const float inv = __ldg(&p.w_inv_scale[g]) * __ldg(p.a_inv_scale);
   const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
@@ -269,6 +361,7 @@ __device__ __forceinline__ void epilogue_dgrad(const GateParams& p, uint32_t t_r
     ptx::tmem_ld16(t_row + j * 16, v);
     ptx::tmem_ld_wait();
     if (!row_ok) continue;
+    if (n_peers) sk_add16(v, part, n_peers, peer_stride, j, row);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] *= inv;
     const int c = col0 + j * 16;
@@ -358,14 +451,11 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   // tile walk: a work unit is one M tile (1 CTA) or one pair of adjacent M tiles (CTA pair) x one N tile
-  const int unit_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
-  const int unit_first = PAIR ? blockIdx.x >> 1 : blockIdx.x;
-  const int m_units = p.n_munits;
-  const int total_tiles = m_units * p.n_ntiles;
+  const int n_workers = PAIR ? gridDim.x >> 1 : gridDim.x;
+  const int worker = PAIR ? blockIdx.x >> 1 : blockIdx.x;
   const int cx_chunks = p.Cin / BLOCK_K;
   const int ch_chunks = p.Co / BLOCK_K;
   const int chunks_per_tap = cx_chunks + (p.has_hidden ? ch_chunks : 0);
-  const int nkb_full = 9 * chunks_per_tap;
   const int tiles_x = p.W / p.bw;
   const int tiles_per_img = (p.H / p.bh) * tiles_x;
 
@@ -376,10 +466,11 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       uint32_t phase = 0;
       // the leader's full barriers (shared::cluster addresses; the CTA windows map linearly)
       const uint32_t full_remote0 = PAIR ? ptx::mapa_u32(&full_bar[0], 0) : 0u;
-      for (int tile = unit_first; tile < total_tiles; tile += unit_stride) {
-        int nt, mu;
-        tile_split(p, tile, m_units, nt, mu);
-        const MUnit un = m_unit<PAIR>(p, mu, static_cast<int>(cta_rank), tiles_x, tiles_per_img);
+      Walk walk(p, worker, n_workers, chunks_per_tap);
+      Seg sg;
+      while (walk.next(p, sg)) {
+        const int nt = sg.nt;
+        const MUnit un = m_unit<PAIR>(p, sg.mu, static_cast<int>(cta_rank), tiles_x, tiles_per_img);
         int wrow = un.g * p.w_group_rows + nt * BLOCK_N;
         if (PAIR) {  // this CTA stages its half of the (possibly narrower, dgrad) N tile
           int width = BLOCK_N;
@@ -387,7 +478,9 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
           wrow += static_cast<int>(cta_rank) * (width >> 1);
         }
         // K blocks walk (source x | h, tap, 64-channel chunk); taps that lie in the zero padding for every row of a
-        // position-major tile are skipped (the MMA issuer counts the same blocks)
+        // position-major tile are skipped (the MMA issuer counts the same blocks); kb numbers the blocks of the item,
+        // of which this segment covers [kb_lo, kb_hi)
+        int kb = 0;
         for (int src = 0; src < (p.has_hidden ? 2 : 1); ++src) {
           const CUtensorMap* ta = un.pos ? (src ? p.tm_hp : p.tm_xp) : (src ? p.tm_h : p.tm_x);
           const int chunks = src ? ch_chunks : cx_chunks;
@@ -396,7 +489,9 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
             if (!((un.taps >> tap) & 1u)) continue;
             const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
             int kcol = kbase + tap * chunks * BLOCK_K;
-            for (int cc = 0; cc < chunks; ++cc, kcol += BLOCK_K) {
+            if (kb + chunks <= sg.kb_lo || kb >= sg.kb_hi) { kb += chunks; continue; }
+            for (int cc = 0; cc < chunks; ++cc, kcol += BLOCK_K, ++kb) {
+              if (kb < sg.kb_lo || kb >= sg.kb_hi) continue;
               ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* st = smem + stage * C::STAGE_BYTES;
               uint8_t* sb = st + (SPLIT ? 2 : 1) * A_TILE_BYTES;
@@ -436,15 +531,14 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       const uint64_t desc_a_lo = ptx::umma_desc_sw128(smem0 + A_TILE_BYTES);
       const uint64_t desc_b_hi = ptx::umma_desc_sw128(smem0 + (SPLIT ? 2 : 1) * A_TILE_BYTES);
       const uint64_t desc_b_lo = ptx::umma_desc_sw128(smem0 + (SPLIT ? 2 : 1) * A_TILE_BYTES + C::B_TILE_BYTES);
-      for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
+      Walk walk(p, worker, n_workers, chunks_per_tap);
+      Seg sg;
+      for (; walk.next(p, sg); ++it) {
         // dgrad: the last N tile of a row may be narrower than BLOCK_N (UMMA N is a runtime field)
         int width = BLOCK_N;
-        int nt, mu;
-        tile_split(p, tile, m_units, nt, mu);
-        if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
-        // K blocks of this tile: the taps the producer walks x the channel chunks of both sources
-        int nkb = nkb_full;
-        if (mu < p.pos_units) nkb = __popc(m_unit<PAIR>(p, mu, 0, tiles_x, tiles_per_img).taps) * chunks_per_tap;
+        if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - sg.nt * BLOCK_N);
+        // K blocks of this segment: the taps the producer walks x the channel chunks of both sources
+        const int nkb = sg.kb_hi - sg.kb_lo;
         const uint32_t idesc = ptx::umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, width);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -499,10 +593,12 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
     uint32_t tmem_empty_leader[2];
     if (PAIR)
       for (int a = 0; a < 2; ++a) tmem_empty_leader[a] = ptx::mapa_u32(&tmem_empty[a], 0);
-    for (int tile = unit_first; tile < total_tiles; tile += unit_stride, ++it) {
-      int nt, mu;
-      tile_split(p, tile, m_units, nt, mu);
-      const MUnit un = m_unit<PAIR>(p, mu, static_cast<int>(cta_rank), tiles_x, tiles_per_img);
+    constexpr int RANKS = PAIR ? 2 : 1;
+    Walk walk(p, worker, n_workers, chunks_per_tap);
+    Seg sg;
+    for (; walk.next(p, sg); ++it) {
+      const int nt = sg.nt;
+      const MUnit un = m_unit<PAIR>(p, sg.mu, static_cast<int>(cta_rank), tiles_x, tiles_per_img);
       const int g = un.g;
       // this thread's row: pixel (yl, xl) of image nl of the box, or image `row` of a position-major tile
       const int rn = un.n0 + (un.pos ? row : nl), ry = un.y0 + (un.pos ? 0 : yl), rx = un.x0 + (un.pos ? 0 : xl);
@@ -513,10 +609,54 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-      if (EPI == EPI_GATES)
-        epilogue_gates<SPLIT, BLOCK_N>(p, t_row, nt, g, rn, ry, rx, row_ok);
-      else
-        epilogue_dgrad<SPLIT, BLOCK_N>(p, t_row, nt, g, rn, ry, rx, row_ok);
+      if (sg.kb_lo > 0) {
+        // stream-K, not the item's first part: publish the raw accumulator for the worker that has the first part
+        int width = BLOCK_N;
+        if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
+        float* dst = sk_slot(p, worker, RANKS, static_cast<int>(cta_rank));
+        for (int j = 0; j < width / 16; ++j) {
+          float v[16];
+          ptx::tmem_ld16(t_row + j * 16, v);
+          ptx::tmem_ld_wait();
+          store_f32x16(dst + (static_cast<size_t>(j) * TILE_M + row) * 16, v);
+        }
+        __threadfence();
+        epilogue_bar_sync();
+        if (threadIdx.x == 64) atomicExch(&p.sk_flags[worker * RANKS + cta_rank], 1u);
+      } else {
+        // stream-K, first part of an item that other workers finish: their partials were published at the start of
+        // their ranges (or, for a worker whose whole range lies inside this item, at its end)
+        int n_peers = 0;
+        if (sg.kb_hi < sg.nkb) {
+          while (worker + 1 + n_peers < n_workers && Walk::range_begin(p, worker + 1 + n_peers, n_workers) < sg.g0 + sg.nkb)
+            ++n_peers;
+          if (lane == 0) {
+            for (int pp = 0; pp < n_peers; ++pp) {
+              const unsigned int* f = &p.sk_flags[(worker + 1 + pp) * RANKS + cta_rank];
+              uint64_t t0 = 0;
+              for (uint32_t spin = 0; ld_acquire_u32(f) != 1u; ++spin) {
+                __nanosleep(64);
+                if ((spin & 0x3FFu) == 0x3FFu) {
+                  const uint64_t now = ptx::globaltimer_ns();
+                  if (t0 == 0) t0 = now;
+                  else if (now - t0 > 4000000000ull) __trap();
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+        const float* part = sk_slot(p, worker + 1, RANKS, static_cast<int>(cta_rank));
+        if (EPI == EPI_GATES)
+          epilogue_gates<SPLIT, BLOCK_N>(p, t_row, nt, g, rn, ry, rx, row_ok, part, n_peers, RANKS * SK_SLOT_FLOATS, row);
+        else
+          epilogue_dgrad<SPLIT, BLOCK_N>(p, t_row, nt, g, rn, ry, rx, row_ok, part, n_peers, RANKS * SK_SLOT_FLOATS, row);
+        if (n_peers) {   // every epilogue warp has read the partials: hand the slots back
+          epilogue_bar_sync();
+          if (threadIdx.x == 64)
+            for (int pp = 0; pp < n_peers; ++pp) atomicExch(&p.sk_flags[(worker + 1 + pp) * RANKS + cta_rank], 0u);
+        }
+      }
       // release the accumulator to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
@@ -535,7 +675,7 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
 }
 
 template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
-int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
+int configure_t() {
   using C = Cfg<SPLIT, BLOCK_N, PAIR>;
   auto kern = conv_gemm_kernel<SPLIT, BLOCK_N, EPI, PAIR>;
   static bool configured[64] = {};  // per instantiation and device (the attribute is per device)
@@ -546,25 +686,67 @@ int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured[dev] = true;
   }
-  const int total = p.n_munits * p.n_ntiles;
-  if (!PAIR) {
-    const int grid = total < num_sms ? total : num_sms;
-    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
-    return static_cast<int>(cudaGetLastError());
-  }
-  const int pairs = num_sms / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * (total < pairs ? total : pairs));
+  return 0;
+}
+
+template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
+void pair_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int ctas, cudaStream_t stream) {
+  using C = Cfg<SPLIT, BLOCK_N, PAIR>;
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+}
+
+// workers (CTAs, or CTA pairs) that are resident at the same time: the stream-K schedule lets a worker wait for the
+// partial accumulators of the workers behind it, so it must never launch more than this
+template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
+int max_workers_t(int num_sms) {
+  if (configure_t<SPLIT, BLOCK_N, EPI, PAIR>()) return 0;
+  const int cap = PAIR ? SK_MAX_WORKERS / 2 : SK_MAX_WORKERS;
+  if (!PAIR) return num_sms < cap ? num_sms : cap;   // one CTA per SM (shared memory)
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!cached[dev]) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    pair_launch_config<SPLIT, BLOCK_N, EPI, PAIR>(cfg, attr, 2 * (num_sms / 2), nullptr);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<SPLIT, BLOCK_N, EPI, PAIR>, &cfg) != cudaSuccess) n = 0;
+    (void)cudaGetLastError();
+    cached[dev] = n > 0 ? n : -1;
+  }
+  const int n = cached[dev] > 0 ? cached[dev] : 0;
+  return n < cap ? (n < num_sms / 2 ? n : num_sms / 2) : cap;
+}
+
+template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
+int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<SPLIT, BLOCK_N, PAIR>;
+  auto kern = conv_gemm_kernel<SPLIT, BLOCK_N, EPI, PAIR>;
+  if (int e = configure_t<SPLIT, BLOCK_N, EPI, PAIR>()) return e;
+  const int total = p.n_munits * p.n_ntiles;
+  int workers = PAIR ? num_sms / 2 : num_sms;
+  if (total < workers) workers = total;
+  if (p.sk_on) {
+    workers = p.sk_workers;
+    if (workers < 1 || workers > max_workers_t<SPLIT, BLOCK_N, EPI, PAIR>(num_sms)) return static_cast<int>(cudaErrorInvalidValue);
+  }
+  if (!PAIR) {
+    kern<<<workers, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pair_launch_config<SPLIT, BLOCK_N, EPI, PAIR>(cfg, attr, 2 * workers, stream);
   return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, p));
 }
 
@@ -612,6 +794,28 @@ int launch_convlstm_dgrad(const GateParams& p, bool split, bool pair, int num_sm
   }
   return split ? launch_t<true, 256, EPI_DGRAD, false>(p, num_sms, stream)
                : launch_t<false, 256, EPI_DGRAD, false>(p, num_sms, stream);
+}
+
+int conv_gemm_max_workers(bool split, int block_n, bool dgrad, bool pair, int num_sms) {
+  if (dgrad) {
+    if (pair) return split ? max_workers_t<true, 256, EPI_DGRAD, true>(num_sms) : max_workers_t<false, 256, EPI_DGRAD, true>(num_sms);
+    return split ? max_workers_t<true, 256, EPI_DGRAD, false>(num_sms) : max_workers_t<false, 256, EPI_DGRAD, false>(num_sms);
+  }
+  if (pair) return split ? max_workers_t<true, 256, EPI_GATES, true>(num_sms) : max_workers_t<false, 256, EPI_GATES, true>(num_sms);
+  if (split) {
+    switch (block_n) {
+      case 256: return max_workers_t<true, 256, EPI_GATES, false>(num_sms);
+      case 128: return max_workers_t<true, 128, EPI_GATES, false>(num_sms);
+      case 64: return max_workers_t<true, 64, EPI_GATES, false>(num_sms);
+    }
+  } else {
+    switch (block_n) {
+      case 256: return max_workers_t<false, 256, EPI_GATES, false>(num_sms);
+      case 128: return max_workers_t<false, 128, EPI_GATES, false>(num_sms);
+      case 64: return max_workers_t<false, 64, EPI_GATES, false>(num_sms);
+    }
+  }
+  return 0;
 }
 
 }  // namespace drasic

@@ -71,6 +71,17 @@ struct GateParams {
   int pos_units, pos_upp;      // units in the position-major region; units (image tiles / pairs of them) per position
   int pos_tile_base;
   const int* pos_order;        // [H*W] pixel positions (y*W + x), most in-bounds taps first
+  // ---- stream-K schedule (sk_on): the K blocks of all work items, laid end to end in item order, are cut into
+  // one equal range per worker (CTA or CTA pair).  A worker whose range starts inside an item computes that part
+  // first and publishes the fp32 partial accumulator (sk_scratch, sk_flags); the worker that computed the item's
+  // first K block adds the partials of the workers behind it in its epilogue.  Items of class k (same K-block
+  // count: position-major units with 9 / 6 / 4 ... in-bounds taps, then the pixel-major units) are
+  // [sk_item0[k], sk_item0[k+1]) and start at global K block sk_kb0[k].
+  int sk_on, sk_classes;
+  int sk_workers;             // CTAs (CTA pairs) of a stream-K launch: all co-resident
+  int sk_item0[9], sk_kb0[9], sk_nkb[8];
+  float* sk_scratch;           // [workers][CTAs per worker][BLOCK_N/16][128 rows][16] fp32
+  unsigned int* sk_flags;      // [workers][CTAs per worker]: 1 while a published partial waits for its consumer
   // ---- dgrad epilogue (EPI_DGRAD): D[pixels, Nout] = conv3x3^T(dG) ; Cin here = 4*Co of the layer
   int w_group_rows;            // weight-matrix rows per group (4Co for gates, Nout rounded for dgrad)
   int n_out;                   // dgrad: output columns = layer Cin + layer Co
@@ -87,6 +98,10 @@ enum EpiKind : int { EPI_GATES = 0, EPI_DGRAD = 1 };
 int launch_convlstm_gates(const GateParams& p, bool split, int block_n, bool pair, int num_sms,
                           cudaStream_t stream);
 int launch_convlstm_dgrad(const GateParams& p, bool split, bool pair, int num_sms, cudaStream_t stream);
+// workers (CTAs, or CTA pairs) a stream-K launch of this configuration may use: all of them must be co-resident
+int conv_gemm_max_workers(bool split, int block_n, bool dgrad, bool pair, int num_sms);
+constexpr int SK_MAX_WORKERS = 148;                       // sizes of the stream-K scratch: one slot per CTA
+constexpr size_t SK_SLOT_FLOATS = 128 * 256;              // one 128-row x 256-column fp32 accumulator
 size_t convlstm_gates_smem_bytes(bool split, int block_n);
 
 }  // namespace drasic

@@ -22,7 +22,7 @@ class ConvLSTMArgs(C.Structure):
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'has_state', 'next_mode',
                                   'next_f32', 'split', 'precise', 'block_n', 'gates_f32', 'cta_pair')] + \
                [('group_mtile_start', vp), ('group_unit_end', vp), ('group_img_end', vp), ('n_units', ip),
-                ('pos_order', vp), ('pos_imgs', ip)]
+                ('pos_order', vp), ('pos_imgs', ip), ('stream_k', ip), ('sk_scratch', vp), ('sk_flags', vp)]
 
 
 class BottleneckArgs(C.Structure):
@@ -44,7 +44,7 @@ class DgradArgs(C.Structure):
                                   'dhrec_out', 'group_mtile_end')] + \
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'dx_mode', 'split', 'cta_pair')] + \
                [('group_mtile_start', vp), ('group_unit_end', vp), ('group_img_end', vp), ('n_units', ip),
-                ('pos_order', vp), ('pos_imgs', ip)]
+                ('pos_order', vp), ('pos_imgs', ip), ('stream_k', ip), ('sk_scratch', vp), ('sk_flags', vp)]
 
 
 class WgradArgs(C.Structure):
@@ -86,6 +86,7 @@ DX_SAME, DX_INV_DOWN, DX_INV_UP = 0, 1, 2
 
 # every symbol include/drasic_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes',
+           'drasic_stream_k_scratch_bytes', 'drasic_stream_k_flag_bytes',
            'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
            'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_fused',
            'drasic_pack_dgrad_weights', 'drasic_convlstm_bwd_data', 'drasic_convlstm_bwd_weight',
@@ -111,6 +112,10 @@ def lib():
     L.drasic_device_sms.restype = C.c_int
     L.drasic_packed_weight_bytes.restype = C.c_size_t
     L.drasic_packed_weight_bytes.argtypes = [C.c_int, C.c_int]
+    L.drasic_stream_k_scratch_bytes.restype = C.c_size_t
+    L.drasic_stream_k_scratch_bytes.argtypes = []
+    L.drasic_stream_k_flag_bytes.restype = C.c_size_t
+    L.drasic_stream_k_flag_bytes.argtypes = []
     L.drasic_pack_lstm_weights.restype = C.c_int
     L.drasic_pack_lstm_weights.argtypes = [vp, vp, ip, ip, ip, ip, ip, vp, vp, vp, vp, vp]
     L.drasic_convlstm_fwd.restype = C.c_int

@@ -200,7 +200,7 @@ class CodecEngine(object):
     functions (fp32-grade, bit-exact codes); 'fast' = single fp16 operands with tanh.approx."""
 
     def __init__(self, num_channel, code_size, num_node, separate=False, precision='parity', grad_precision='fp16',
-                 cta_pair='auto'):
+                 cta_pair='auto', stream_k='auto'):
         """grad_precision: 'fp16' = backward GEMMs on single fp16 operands, gates saved in fp16 (gradients
         within ~1e-3 relative of the fp32 reference); 'parity' = split-fp16 backward GEMMs and fp32 saved
         gates (fp32-grade gradients; needs precision='parity')."""
@@ -210,8 +210,10 @@ class CodecEngine(object):
             raise ValueError('Not valid grad_precision')
         if cta_pair not in ('auto', 'on', 'off'):
             raise ValueError('Not valid cta_pair')
+        if stream_k not in ('auto', 'on', 'off'):
+            raise ValueError('Not valid stream_k')
         self._ctor = dict(num_channel=num_channel, code_size=code_size, num_node=num_node, separate=separate,
-                          precision=precision, grad_precision=grad_precision, cta_pair=cta_pair)
+                          precision=precision, grad_precision=grad_precision, cta_pair=cta_pair, stream_k=stream_k)
         # counts the forwards that saved state for a backward, over this engine and the engines cloned from it (one
         # per captured graph): whoever holds packed weight planes re-packs when it has moved (see _stale below)
         self.train_count = [0]
@@ -244,12 +246,33 @@ class CodecEngine(object):
         # encoder too with a single source): padding taps are never issued (15 % of the MACs of an iteration)
         self.pos_major = True
         self._pos_tables = {}
+        # stream-K schedule of the gate / dgrad GEMMs: 'auto' = launches with fewer than SK_WAVES whole work items
+        # per CTA (pair), where dealing whole items leaves SMs idle in the last wave (every layer at B=128 has 256 or
+        # 128 items for 148 SMs) or altogether (the 4x4 layers); 'on' / 'off' force it (tests)
+        self.stream_k = stream_k
+        self._sk = {}
 
     def _pos_order(self, h, w, dev):
         key = (h, w, str(dev))
         if key not in self._pos_tables:
             self._pos_tables[key] = torch.from_numpy(position_order(h, w)).to(dev)
         return self._pos_tables[key]
+
+    SK_WAVES = 8
+
+    def _sk_buffers(self, dev):
+        key = str(dev)
+        if key not in self._sk:
+            L = B.lib()
+            self._sk[key] = (torch.empty(L.drasic_stream_k_scratch_bytes() // 4, dtype=torch.float32, device=dev),
+                             torch.zeros(L.drasic_stream_k_flag_bytes() // 4, dtype=torch.int32, device=dev))
+        return self._sk[key]
+
+    def _use_stream_k(self, ly, n_ntiles):
+        if self.stream_k != 'auto':
+            return self.stream_k == 'on'
+        workers = self.sms() // 2 if ly.pair else self.sms()
+        return ly.n_units * n_ntiles < self.SK_WAVES * workers
 
     def _plan_units(self, ly, Bp, plan, dev):
         """work units of the M dimension of one layer: per-node tile ranges (device tables of the batch plan) for
@@ -281,6 +304,7 @@ class CodecEngine(object):
         self._arena = self._arena_key = None
         self._bwd_buf = self._bwd_key = None
         self._wcache = {}
+        self._sk = {}
         self._gen = getattr(self, '_gen', 0) + 1      # a pending backward() can no longer run
         self._stale = False
 
@@ -564,6 +588,9 @@ class CodecEngine(object):
             a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
             a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
             a.pos_order, a.pos_imgs = P(ly.pos_order), ly.pos_imgs
+            if self._use_stream_k(ly, 4 * ly.co // ly.block_n):
+                a.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
+                a.sk_scratch, a.sk_flags = P(sk_s), P(sk_f)
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups = ly.groups
             a.has_state = 1 if t > 0 else 0
@@ -697,6 +724,9 @@ class CodecEngine(object):
                 g.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
                 g.group_img_end, g.n_units = P(plan.group_img_end), ly.n_units
                 g.pos_order, g.pos_imgs = P(ly.pos_order), ly.pos_imgs
+                if self._use_stream_k(ly, 4 * ly.co // ly.block_n):
+                    g.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
+                    g.sk_scratch, g.sk_flags = P(sk_s), P(sk_f)
                 g.B_pad, g.H, g.W, g.Cin, g.Co = Bp, ly.h, ly.w, ly.cin, ly.co
                 g.n_groups, g.has_state = ly.groups, 1 if t > 0 else 0
                 g.next_mode, g.next_f32 = ly.next_mode, ly.next_f32
@@ -862,6 +892,9 @@ class CodecEngine(object):
             a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
             a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
             a.pos_order, a.pos_imgs = P(ly.pos_order), ly.pos_imgs
+            if self._use_stream_k(ly, (ly.cin + (ly.co if t > 0 else 0) + 255) // 256):
+                a.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
+                a.sk_scratch, a.sk_flags = P(sk_s), P(sk_f)
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
             a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.gsplit
             a.cta_pair = int(ly.pair)

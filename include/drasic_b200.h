@@ -49,6 +49,9 @@ int drasic_device_sms(void);
 
 /* bytes of one packed fp16 plane for a ConvLSTM cell: 4*Co * 9*(Cin+Co) * 2 */
 size_t drasic_packed_weight_bytes(int Cin, int Co);
+/* sizes of the stream-K work buffers of drasic_convlstm_fwd / drasic_convlstm_bwd_data (see stream_k below) */
+size_t drasic_stream_k_scratch_bytes(void);
+size_t drasic_stream_k_flag_bytes(void);
 
 /*
  * Pack the gate weights of one ConvLSTMCell (modules/cell.py:82-100: cell[0]['in'].weight
@@ -102,6 +105,13 @@ typedef struct {
    * pixel-major tiles; n_units = H*W * pos_imgs/128 (cta_pair: /256) + the units of those tiles. */
   const int* pos_order;
   int pos_imgs;
+  /* Stream-K schedule (stream_k != 0): instead of dealing whole (M unit, N tile) work items to the persistent CTAs,
+   * the K blocks of all items laid end to end are cut into one equal range per CTA (pair); partial accumulators
+   * travel through sk_scratch (drasic_stream_k_scratch_bytes() bytes) guarded by sk_flags
+   * (drasic_stream_k_flag_bytes() bytes, zero before the first launch; every launch leaves them zero).  For
+   * launches with few items per CTA -- small batches, the 4x4 layers -- where whole items would leave SMs idle. */
+  int stream_k;
+  void* sk_scratch; void* sk_flags;
 } drasic_convlstm_args;
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream);
 
@@ -188,6 +198,7 @@ typedef struct {
   const int* group_mtile_start; const int* group_unit_end; const int* group_img_end;   /* as in drasic_convlstm_args */
   int n_units;
   const int* pos_order; int pos_imgs;   /* position-major M tiles, as in drasic_convlstm_args */
+  int stream_k; void* sk_scratch; void* sk_flags;   /* stream-K schedule, as in drasic_convlstm_args */
 } drasic_dgrad_args;
 int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream);
 

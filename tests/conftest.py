@@ -25,7 +25,7 @@ def golden_dir():
 
 
 def build_model(name, data_name, num_node, num_iter, seed=0, device='cuda', precision='parity', code_size=8,
-                loss_fn='mae', pack_mode='reference', cta_pair='auto'):
+                loss_fn='mae', pack_mode='reference', cta_pair='auto', stream_k='auto'):
     """the reference's own construction sequence (train_model.py:39-58) against the B200 packages"""
     import torch
     import config
@@ -38,6 +38,7 @@ def build_model(name, data_name, num_node, num_iter, seed=0, device='cuda', prec
     config.PARAM['loss_fn'] = loss_fn
     config.PARAM['pack_mode'] = pack_mode
     config.PARAM['cta_pair'] = cta_pair
+    config.PARAM['stream_k'] = stream_k
     import utils
     utils.process_control_name()
     import models

@@ -269,3 +269,47 @@ def test_position_major_tiles_are_bit_identical_to_pixel_major(M, B, cta_pair):
         ref = O.codec_forward(sd, img[sub], label[sub], T, M)
     assert torch.equal(res[True][0].cpu()[:, sub], torch.stack(ref['code_pm1']))
     assert (res[True][1].cpu()[:, sub] - torch.stack(ref['img'])).abs().max().item() < RECON_TOL
+
+
+@pytest.mark.parametrize('M,B,T,cta_pair', [(8, 61, 6, 'off'), (8, 61, 6, 'on'), (1, 264, 3, 'on'), (3, 20, 16, 'auto'),
+                                            (1, 136, 3, 'off')])
+def test_stream_k_schedule_vs_oracle(M, B, T, cta_pair):
+    """stream_k='on': every gate / dgrad GEMM cuts its K-block sequence into one range per CTA (pair) and exchanges
+    partial accumulators.  Same fp32-grade numerics (the partial sums are added in another order): codes equal the
+    oracle's, reconstructions within tolerance, training gradients within the fp16-backward tolerance -- for
+    grouped layers (M=8, ragged, one empty node), position-major tiles with and without a pixel-major remainder."""
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=43, cta_pair=cta_pair, stream_k='on')
+    g = torch.Generator().manual_seed(44)
+    img = torch.rand(B, 3, 32, 32, generator=g)
+    label = torch.randint(0, M, (B,), generator=g)
+    if M > 2:
+        label[label == 1] = 0
+    sub = torch.arange(0, B, max(1, B // 24))[:24]
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.codec_forward(sd, img[sub], label[sub], T, M)
+    for _ in range(2):                                               # twice: the flags must come back to zero
+        out = run(m, img, label)
+        codes, refc, refz = out['code_pm1'].cpu()[:, sub], torch.stack(ref['code_pm1']), torch.stack(ref['z'])
+        margins, clean = first_mismatch_margins(codes, refc, refz)
+        assert all(mg < MARGIN_TOL for mg in margins), margins
+        assert clean >= len(sub) - 1
+        ok = torch.tensor([bool((codes[:, b] == refc[:, b]).all()) for b in range(len(sub))])
+        err = (torch.stack(out['img']).cpu()[:, sub][:, ok] - torch.stack(ref['img'])[:, ok]).abs().max().item()
+        assert err < RECON_TOL
+    assert int(m._engine._sk_buffers(torch.device('cuda', 0))[1].abs().sum()) == 0
+    # training step against the oracle's autograd on a small batch
+    Bt = 16
+    sdg = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    noise = torch.rand(T, Bt, 8, 4, 4, generator=g)
+    rt = O.codec_forward(sdg, img[:Bt], label[:Bt], T, M, training=True, noise=[n for n in noise])
+    rt['loss'].backward()
+    tr = train_step(m, img[:Bt], label[:Bt], noise)
+    assert int((tr['code_pm1'].cpu() != torch.stack(rt['code_pm1'])).sum()) == 0
+    assert abs(tr['loss'].item() - rt['loss'].item()) < 1e-5
+    for k, p in m.named_parameters():
+        if sdg[k].grad is None:
+            assert float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert rel_err(p.grad.cpu(), sdg[k].grad) < GRAD_TOL['fp16'], k
+    assert int(m._engine._sk_buffers(torch.device('cuda', 0))[1].abs().sum()) == 0
