@@ -40,6 +40,7 @@ METRIC = 'images/s train & encode+decode at T=16 (CIFAR-10 32x32), 1/2/4/8 B200;
 # one CPU sample per mode, used by BOTH `cpu_baseline` (our arm) and `--impl reference`
 CPU_SAMPLE = {'train': 64, 'eval': 256}
 PARITY_SAMPLE = 256
+STREAM_K = 'auto'          # --stream-k: schedule of the gate / dgrad GEMMs (auto: stream-K for launches of few work items per SM)
 
 
 def measured_peaks():
@@ -206,7 +207,7 @@ class Arm(object):
     def _apply_config(self):
         c = self.config
         c.PARAM.update(device='cuda', data_name='CIFAR10' if self.channels == 3 else 'MNIST', precision=self.precision,
-                       pack_mode='reference', grad_precision=self.grad_precision, loss_fn='mae')
+                       pack_mode='reference', grad_precision=self.grad_precision, loss_fn='mae', stream_k=STREAM_K)
         c.PARAM['control'] = {'normalization': 'none', 'activation': 'tanh', 'num_iter': str(T_ITER),
                               'code_size': '8', 'num_node': str(self.nodes)}
         import utils
@@ -355,7 +356,7 @@ class Arm(object):
                          'tests/test_gpu_train.py)') if train else ''),
             'config': workload_config(r['mode'], B, world, self.channels, self.nodes),
             'impl_config': {'precision': self.precision, 'grad_precision': self.grad_precision if train else None,
-                            'cuda_graph': r['graph'],
+                            'cuda_graph': r['graph'], 'stream_k': STREAM_K,
                             'parallelism': (('dp{}: sharded by source (rank r owns nodes r mod N), one NCCL all-reduce of the joint '
                                              "decoder's gradients per step" if self.by_source else
                                              'dp{}: batch sharded, one NCCL all-reduce of gradients per step').format(world) if train
@@ -573,11 +574,14 @@ def main():
                          "owns nodes j = r mod N and their samples, only the joint decoder's gradients are all-reduced; "
                          "'auto' = source when there are at least as many nodes as ranks")
     ap.add_argument('--multi-parity', action='store_true', help='N>1: run the in-line gradient parity check in train / eval mode too')
+    ap.add_argument('--stream-k', default='auto', choices=['auto', 'on', 'off'])
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-fast', action='store_true', help='skip the secondary fast-precision measurement')
     args = ap.parse_args()
     if args.shard == 'auto':
         args.shard = 'batch'
+    global STREAM_K
+    STREAM_K = args.stream_k
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -245,7 +245,9 @@ def test_position_major_tiles_are_bit_identical_to_pixel_major(M, B, cta_pair):
     and -- up to the atomics' order in wgrad -- the gradients.  M=1: encoder and decoder layers; M=4: the joint
     decoder only.  B=264 / 136 / 272 leave a pixel-major remainder behind the position-major region."""
     T = 3
-    m = build_model('dist_codec', 'CIFAR10', M, T, seed=37, cta_pair=cta_pair)
+    # (static schedule: under stream-K the two walks cut the K sequence at different places, which changes the order
+    # of the fp32 partial sums -- test_stream_k_schedule_vs_oracle covers that combination against the oracle)
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=37, cta_pair=cta_pair, stream_k='off')
     g = torch.Generator().manual_seed(38)
     img = torch.rand(B, 3, 32, 32, generator=g)
     label = torch.randint(0, M, (B,), generator=g)

@@ -184,7 +184,8 @@ def test_config5_kodak_patches_properties():
     sub = torch.arange(100, 164)
     out_sub = run(m, patches[sub], label[sub])
     assert torch.equal(out_sub['code_pm1'], codes[:, sub.cuda()])
-    assert torch.equal(out_sub['img'][-1], out['img'][-1][sub.cuda()])
+    # (the 64-image launch runs the stream-K schedule, the 4096-image one whole tiles: fp32 summation order differs)
+    assert (out_sub['img'][-1] - out['img'][-1][sub.cuda()]).abs().max().item() < 1e-5
     # (2) the code is progressive: a T=8 run emits the first 8 iterations of the T=16 run
     import config
     config.PARAM['num_iter'] = 8

@@ -241,7 +241,8 @@ def test_cuda_graph_matches_eager_eval_and_train():
         for k in grads[True][0]:
             # fp32 atomics in the weight-gradient accumulation make the sums order dependent at the 1e-6 level
             a, b = grads[True][0][k], grads[False][0][k]
-            assert (a - b).norm().item() <= 1e-4 * max(b.norm().item(), 1e-30), k
+            # ... and the graph's static plan has another slot count, hence other K cuts in the stream-K GEMMs
+            assert (a - b).norm().item() <= 1e-3 * max(b.norm().item(), 1e-30), k
         opt.step()
     config.PARAM['cuda_graph'] = False
 
@@ -282,7 +283,8 @@ def test_config2_full_size_training_step_properties():
     assert worst < 2e-3, worst
     # (4) the decoder-only path reproduces the training-mode reconstructions from the emitted bits
     rec = m.decode(out['bits'][:4], label.cuda())
-    assert torch.equal(rec[3], out['img'][3].detach())
+    # (another slot count -> other K cuts in the stream-K GEMMs: equal up to fp32 summation order)
+    assert (rec[3] - out['img'][3].detach()).abs().max().item() < 1e-5
 
 
 @pytest.mark.parametrize('M,code,B', [(10, 16, 21), (2, 4, 6)])
