@@ -199,29 +199,49 @@ static int setup_stream_k(drasic::GateParams& p, const char* who, int stream_k, 
     for (int ty = 1; ty <= 3; ++ty)
       for (int tx = 1; tx <= 3; ++tx) count[ty * tx] += cy[ty] * cx[tx];
   }
-  int k = 0, item = 0;
-  long long kb = 0;
+  // classes of the whole launch: (first item, items, K blocks per item)
+  int c_item[8], c_n[8], c_nkb[8], nc = 0, item = 0;
   for (int taps = 9; taps >= 1; --taps) {
     if (!count[taps]) continue;
-    p.sk_item0[k] = item; p.sk_kb0[k] = static_cast<int>(kb); p.sk_nkb[k] = taps * chunks_per_tap;
-    const int items = count[taps] * p.pos_upp * p.n_ntiles;
-    item += items; kb += static_cast<long long>(items) * p.sk_nkb[k];
-    ++k;
+    c_item[nc] = item; c_n[nc] = count[taps] * p.pos_upp * p.n_ntiles; c_nkb[nc] = taps * chunks_per_tap;
+    item += c_n[nc++];
   }
   const int rest = (p.n_munits - p.pos_units) * p.n_ntiles;
-  if (rest > 0) {
-    p.sk_item0[k] = item; p.sk_kb0[k] = static_cast<int>(kb); p.sk_nkb[k] = 9 * chunks_per_tap;
-    item += rest; kb += static_cast<long long>(rest) * p.sk_nkb[k];
-    ++k;
+  if (rest > 0) { c_item[nc] = item; c_n[nc] = rest; c_nkb[nc] = 9 * chunks_per_tap; item += rest; ++nc; }
+  if (nc == 0 || item != p.n_munits * p.n_ntiles) return fail(DRASIC_ERR_INVALID, "%s: stream_k: inconsistent work item count", who);
+  // whole waves are dealt statically; the stream-K region is the partial last wave
+  const int total_items = item;
+  int workers = max_workers;
+  long long kb_all = 0;
+  for (int c = 0; c < nc; ++c) kb_all += static_cast<long long>(c_n[c]) * c_nkb[c];
+  if (total_items < workers) {                      // fewer items than workers: at least four K blocks per worker
+    const long long w = kb_all / 4 < 1 ? 1 : kb_all / 4;
+    if (w < workers) workers = static_cast<int>(w);
   }
-  if (k == 0 || kb <= 0 || kb > 0x3fffffffLL || item != p.n_munits * p.n_ntiles)
-    return fail(DRASIC_ERR_INVALID, "%s: stream_k: inconsistent work item count", who);
-  p.sk_item0[k] = item; p.sk_kb0[k] = static_cast<int>(kb);
+  int n_static = total_items / workers * workers;
+  if (n_static == total_items) return 0;            // whole waves only: nothing to balance
+  int k = 0;
+  long long kb = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    k = 0; kb = 0;
+    for (int c = 0; c < nc; ++c) {
+      const int lo = c_item[c] > n_static ? c_item[c] : n_static, hi = c_item[c] + c_n[c];
+      if (lo >= hi) continue;
+      p.sk_item0[k] = lo; p.sk_kb0[k] = static_cast<int>(kb); p.sk_nkb[k] = c_nkb[c];
+      kb += static_cast<long long>(hi - lo) * c_nkb[c];
+      ++k;
+    }
+    // every worker needs a non-empty range (a worker waits for the partials of ALL workers behind it inside its
+    // item): a remainder of very few K blocks takes one whole wave along
+    if (kb >= 4LL * workers || n_static < workers) break;
+    n_static -= workers;
+  }
+  if (k == 0 || kb < workers || kb > 0x3fffffffLL) return fail(DRASIC_ERR_INVALID, "%s: stream_k: inconsistent K-block count", who);
+  p.sk_item0[k] = total_items; p.sk_kb0[k] = static_cast<int>(kb);
   p.sk_classes = k;
   p.sk_on = 1;
-  long long w = kb / 4;                       // at least four K blocks per worker
-  if (w < 1) w = 1;
-  p.sk_workers = static_cast<int>(w < max_workers ? w : max_workers);
+  p.sk_static = n_static;
+  p.sk_workers = workers;
   p.sk_scratch = static_cast<float*>(scratch);
   p.sk_flags = static_cast<unsigned int*>(flags);
   p.tile_order = 0;

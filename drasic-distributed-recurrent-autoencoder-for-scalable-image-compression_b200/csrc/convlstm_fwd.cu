@@ -183,11 +183,15 @@ struct Walk {
     n_workers = n_workers_;
     item = worker; stride = n_workers_; total = p.n_munits * p.n_ntiles;
     g = g_end = 0;
-    if (p.sk_on) { g = range_begin(p, worker, n_workers_); g_end = range_begin(p, worker + 1, n_workers_); }
+    if (p.sk_on) {
+      total = p.sk_static;
+      g = range_begin(p, worker, n_workers_);
+      g_end = range_begin(p, worker + 1, n_workers_);
+    }
   }
   __device__ __forceinline__ bool next(const GateParams& p, Seg& s) {
     int it;
-    if (p.sk_on) {
+    if (item >= total) {   // whole items dealt: the stream-K range, if any
       if (g >= g_end) return false;
       int k = 0;
       while (k + 1 < p.sk_classes && g >= p.sk_kb0[k + 1]) ++k;
@@ -202,7 +206,6 @@ struct Walk {
       tile_split(p, it, p.n_munits, s.nt, s.mu);
       return true;
     }
-    if (item >= total) return false;
     it = item;
     item += stride;
     tile_split(p, it, p.n_munits, s.nt, s.mu);

@@ -71,14 +71,17 @@ struct GateParams {
   int pos_units, pos_upp;      // units in the position-major region; units (image tiles / pairs of them) per position
   int pos_tile_base;
   const int* pos_order;        // [H*W] pixel positions (y*W + x), most in-bounds taps first
-  // ---- stream-K schedule (sk_on): the K blocks of all work items, laid end to end in item order, are cut into
-  // one equal range per worker (CTA or CTA pair).  A worker whose range starts inside an item computes that part
-  // first and publishes the fp32 partial accumulator (sk_scratch, sk_flags); the worker that computed the item's
-  // first K block adds the partials of the workers behind it in its epilogue.  Items of class k (same K-block
-  // count: position-major units with 9 / 6 / 4 ... in-bounds taps, then the pixel-major units) are
-  // [sk_item0[k], sk_item0[k+1]) and start at global K block sk_kb0[k].
+  // ---- stream-K schedule (sk_on) of the LAST, partial wave: the first sk_static items are dealt whole, round
+  // robin, like without it (the workers then run in lockstep over the same weight K blocks, which is what the L2
+  // likes); the K blocks of the remaining items, laid end to end in item order, are cut into one equal range per
+  // worker (CTA or CTA pair).  A worker whose range starts inside an item computes that part first and publishes
+  // the fp32 partial accumulator (sk_scratch, sk_flags); the worker that computed the item's first K block adds the
+  // partials of the workers behind it in its epilogue.  Items of class k (same K-block count: position-major units
+  // with 9 / 6 / 4 ... in-bounds taps, then the pixel-major units) are [sk_item0[k], sk_item0[k+1]) and start at
+  // K block sk_kb0[k] of the stream-K region.
   int sk_on, sk_classes;
   int sk_workers;             // CTAs (CTA pairs) of a stream-K launch: all co-resident
+  int sk_static;              // items [0, sk_static) are dealt whole; a multiple of sk_workers
   int sk_item0[9], sk_kb0[9], sk_nkb[8];
   float* sk_scratch;           // [workers][CTAs per worker][BLOCK_N/16][128 rows][16] fp32
   unsigned int* sk_flags;      // [workers][CTAs per worker]: 1 while a published partial waits for its consumer
