@@ -247,8 +247,9 @@ class CodecEngine(object):
         self.pos_major = True
         self._pos_tables = {}
         # stream-K schedule of the gate / dgrad GEMMs: 'auto' = launches with fewer than SK_WAVES whole work items
-        # per CTA (pair), where dealing whole items leaves SMs idle in the last wave (every layer at B=128 has 256 or
-        # 128 items for 148 SMs) or altogether (the 4x4 layers); 'on' / 'off' force it (tests)
+        # per CTA (pair), where dealing whole items leaves most SMs idle (the 4x4 and 8x8 layers of a small batch);
+        # measured, it does not pay for launches of several waves: those are bound by L2 -> SMEM fill, a shared
+        # resource, so a last wave on half of the SMs already runs faster.  'on' / 'off' force it (tests)
         self.stream_k = stream_k
         self._sk = {}
 
@@ -258,7 +259,7 @@ class CodecEngine(object):
             self._pos_tables[key] = torch.from_numpy(position_order(h, w)).to(dev)
         return self._pos_tables[key]
 
-    SK_WAVES = 8
+    SK_WAVES = 2
 
     def _sk_buffers(self, dev):
         key = str(dev)
@@ -272,7 +273,7 @@ class CodecEngine(object):
         if self.stream_k != 'auto':
             return self.stream_k == 'on'
         workers = self.sms() // 2 if ly.pair else self.sms()
-        return ly.n_units * n_ntiles < self.SK_WAVES * workers
+        return ly.n_units * n_ntiles < self.SK_WAVES * workers and (ly.n_units * n_ntiles) % workers != 0
 
     def _plan_units(self, ly, Bp, plan, dev):
         """work units of the M dimension of one layer: per-node tile ranges (device tables of the batch plan) for
@@ -336,18 +337,26 @@ class CodecEngine(object):
         return out
 
     def _block_n(self, n_mtiles, co):
+        """N tile of a single-CTA launch.  With the stream-K schedule available the tiles stay 256 columns wide
+        (least L2 -> SMEM traffic per MMA) and a launch of few tiles is spread over the SMs along K instead;
+        without it, narrower tiles until there is one per SM."""
+        if self.stream_k != 'off':
+            return 256
         for bn in (256, 128, 64):
             if n_mtiles * (4 * co // bn) >= self.sms():
                 return bn
         return 64
 
-    def _use_pair(self, n_mtiles, hw, co):
+    def _use_pair(self, n_mtiles, hw, co, groups=1, B_pad=0):
         """CTA pairs (256-column N tiles): pair units are formed inside each node (BatchPlan.m_units), a node
         with an odd number of M tiles leaves half of its last unit idle"""
         if self.cta_pair == 'off':
             return False
         if self.cta_pair == 'on':
             return True
+        if self.stream_k != 'off':
+            # pairs whenever they do not cost the position-major tiles (which need 256 slots per pair unit)
+            return groups > 1 or B_pad >= 256 or not self.pos_major
         return (n_mtiles + 1) // 2 * (4 * co // 256) >= self.sms() // 2
 
     def _get_arena(self, B_pad, H, W, device, T=0):
@@ -505,9 +514,9 @@ class CodecEngine(object):
             ly.name, ly.cin, ly.co, ly.h, ly.w = name, cin, co, h, w
             ly.next_mode, ly.next_f32 = nmode, nf32
             ly.in_order, ly.out_order, ly.is_enc, ly.idx, ly.prefs = io, oo, is_enc, idx, prefs
-            ly.pair = self._use_pair(n_mtiles, h * w, co)
-            ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.groups = len(prefs)
+            ly.pair = self._use_pair(n_mtiles, h * w, co, ly.groups, Bp)
+            ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
             self._plan_units(ly, Bp, plan, dev)
@@ -682,9 +691,9 @@ class CodecEngine(object):
             n_mtiles = Bp * h * w // 128
             ly = _Layer()
             ly.name, ly.cin, ly.co, ly.h, ly.w, ly.next_mode, ly.next_f32 = name, cin, co, h, w, nmode, nf32
-            ly.pair = self._use_pair(n_mtiles, h * w, co)
-            ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.groups = len(dec_pref)
+            ly.pair = self._use_pair(n_mtiles, h * w, co, ly.groups, Bp)
+            ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, DEC_IDX[name]) for p in dec_pref], cin, co, io, oo,
                                                    ly.block_n, stream)[:3]
             self._plan_units(ly, Bp, plan, dev)
