@@ -526,6 +526,14 @@ def run_ours(args):
     if world > 1 and (everything or args.multi_parity):
         arm.release()
         extras['multi_gpu_parity'] = multi_gpu_parity(arm)
+    if world > 1 and everything and B % world == 0:
+        # strong scaling: the N=1 global batch spread over the ranks (the line's own value is weak scaling)
+        arm.release()
+        st = arm.record(arm.measure('train', B // world, k2, W))
+        extras['strong_scaling'] = {'global_batch': B, 'batch_per_gpu': B // world, 'value': st['value'], 'unit': 'images/s',
+                                    'ms_per_step': st['ms_per_step'], 'e2e': st['e2e'], 'roofline': st['roofline'],
+                                    'kernels_ms_per_step': st['kernels_ms_per_step'],
+                                    'note': 'same global batch as the N=1 line; efficiency = value / (N x the N=1 value)'}
     if world == 1 and not args.no_cpu:
         arm.release()
         extras['parity'] = parity_check(arm, PARITY_SAMPLE)
@@ -579,7 +587,10 @@ def main():
     ap.add_argument('--no-fast', action='store_true', help='skip the secondary fast-precision measurement')
     args = ap.parse_args()
     if args.shard == 'auto':
-        args.shard = 'batch'
+        # with at least as many sources as ranks every rank owns whole nodes (their encoders and samples)
+        # and only the joint decoder's gradients are exchanged
+        world = int(os.environ.get('WORLD_SIZE', '1'))
+        args.shard = 'source' if (world > 1 and M_NODES >= world) else 'batch'
     global STREAM_K
     STREAM_K = args.stream_k
     if args.impl == 'reference':

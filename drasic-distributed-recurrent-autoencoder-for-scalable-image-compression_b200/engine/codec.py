@@ -275,6 +275,19 @@ class CodecEngine(object):
         workers = self.sms() // 2 if ly.pair else self.sms()
         return ly.n_units * n_ntiles < self.SK_WAVES * workers and (ly.n_units * n_ntiles) % workers != 0
 
+    @staticmethod
+    def _active_groups(ly, plan):
+        """which weight groups (nodes) of a layer this batch touches.  ly.active: None (all: a single group, or a
+        static plan whose node counts change per replay) or the list of nodes that have samples.  When exactly one
+        node of a per-node layer has samples -- a rank of a source-sharded run that owns one node, single-source
+        data through a multi-node model -- the layer runs as ONE group on that node's weight planes (ly.g0), which
+        opens the position-major tiles to it."""
+        ly.active, ly.g0, ly.gemm_groups = None, 0, ly.groups
+        if ly.groups > 1 and plan is not None and not plan.static:
+            ly.active = [int(j) for j in np.nonzero(plan.counts)[0]]
+            if len(ly.active) == 1:
+                ly.g0, ly.gemm_groups = ly.active[0], 1
+
     def _plan_units(self, ly, Bp, plan, dev):
         """work units of the M dimension of one layer: per-node tile ranges (device tables of the batch plan) for
         grouped layers; for a layer shared by the whole batch, position-major tiles over as many slots as fill whole
@@ -282,7 +295,7 @@ class CodecEngine(object):
         hw = ly.h * ly.w
         n_mtiles = Bp * hw // 128
         ly.units, ly.pos_imgs, ly.pos_order = None, 0, None
-        if ly.groups > 1:
+        if getattr(ly, 'gemm_groups', ly.groups) > 1:
             ly.units, ly.n_units = plan.m_units(hw, ly.pair)
             return
         unit_imgs = 256 if ly.pair else 128
@@ -355,8 +368,10 @@ class CodecEngine(object):
         if self.cta_pair == 'on':
             return True
         if self.stream_k != 'off':
-            # pairs whenever they do not cost the position-major tiles (which need 256 slots per pair unit)
-            return groups > 1 or B_pad >= 256 or not self.pos_major
+            # pairs, unless they cost position-major tiles that are worth more: a pair unit needs 256 slots, and below
+            # that only the 4x4 layers skip enough padding taps (30 %) to make up for single-CTA tiles (measured at
+            # B=128: D1 single + position-major 110 us vs 108; D2 363 vs 378; D3 166 vs 160 for pairs)
+            return groups > 1 or B_pad >= 256 or not self.pos_major or B_pad < 128 or hw > 64
         return (n_mtiles + 1) // 2 * (4 * co // 256) >= self.sms() // 2
 
     def _get_arena(self, B_pad, H, W, device, T=0):
@@ -393,36 +408,46 @@ class CodecEngine(object):
         self._arena, self._arena_key = A, key
         return A
 
-    def _packed(self, name, weights, cin, co, in_order, out_order, block_n, stream):
-        """weights: list over groups of (w_in, w_h) fp32 tensors. Cached on tensor identity+version."""
+    def _packed(self, name, weights, cin, co, in_order, out_order, block_n, stream, needed=None):
+        """weights: list over groups of (w_in, w_h) fp32 tensors.  Cached on tensor identity + version; within one
+        cache generation only the groups a call needs (`needed`: nodes that have samples in this batch; None = all)
+        are packed -- a rank of a source-sharded run never packs the encoders of the other ranks' nodes."""
         key = (name, block_n) + tuple((w.data_ptr(), w._version) for pair in weights for w in pair)
         hit = self._wcache.get(name)
-        if hit is not None and hit[0] == key and not (self.force_pack or self._repack):
+        G = len(weights)
+        need = set(range(G)) if needed is None else set(int(g) for g in needed)
+        if hit is not None and hit[0] == key and not (self.force_pack or self._repack) and need <= hit[2]:
             return hit[1]
         L = B.lib()
-        G = len(weights)
         dev = weights[0][0].device
         K = 9 * (cin + co)
+        fresh = set()
         if hit is not None and hit[0][:2] == key[:2] and hit[1][0].shape == (G * 4 * co, K):
             hi, lo, inv, _, scratch = hit[1]                   # repack into the same (graph-static) buffers
+            if hit[0] == key and not (self.force_pack or self._repack):
+                fresh = hit[2]                                 # same generation: only the missing groups
         else:
             hi = torch.empty((G * 4 * co, K), dtype=torch.float16, device=dev)
             lo = torch.empty((G * 4 * co, K), dtype=torch.float16, device=dev)
             inv = torch.empty((G,), dtype=torch.float32, device=dev)
             scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
         plane = 4 * co * K * 2
+        w_in = w_h = None
         for g, (w_in, w_h) in enumerate(weights):
             if tuple(w_in.shape) != (4 * co, cin, 3, 3) or tuple(w_h.shape) != (4 * co, co, 3, 3):
                 raise ValueError('Not valid ConvLSTM weight shape for {}'.format(name))
+            if g in fresh or g not in need:
+                continue
             w_in = w_in.detach().contiguous()
             w_h = w_h.detach().contiguous()
-            B.check(L.drasic_pack_lstm_weights(w_in.data_ptr(), w_h.data_ptr(), cin, co, in_order, out_order,
-                                               block_n, hi.data_ptr() + g * plane, lo.data_ptr() + g * plane,
-                                               inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
-                    'pack_lstm_weights')
+            self._timed('pack_weights', 0.0, lambda: B.check(
+                L.drasic_pack_lstm_weights(w_in.data_ptr(), w_h.data_ptr(), cin, co, in_order, out_order,
+                                           block_n, hi.data_ptr() + g * plane, lo.data_ptr() + g * plane,
+                                           inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
+                'pack_lstm_weights'))
             self.launches += 2
         val = (hi, lo, inv, (w_in, w_h), scratch)
-        self._wcache[name] = (key, val)
+        self._wcache[name] = (key, val, fresh | need)
         return val
 
     # ------------------------------------------------------------------ the loop
@@ -515,10 +540,11 @@ class CodecEngine(object):
             ly.next_mode, ly.next_f32 = nmode, nf32
             ly.in_order, ly.out_order, ly.is_enc, ly.idx, ly.prefs = io, oo, is_enc, idx, prefs
             ly.groups = len(prefs)
-            ly.pair = self._use_pair(n_mtiles, h * w, co, ly.groups, Bp)
+            self._active_groups(ly, plan)
+            ly.pair = self._use_pair(n_mtiles, h * w, co, ly.gemm_groups, Bp)
             ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, idx) for p in prefs], cin, co, io, oo,
-                                                   ly.block_n, stream)[:3]
+                                                   ly.block_n, stream, needed=ly.active)[:3]
             self._plan_units(ly, Bp, plan, dev)
             layers.append(ly)
 
@@ -589,7 +615,8 @@ class CodecEngine(object):
             a.x_hi, a.x_lo = P(x_planes[0]), P(x_planes[1])
             if t > 0:
                 a.h_hi, a.h_lo = P(prv[0]), P(prv[1])
-            a.w_hi, a.w_lo, a.w_inv_scale = P(ly.hi), P(ly.lo), P(ly.inv)
+            wplane = ly.g0 * 4 * ly.co * 9 * (ly.cin + ly.co) * 2        # (a collapsed layer reads its one node's planes)
+            a.w_hi, a.w_lo, a.w_inv_scale = P(ly.hi) + wplane, (P(ly.lo) + wplane) if ly.lo is not None else None, P(ly.inv) + 4 * ly.g0
             a.h_out_hi, a.h_out_lo = P(cur[0]), P(cur[1])
             a.next_hi, a.next_lo = P(nxt[0]), P(nxt[1])
             a.group_mtile_start = ly.units[0].data_ptr() if ly.units is not None else None
@@ -601,7 +628,7 @@ class CodecEngine(object):
                 a.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
                 a.sk_scratch, a.sk_flags = P(sk_s), P(sk_f)
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
-            a.n_groups = ly.groups
+            a.n_groups = ly.gemm_groups
             a.has_state = 1 if t > 0 else 0
             a.next_mode, a.next_f32 = ly.next_mode, ly.next_f32
             a.split, a.precise, a.block_n = self.split, self.precise, ly.block_n
@@ -692,10 +719,11 @@ class CodecEngine(object):
             ly = _Layer()
             ly.name, ly.cin, ly.co, ly.h, ly.w, ly.next_mode, ly.next_f32 = name, cin, co, h, w, nmode, nf32
             ly.groups = len(dec_pref)
-            ly.pair = self._use_pair(n_mtiles, h * w, co, ly.groups, Bp)
+            self._active_groups(ly, plan)
+            ly.pair = self._use_pair(n_mtiles, h * w, co, ly.gemm_groups, Bp)
             ly.block_n = 256 if ly.pair else self._block_n(n_mtiles, co)
             ly.hi, ly.lo, ly.inv = self._packed(name, [lstm_w(p, DEC_IDX[name]) for p in dec_pref], cin, co, io, oo,
-                                                   ly.block_n, stream)[:3]
+                                                   ly.block_n, stream, needed=ly.active)[:3]
             self._plan_units(ly, Bp, plan, dev)
             layers.append(ly)
         self._repack = False      # (the encoder planes stay stale: _stale is cleared only by a full forward)
@@ -725,7 +753,8 @@ class CodecEngine(object):
                 g.x_hi, g.x_lo = P(x[0]), P(x[1])
                 if t > 0:
                     g.h_hi, g.h_lo = P(prv[0]), P(prv[1])
-                g.w_hi, g.w_lo, g.w_inv_scale = P(ly.hi), P(ly.lo), P(ly.inv)
+                wplane = ly.g0 * 4 * ly.co * 9 * (ly.cin + ly.co) * 2
+                g.w_hi, g.w_lo, g.w_inv_scale = P(ly.hi) + wplane, P(ly.lo) + wplane, P(ly.inv) + 4 * ly.g0
                 g.h_out_hi, g.h_out_lo = P(cur[0]), P(cur[1])
                 g.next_hi, g.next_lo = P(nxt[0]), P(nxt[1])
                 g.group_mtile_start = ly.units[0].data_ptr() if ly.units is not None else None
@@ -737,7 +766,7 @@ class CodecEngine(object):
                     g.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
                     g.sk_scratch, g.sk_flags = P(sk_s), P(sk_f)
                 g.B_pad, g.H, g.W, g.Cin, g.Co = Bp, ly.h, ly.w, ly.cin, ly.co
-                g.n_groups, g.has_state = ly.groups, 1 if t > 0 else 0
+                g.n_groups, g.has_state = ly.gemm_groups, 1 if t > 0 else 0
                 g.next_mode, g.next_f32 = ly.next_mode, ly.next_f32
                 g.split, g.precise, g.block_n, g.cta_pair = self.split, self.precise, ly.block_n, int(ly.pair)
                 B.check(L.drasic_convlstm_fwd(g, stream), 'convlstm_fwd (decode)')
@@ -763,7 +792,8 @@ class CodecEngine(object):
         weights = [lstm_w(p, ly.idx) for p in ly.prefs]
         key = tuple((w.data_ptr(), w._version) for pair in weights for w in pair)
         hit = self._wcache.get('dgrad_' + ly.name)
-        if hit is not None and hit[0] == key and not (self.force_pack or self._repack):
+        need = set(range(len(weights))) if ly.active is None else set(ly.active)
+        if hit is not None and hit[0] == key and not (self.force_pack or self._repack) and need <= hit[2]:
             return hit[1][:3]
         L = B.lib()
         dev = weights[0][0].device
@@ -777,13 +807,16 @@ class CodecEngine(object):
             scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
         plane = n_out * K * 2
         for g, (w_in, w_h) in enumerate(weights):
+            if g not in need:
+                continue
             w_in, w_h = w_in.detach().contiguous(), w_h.detach().contiguous()
-            B.check(L.drasic_pack_dgrad_weights(w_in.data_ptr(), w_h.data_ptr(), ly.cin, ly.co, ly.in_order,
-                                                ly.out_order, hi.data_ptr() + g * plane, lo.data_ptr() + g * plane,
-                                                inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
-                    'pack_dgrad_weights')
+            self._timed('pack_dgrad_weights', 0.0, lambda: B.check(
+                L.drasic_pack_dgrad_weights(w_in.data_ptr(), w_h.data_ptr(), ly.cin, ly.co, ly.in_order,
+                                            ly.out_order, hi.data_ptr() + g * plane, lo.data_ptr() + g * plane,
+                                            inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
+                'pack_dgrad_weights'))
             self.launches += 2
-        self._wcache['dgrad_' + ly.name] = (key, (hi, lo, inv, scratch))
+        self._wcache['dgrad_' + ly.name] = (key, (hi, lo, inv, scratch), need)
         return hi, lo, inv
 
     def _bwd_buffers(self, layers, Bp, H, W, dev):
@@ -892,8 +925,9 @@ class CodecEngine(object):
                 planes_ready.record(main)
             hi, lo, inv = dpk[ly.name]
             a = B.DgradArgs()
-            a.dg_hi, a.dg_lo, a.w_hi, a.w_lo = P(dg_hi), P(dg_lo), P(hi), P(lo)
-            a.w_inv_scale, a.dg_inv_scale = P(inv), P(inv_dg)
+            dplane = ly.g0 * (ly.cin + ly.co) * 36 * ly.co * 2
+            a.dg_hi, a.dg_lo, a.w_hi, a.w_lo = P(dg_hi), P(dg_lo), P(hi) + dplane, P(lo) + dplane
+            a.w_inv_scale, a.dg_inv_scale = P(inv) + 4 * ly.g0, P(inv_dg)
             a.dx_out = P(dx_of[ly.name][0])
             a.dhrec_out = P(wb['dh_rec']) if t > 0 else None
             a.group_mtile_start = ly.units[0].data_ptr() if ly.units is not None else None
@@ -905,7 +939,7 @@ class CodecEngine(object):
                 a.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
                 a.sk_scratch, a.sk_flags = P(sk_s), P(sk_f)
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
-            a.n_groups, a.dx_mode, a.split = ly.groups, dx_of[ly.name][1], self.gsplit
+            a.n_groups, a.dx_mode, a.split = ly.gemm_groups, dx_of[ly.name][1], self.gsplit
             a.cta_pair = int(ly.pair)
             fl = 2.0 * Bn * ly.h * ly.w * 36 * ly.co * (ly.cin + (ly.co if t > 0 else 0))
             self._timed('dgrad_' + ly.name, fl, lambda: B.check(L.drasic_convlstm_bwd_data(a, stream), 'convlstm_bwd_data'))
@@ -974,27 +1008,43 @@ class CodecEngine(object):
             main.wait_stream(side)          # join: the unpack below reads the accumulated weight gradients
         for ly in layers:
             WB[ly.name]['last_amax'].copy_(amax_tab[ly.name][T - 1:T])
-        grads = {}
+        # Every gradient is a view of ONE flat fp32 buffer laid out in the state_dict's own order (model.encoder.* then
+        # model.decoder.*): the all-reduce of a multi-GPU step is then a single in-place collective on the buffer --
+        # or on the contiguous slice that holds the joint decoder when the batch is sharded by source (engine/dist.py).
+        # Gradients of nodes without samples are zero, like autograd's for an unused encoder would be None -> zero.
+        offs, total = {}, 0
+        for k, v in sd.items():
+            offs[k] = total
+            total += v.numel()
+        flat = torch.zeros((total,), **f32)
+
+        def view(k):
+            v = sd[k]
+            return flat[offs[k]:offs[k] + v.numel()].view(v.shape)
+        grads = {k: view(k) for k in sd}
         for ly in layers:
             for g, pref in enumerate(ly.prefs):
+                if ly.active is not None and g not in ly.active:
+                    continue                                          # no samples: the zeros of `flat` stand
                 base = '{}.{}.cell.cell.0.'.format(pref, ly.idx)
-                dwi = torch.empty((4 * ly.co, ly.cin, 3, 3), **f32)
-                dwh = torch.empty((4 * ly.co, ly.co, 3, 3), **f32)
-                B.check(L.drasic_unpack_wgrad(gw[ly.name][g].data_ptr(), ly.cin, ly.co, ly.in_order, ly.out_order,
-                                              dwi.data_ptr(), dwh.data_ptr(), stream), 'unpack_wgrad')
+                dwi, dwh = grads[base + 'in.cell.cell.main.weight'], grads[base + 'hidden.cell.cell.main.weight']
+                self._timed('unpack_wgrad', 0.0, lambda: B.check(
+                    L.drasic_unpack_wgrad(gw[ly.name][g].data_ptr(), ly.cin, ly.co, ly.in_order, ly.out_order,
+                                          dwi.data_ptr(), dwh.data_ptr(), stream), 'unpack_wgrad'))
                 self.launches += 1
-                grads[base + 'in.cell.cell.main.weight'] = dwi
-                grads[base + 'hidden.cell.cell.main.weight'] = dwh
+        dst, src = [], []
         for j, pref in enumerate(ctx['enc_pref']):
-            grads[pref + '.0.cell.cell.main.weight'] = dw_e0[j].reshape(sd[pref + '.0.cell.cell.main.weight'].shape)
+            dst.append(grads[pref + '.0.cell.cell.main.weight']); src.append(dw_e0[j].reshape(dst[-1].shape))
             if db_e0 is not None:
-                grads[pref + '.0.cell.cell.main.bias'] = db_e0[j].reshape(sd[pref + '.0.cell.cell.main.bias'].shape)
-            grads[pref + '.7.cell.cell.main.weight'] = dw_e4[j].reshape(sd[pref + '.7.cell.cell.main.weight'].shape)
+                dst.append(grads[pref + '.0.cell.cell.main.bias']); src.append(db_e0[j].reshape(dst[-1].shape))
+            dst.append(grads[pref + '.7.cell.cell.main.weight']); src.append(dw_e4[j].reshape(dst[-1].shape))
         for j, pref in enumerate(ctx['dec_pref']):
-            grads[pref + '.0.cell.cell.main.weight'] = dw_d0[j].reshape(sd[pref + '.0.cell.cell.main.weight'].shape)
-            grads[pref + '.7.cell.cell.main.weight'] = dw_d4[j].reshape(sd[pref + '.7.cell.cell.main.weight'].shape)
+            dst.append(grads[pref + '.0.cell.cell.main.weight']); src.append(dw_d0[j].reshape(dst[-1].shape))
+            dst.append(grads[pref + '.7.cell.cell.main.weight']); src.append(dw_d4[j].reshape(dst[-1].shape))
+        torch._foreach_copy_(dst, src)
         if g_loss is not None:
-            torch._foreach_mul_(list(grads.values()), g_loss)      # chain rule for d(anything)/d(loss), in place
+            flat.mul_(g_loss)                                      # chain rule for d(anything)/d(loss), in place
+        self.grad_flat, self.grad_offsets = flat, offs             # (engine/dist.py reduces the buffer in place)
         return grads
 
     @staticmethod

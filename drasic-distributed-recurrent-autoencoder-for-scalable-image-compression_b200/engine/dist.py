@@ -28,14 +28,39 @@ def shard_range(n_global, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def flat_gradient_view(params):
+    """The gradients of `params` as ONE 1-D tensor when they are adjacent views of one buffer (the engine's
+    backward lays every gradient out in a single flat fp32 buffer in state_dict order, engine/codec.py), else None."""
+    grads = [p.grad for p in params]
+    if not grads or any(g is None or not g.is_contiguous() or g.dtype != grads[0].dtype for g in grads):
+        return None
+    store = grads[0].untyped_storage()
+    if any(g.untyped_storage().data_ptr() != store.data_ptr() for g in grads):
+        return None
+    order = sorted(grads, key=lambda g: g.storage_offset())
+    off = order[0].storage_offset()
+    for g in order:
+        if g.storage_offset() != off:
+            return None
+        off += g.numel()
+    first = order[0].storage_offset()
+    return torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(store, first, (off - first,))
+
+
 def allreduce_gradients(params, n_local, n_global, group=None, bucket_bytes=1 << 28):
     """In place: p.grad <- sum_r (n_r / N) * p.grad_r for every parameter (missing grads count as zero).
-    Gradients travel in a few large fp32 buckets: NVSwitch makes collective cost latency-, not
-    link-bound, so buckets are sized for launch count."""
+    When the gradients are views of one flat buffer -- what the engine's backward produces -- this is ONE in-place
+    collective on that buffer, no flatten / unflatten copies.  Otherwise they travel in a few large fp32 buckets:
+    NVSwitch makes collective cost latency-, not link-bound, so buckets are sized for launch count."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
     w = float(n_local) / float(n_global)
     params = [p for p in params if p.requires_grad]
+    flat = flat_gradient_view(params)
+    if flat is not None:
+        flat.mul_(w)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return 1
     for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)
@@ -113,12 +138,15 @@ def reduce_source_sharded(model, n_local, n_global, rank=None, world=None, group
     shared, per_node = split_parameters(model)
     n = allreduce_gradients(shared, n_local, n_global, group=group)
     w = float(n_local) / float(n_global)
+    mine = []
     for j, ps in per_node.items():
         for p in ps:
             if j % world != rank:
                 p.grad = None
             elif p.grad is not None and world > 1:
-                p.grad.mul_(w)
+                mine.append(p.grad)
+    if mine:
+        torch._foreach_mul_(mine, w)
     return n
 
 

@@ -222,3 +222,21 @@ def test_source_sharded_checkpoint_round_trip(tmp_path):
         results = mgr.dict()
         mp.spawn(_ckpt_worker, args=(world, port, str(tmp_path), results), nprocs=world, join=True)
         assert results[0] and results[1]
+
+
+def test_flat_gradient_view():
+    """adjacent views of one buffer are recognised (one in-place collective); anything else is not"""
+    from engine.dist import flat_gradient_view
+    flat = torch.arange(20, dtype=torch.float32)
+    ps = [torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(5, 2))]
+    ps[0].grad, ps[1].grad, ps[2].grad = flat[0:6].view(2, 3), flat[6:10], flat[10:20].view(5, 2)
+    v = flat_gradient_view(ps)
+    assert v is not None and v.numel() == 20 and v.data_ptr() == flat.data_ptr()
+    v.mul_(2.0)
+    assert float(ps[2].grad[4, 1]) == 38.0
+    assert flat_gradient_view(ps[1:]).numel() == 14                         # a contiguous sub-range (the joint decoder)
+    assert flat_gradient_view([ps[0], ps[2]]) is None                       # a gap
+    ps[1].grad = torch.zeros(4)
+    assert flat_gradient_view(ps) is None                                   # another buffer
+    ps[1].grad = None
+    assert flat_gradient_view(ps) is None
