@@ -185,7 +185,7 @@ def test_config5_kodak_patches_properties():
     out_sub = run(m, patches[sub], label[sub])
     assert torch.equal(out_sub['code_pm1'], codes[:, sub.cuda()])
     # (the 64-image launch runs the stream-K schedule, the 4096-image one whole tiles: fp32 summation order differs)
-    assert (out_sub['img'][-1] - out['img'][-1][sub.cuda()]).abs().max().item() < 1e-5
+    assert (out_sub['img'][-1] - out['img'][-1][sub.cuda()]).abs().max().item() < 5e-5     # (16 cumulative refinements)
     # (2) the code is progressive: a T=8 run emits the first 8 iterations of the T=16 run
     import config
     config.PARAM['num_iter'] = 8
