@@ -315,3 +315,48 @@ def test_stream_k_schedule_vs_oracle(M, B, T, cta_pair):
         else:
             assert rel_err(p.grad.cpu(), sdg[k].grad) < GRAD_TOL['fp16'], k
     assert int(m._engine._sk_buffers(torch.device('cuda', 0))[1].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('name,B', [('dist_codec', 40), ('dist_codec', 264), ('sep_codec', 24)])
+def test_single_active_node_runs_as_one_group(name, B):
+    """All samples of a batch on ONE node of a multi-node model (what a rank of a source-sharded run sees):
+    the per-node layers run as a single group on that node's weight planes -- position-major tiles included at
+    B >= 256 -- and only that node's weights are packed.  Eval and training step against the oracle."""
+    M, T, node = 4, 3, 2
+    m = build_model(name, 'CIFAR10', M, T, seed=47)
+    sep = name == 'sep_codec'
+    g = torch.Generator().manual_seed(48)
+    img = torch.rand(B, 3, 32, 32, generator=g)
+    label = torch.full((B,), node, dtype=torch.long)
+    sub = torch.arange(0, B, max(1, B // 20))[:20]
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.codec_forward(sd, img[sub], label[sub], T, M, separate=sep)
+    out = run(m, img, label)
+    enc_layers = [ly for ly in m._engine._last_layers if ly.is_enc]
+    assert all(ly.gemm_groups == 1 and ly.g0 == node and ly.active == [node] for ly in enc_layers)
+    if B >= 256:
+        assert all(ly.pos_imgs == 256 for ly in enc_layers)
+    codes, refc = out['code_pm1'].cpu()[:, sub], torch.stack(ref['code_pm1'])
+    assert torch.equal(codes, refc)
+    assert (torch.stack(out['img']).cpu()[:, sub] - torch.stack(ref['img'])).abs().max().item() < RECON_TOL
+    # training step: the other nodes' gradients are exactly zero, the active node's match autograd
+    Bt = 12
+    sdg = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    noise = torch.rand(T, Bt, 8, 4, 4, generator=g)
+    rt = O.codec_forward(sdg, img[:Bt], label[:Bt], T, M, training=True, noise=[n for n in noise], separate=sep)
+    rt['loss'].backward()
+    tr = train_step(m, img[:Bt], label[:Bt], noise)
+    assert abs(tr['loss'].item() - rt['loss'].item()) < 1e-5
+    for k, p in m.named_parameters():
+        if sdg[k].grad is None:
+            assert float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert rel_err(p.grad.cpu(), sdg[k].grad) < GRAD_TOL['fp16'], k
+    # a later batch that touches another node packs that node's weights then
+    label2 = label.clone()
+    label2[::2] = 0
+    with torch.no_grad():
+        ref2 = O.codec_forward(sd, img[sub], label2[sub], T, M, separate=sep)
+    out2 = run(m, img, label2)
+    assert torch.equal(out2['code_pm1'].cpu()[:, sub], torch.stack(ref2['code_pm1']))
