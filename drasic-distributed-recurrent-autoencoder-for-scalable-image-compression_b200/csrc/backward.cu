@@ -34,6 +34,8 @@ __device__ __forceinline__ int shift_for(float amax, int target_exp) {
 }
 
 __global__ void __launch_bounds__(256, 3) lstm_bwd_fused_kernel(const LstmBwdFusedParams p) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   // predicted scale: the previous iteration's amax lands in [2^11, 2^12) -- 16x head-room for growth
   const int shift_pred = shift_for(__uint_as_float(*p.prev_amax_bits), 12);
   int shift = shift_pred;
@@ -192,6 +194,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ gw, int Cin, int C
 // ------------------------------------------------------------------ bottleneck backward
 // forward (pointwise.cu bottleneck_kernel): z = tanh(W4 h3); q = Q(z) (straight-through); d0 = tanh(W0 q)
 __global__ void __launch_bounds__(128) bottleneck_bwd_kernel(const BottleneckBwdParams p) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   extern __shared__ float sm[];
   const int HW = p.HW, CH = p.Ch, code = p.code;
   float* s_a = sm;                    // [HW][CH]   dd0 -> dpre0
@@ -289,6 +293,8 @@ struct QuadMapB {  // quad-major pixel index -> raster pixel offset
 // iteration t: G = (has_acc ? G : 0) + dLoss_t/dRecon_t ; d = tanh(W4 v4) ; backward through it
 template <int NC>
 __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdParams p) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   __shared__ float s_acc[MAXC * FEATB];
   __shared__ alignas(16) float s_w4[MAXC][4][8];   // [c][sub][j]
   const int HW = p.H * p.W;
@@ -425,6 +431,8 @@ __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdPa
 // iteration t: e0 = tanh(W0 x + b) recomputed; backward to W0, b and (dist codec, t > 0) to recon_{t-1}
 template <int NC>
 __global__ void __launch_bounds__(TB_THREADS, 3) head_bwd_kernel(const HeadBwdParams p) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   __shared__ float s_acc[FEATB * MAXC + FEATB];
   __shared__ alignas(16) float s_w0[4][8][MAXC];   // [sub][j][c]
   __shared__ alignas(16) float s_b0[4][8];
@@ -566,7 +574,7 @@ int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream) {
   // the verify pass almost always returns at once: one resident wave (3 blocks per SM) keeps its launch short and
   // still runs at full bandwidth (grid-stride loop) when the tensor does have to be redone
   if (p.verify && grid > 148 * 3) grid = 148 * 3;
-  lstm_bwd_fused_kernel<<<grid, 256, 0, stream>>>(p);
+  launch_pdl(lstm_bwd_fused_kernel, dim3(grid), dim3(256), 0, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
@@ -587,7 +595,7 @@ int launch_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_
 }
 int launch_bottleneck_bwd(const BottleneckBwdParams& p, cudaStream_t stream) {
   const size_t smem = (static_cast<size_t>(2) * p.HW * p.Ch + 2 * p.HW * p.code) * sizeof(float);
-  bottleneck_bwd_kernel<<<p.B_pad, 128, smem, stream>>>(p);
+  launch_pdl(bottleneck_bwd_kernel, dim3(p.B_pad), dim3(128), smem, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_tail_bwd(const TailBwdParams& p, cudaStream_t stream) {
@@ -595,10 +603,10 @@ int launch_tail_bwd(const TailBwdParams& p, cudaStream_t stream) {
   if (HW % TB_THREADS != 0 || p.C > MAXC || p.C < 1) return static_cast<int>(cudaErrorInvalidValue);
   const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TB_PIX, 148 * 6);
   switch (p.C) {
-    case 1: tail_bwd_kernel<1><<<grid, TB_THREADS, 0, stream>>>(p); break;
-    case 2: tail_bwd_kernel<2><<<grid, TB_THREADS, 0, stream>>>(p); break;
-    case 3: tail_bwd_kernel<3><<<grid, TB_THREADS, 0, stream>>>(p); break;
-    default: tail_bwd_kernel<4><<<grid, TB_THREADS, 0, stream>>>(p); break;
+    case 1: launch_pdl(tail_bwd_kernel<1>, dim3(grid), dim3(TB_THREADS), 0, stream, p); break;
+    case 2: launch_pdl(tail_bwd_kernel<2>, dim3(grid), dim3(TB_THREADS), 0, stream, p); break;
+    case 3: launch_pdl(tail_bwd_kernel<3>, dim3(grid), dim3(TB_THREADS), 0, stream, p); break;
+    default: launch_pdl(tail_bwd_kernel<4>, dim3(grid), dim3(TB_THREADS), 0, stream, p); break;
   }
   return static_cast<int>(cudaGetLastError());
 }
@@ -607,10 +615,10 @@ int launch_head_bwd(const HeadBwdParams& p, cudaStream_t stream) {
   if (HW % TB_THREADS != 0 || p.C > MAXC || p.C < 1) return static_cast<int>(cudaErrorInvalidValue);
   const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TB_PIX, 148 * 6);
   switch (p.C) {
-    case 1: head_bwd_kernel<1><<<grid, TB_THREADS, 0, stream>>>(p); break;
-    case 2: head_bwd_kernel<2><<<grid, TB_THREADS, 0, stream>>>(p); break;
-    case 3: head_bwd_kernel<3><<<grid, TB_THREADS, 0, stream>>>(p); break;
-    default: head_bwd_kernel<4><<<grid, TB_THREADS, 0, stream>>>(p); break;
+    case 1: launch_pdl(head_bwd_kernel<1>, dim3(grid), dim3(TB_THREADS), 0, stream, p); break;
+    case 2: launch_pdl(head_bwd_kernel<2>, dim3(grid), dim3(TB_THREADS), 0, stream, p); break;
+    case 3: launch_pdl(head_bwd_kernel<3>, dim3(grid), dim3(TB_THREADS), 0, stream, p); break;
+    default: launch_pdl(head_bwd_kernel<4>, dim3(grid), dim3(TB_THREADS), 0, stream, p); break;
   }
   return static_cast<int>(cudaGetLastError());
 }

@@ -126,6 +126,12 @@ int drasic_device_sms(void) {
   return n;
 }
 
+int drasic_set_pdl(int enable) {
+  const int was = drasic::pdl_enabled() ? 1 : 0;
+  drasic::set_pdl(enable != 0);
+  return was;
+}
+
 size_t drasic_stream_k_scratch_bytes(void) { return drasic::SK_MAX_WORKERS * drasic::SK_SLOT_FLOATS * sizeof(float); }
 size_t drasic_stream_k_flag_bytes(void) { return drasic::SK_MAX_WORKERS * sizeof(unsigned int); }
 

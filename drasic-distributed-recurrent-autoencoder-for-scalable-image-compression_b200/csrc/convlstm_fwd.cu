@@ -394,6 +394,7 @@ template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ GateParams p) {
   using C = Cfg<SPLIT, BLOCK_N, PAIR>;
+  ptx::griddep_launch_dependents();
   const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
@@ -452,6 +453,8 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
   if (PAIR) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, tensor memory and descriptor prefetches are set up: from here on the kernel reads what its predecessor wrote
+  ptx::griddep_wait();
 
   // tile walk: a work unit is one M tile (1 CTA) or one pair of adjacent M tiles (CTA pair) x one N tile
   const int n_workers = PAIR ? gridDim.x >> 1 : gridDim.x;
@@ -720,7 +723,7 @@ int max_workers_t(int num_sms) {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
   if (!cached[dev]) {
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     pair_launch_config<SPLIT, BLOCK_N, EPI, PAIR>(cfg, attr, 2 * (num_sms / 2), nullptr);
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<SPLIT, BLOCK_N, EPI, PAIR>, &cfg) != cudaSuccess) n = 0;
@@ -743,13 +746,15 @@ int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
     workers = p.sk_workers;
     if (workers < 1 || workers > max_workers_t<SPLIT, BLOCK_N, EPI, PAIR>(num_sms)) return static_cast<int>(cudaErrorInvalidValue);
   }
-  if (!PAIR) {
-    kern<<<workers, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
-    return static_cast<int>(cudaGetLastError());
-  }
+  if (!PAIR) return static_cast<int>(launch_pdl(kern, dim3(workers), dim3(NUM_THREADS), C::SMEM_BYTES, stream, p));
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   pair_launch_config<SPLIT, BLOCK_N, EPI, PAIR>(cfg, attr, 2 * workers, stream);
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, p));
 }
 
@@ -798,6 +803,10 @@ int launch_convlstm_dgrad(const GateParams& p, bool split, bool pair, int num_sm
   return split ? launch_t<true, 256, EPI_DGRAD, false>(p, num_sms, stream)
                : launch_t<false, 256, EPI_DGRAD, false>(p, num_sms, stream);
 }
+
+namespace { bool g_pdl = true; }
+bool pdl_enabled() { return g_pdl; }
+void set_pdl(bool on) { g_pdl = on; }
 
 int conv_gemm_max_workers(bool split, int block_n, bool dgrad, bool pair, int num_sms) {
   if (dgrad) {

@@ -5,7 +5,31 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <utility>
+
 namespace drasic {
+
+// Programmatic dependent launch (PDL): the kernels of the loop are launched so that each may start -- be scheduled,
+// run its prologue -- while the tail of its predecessor still executes; every such kernel calls ptx::griddep_wait()
+// before it touches global memory.  drasic_set_pdl(0) turns it off (plain stream order).
+bool pdl_enabled();
+void set_pdl(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 constexpr int TILE_M = 128;     // UMMA M: pixels per output tile (= TMEM lanes)
 constexpr int BLOCK_K = 64;     // fp16 elements per K block = one 128-byte swizzle row

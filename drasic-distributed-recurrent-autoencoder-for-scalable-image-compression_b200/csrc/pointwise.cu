@@ -41,6 +41,8 @@ __device__ __forceinline__ void store_split(__half* hi, __half* lo, float v, boo
 // padded batch (a 32x32 patch has HW = 16 code pixels: one CTA per image; an un-tiled 768x512 image has
 // 6144: 192 CTAs per image)
 __global__ void __launch_bounds__(128) bottleneck_kernel(const BottleneckParams p) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   extern __shared__ float sm[];
   const int HW = p.HW, CH = p.Ch, code = p.code;
   const int P = HW < 32 ? HW : 32;
@@ -184,6 +186,8 @@ constexpr int TAIL_STAGES = 2;   // chunks of 16 pixels (2 KB) in flight per war
 
 template <bool PRECISE, int NC>
 __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_head_kernel(const TailParams p) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   constexpr int U = TAIL_U;
   using Stream = WarpStream<U, TAIL_STAGES>;
   __shared__ double s_red[2][TAIL_THREADS / 32];
@@ -461,7 +465,7 @@ int launch_bottleneck(const BottleneckParams& p, cudaStream_t stream) {
   const int P = p.HW < 32 ? p.HW : 32;
   if (p.HW % P || (p.code * P) % 32) return static_cast<int>(cudaErrorInvalidValue);
   const size_t smem = static_cast<size_t>(P) * (p.Ch + p.code) * sizeof(float);
-  bottleneck_kernel<<<p.B_pad * (p.HW / P), 128, smem, stream>>>(p);
+  launch_pdl(bottleneck_kernel, dim3(p.B_pad * (p.HW / P)), dim3(128), smem, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -479,8 +483,8 @@ int launch_tail_head(const TailParams& p, cudaStream_t stream) {
   if (HW % TAIL_THREADS != 0 || p.C > MAX_C || p.C < 1 || ((p.H | p.W) & 1)) return static_cast<int>(cudaErrorInvalidValue);
   const int grid = p.B_pad * pixel_blocks_per_image(p.B_pad, HW, TAIL_PIX * TAIL_U, 148 * 4);
 #define DRASIC_TAIL_LAUNCH(NC)                                                            \
-  if (p.precise) tail_head_kernel<true, NC><<<grid, TAIL_THREADS, 0, stream>>>(p);        \
-  else tail_head_kernel<false, NC><<<grid, TAIL_THREADS, 0, stream>>>(p)
+  if (p.precise) launch_pdl(tail_head_kernel<true, NC>, dim3(grid), dim3(TAIL_THREADS), 0, stream, p);        \
+  else launch_pdl(tail_head_kernel<false, NC>, dim3(grid), dim3(TAIL_THREADS), 0, stream, p)
   switch (p.C) {
     case 1: DRASIC_TAIL_LAUNCH(1); break;
     case 2: DRASIC_TAIL_LAUNCH(2); break;

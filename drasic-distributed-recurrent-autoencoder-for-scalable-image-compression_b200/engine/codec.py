@@ -948,16 +948,19 @@ class CodecEngine(object):
             w.dg_hi, w.dg_lo, w.x_hi, w.x_lo = P(dg_hi), P(dg_lo), P(xp[0]), P(xp[1])
             if t > 0:
                 w.h_hi, w.h_lo = P(Lb['h'][t - 1][0]), P(Lb['h'][t - 1][1])
-            w.gw, w.dg_inv_scale = P(gw[ly.name]), P(inv_dg)
-            w.group_kb_end = P(group_kb_end(ly)) if ly.groups > 1 else None
+            # (a per-node layer whose samples all sit on one node accumulates straight into that node's gradient plane)
+            w.gw, w.dg_inv_scale = P(gw[ly.name]) + ly.g0 * 4 * ly.co * 9 * (ly.cin + ly.co) * 4, P(inv_dg)
+            w.group_kb_end = P(group_kb_end(ly)) if ly.gemm_groups > 1 else None
             w.B_pad, w.H, w.W, w.Cin, w.Co = Bp, ly.h, ly.w, ly.cin, ly.co
-            w.n_groups, w.has_h, w.split = ly.groups, 1 if t > 0 else 0, self.gsplit
-            kb_per_group = max(1, Bp * ly.h * ly.w // 64 // ly.groups)
+            w.n_groups, w.has_h, w.split = ly.gemm_groups, 1 if t > 0 else 0, self.gsplit
+            # (groups that hold samples: the tiles of a node without samples find an empty K range and return at once)
+            n_act = 1 if ly.gemm_groups == 1 else (len(ly.active) if ly.active else ly.groups)
+            kb_per_group = max(1, Bp * ly.h * ly.w // 64 // n_act)
             # 4Co/128 M tiles: always even.  512-column pair tiles (one TMEM-wide accumulator, no epilogue overlap)
             # only where a tile's K loop is long enough to amortise the exposed epilogue
             w.cta_pair = 0 if self.cta_pair == 'off' else (self.wgrad_pair_mode if kb_per_group >= 256 else 1)
             upt = 8 if w.cta_pair == 2 else 4
-            tiles = ly.groups * (4 * ly.co // 128) * ((9 * ly.cin // 64 + upt - 1) // upt + ((9 * ly.co // 64 + upt - 1) // upt if t > 0 else 0))
+            tiles = n_act * (4 * ly.co // 128) * ((9 * ly.cin // 64 + upt - 1) // upt + ((9 * ly.co // 64 + upt - 1) // upt if t > 0 else 0))
             units = sms
             if w.cta_pair:
                 tiles, units = tiles // 2, sms // 2

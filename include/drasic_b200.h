@@ -47,6 +47,11 @@ const char* drasic_last_error(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int drasic_device_sms(void);
 
+/* Programmatic dependent launch of the loop's kernels (on by default): each kernel may be scheduled and run its
+ * prologue while the tail of its predecessor in the stream still executes, and waits (griddepcontrol.wait) before it
+ * touches global memory.  Process-wide switch; returns the previous setting.  Results are identical either way. */
+int drasic_set_pdl(int enable);
+
 /* bytes of one packed fp16 plane for a ConvLSTM cell: 4*Co * 9*(Cin+Co) * 2 */
 size_t drasic_packed_weight_bytes(int Cin, int Co);
 /* sizes of the stream-K work buffers of drasic_convlstm_fwd / drasic_convlstm_bwd_data (see stream_k below) */
