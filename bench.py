@@ -254,6 +254,8 @@ class Arm(object):
         torch, config = self.torch, self.config
         self._apply_config()
         train = mode == 'train'
+        if self.rank == 0:
+            print('[bench] {} B={} M={} grad={} graph={}'.format(mode, B, self.nodes, self.grad_precision, graph), file=sys.stderr, flush=True)
         self.model.train(train)
         img_h, label_h = self.batch(B)
         img, label = img_h.to(self.dev), label_h.to(self.dev)

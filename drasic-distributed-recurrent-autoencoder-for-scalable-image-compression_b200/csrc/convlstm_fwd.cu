@@ -394,7 +394,9 @@ template <bool SPLIT, int BLOCK_N, int EPI, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ GateParams p) {
   using C = Cfg<SPLIT, BLOCK_N, PAIR>;
-  ptx::griddep_launch_dependents();
+  // (a stream-K launch keeps to plain stream order on both sides: its workers wait for each other's partial
+  // accumulators, and letting other grids share the SMs with it while they do was observed to hang)
+  if (!p.sk_on) ptx::griddep_launch_dependents();
   const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
@@ -746,11 +748,15 @@ int launch_t(const GateParams& p, int num_sms, cudaStream_t stream) {
     workers = p.sk_workers;
     if (workers < 1 || workers > max_workers_t<SPLIT, BLOCK_N, EPI, PAIR>(num_sms)) return static_cast<int>(cudaErrorInvalidValue);
   }
-  if (!PAIR) return static_cast<int>(launch_pdl(kern, dim3(workers), dim3(NUM_THREADS), C::SMEM_BYTES, stream, p));
+  if (!PAIR) {
+    if (!p.sk_on) return static_cast<int>(launch_pdl(kern, dim3(workers), dim3(NUM_THREADS), C::SMEM_BYTES, stream, p));
+    kern<<<workers, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+  }
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
   pair_launch_config<SPLIT, BLOCK_N, EPI, PAIR>(cfg, attr, 2 * workers, stream);
-  if (pdl_enabled()) {
+  if (pdl_enabled() && !p.sk_on) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
