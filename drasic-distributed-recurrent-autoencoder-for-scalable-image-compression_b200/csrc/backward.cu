@@ -123,24 +123,29 @@ __global__ void __launch_bounds__(256, 3) lstm_bwd_fused_kernel(const LstmBwdFus
 // ------------------------------------------------------------------ dgrad weight packing
 // rows n in [0, Cin+Co): physical input channel of x (n < Cin) or of h; K = tap' * 4Co + gate*Co + p_out
 // with the tap flipped (conv transpose): value = W[gate*Co + co, channel(n), 8 - tap'].
-__global__ void amax2_kernel(const float* __restrict__ a, size_t na, const float* __restrict__ b,
-                             size_t nb, unsigned int* __restrict__ out) {
+__global__ void amax2_kernel(const __grid_constant__ PackBatch b, size_t na, size_t nb, unsigned int* __restrict__ out) {
+  const float* __restrict__ wa = b.w_in[blockIdx.y];
+  const float* __restrict__ wb = b.w_h[blockIdx.y];
   float m = 0.0f;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < na + nb; i += stride)
-    m = fmaxf(m, fabsf(i < na ? a[i] : b[i - na]));
+    m = fmaxf(m, fabsf(i < na ? wa[i] : wb[i - na]));
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) atomicMax(out + b.slot[blockIdx.y], __float_as_uint(m));
 }
 
-__global__ void pack_dgrad_kernel(const float* __restrict__ w_in, const float* __restrict__ w_h, int Cin,
-                                  int Co, int in_order, int out_order,
-                                  const unsigned int* __restrict__ amax_bits, __half* __restrict__ out_hi,
-                                  __half* __restrict__ out_lo, float* __restrict__ inv_scale_out) {
+__global__ void pack_dgrad_kernel(const __grid_constant__ PackBatch b, int Cin, int Co, int in_order, int out_order,
+                                  const unsigned int* __restrict__ amax_all, __half* __restrict__ hi_all,
+                                  __half* __restrict__ lo_all, float* __restrict__ inv_all) {
+  const float* __restrict__ w_in = b.w_in[blockIdx.y];
+  const float* __restrict__ w_h = b.w_h[blockIdx.y];
+  const int slot = b.slot[blockIdx.y];
   const int K = 9 * 4 * Co;
   const int N = Cin + Co;
   const size_t total = static_cast<size_t>(N) * K;
-  const float amax = __uint_as_float(*amax_bits);
+  __half* __restrict__ out_hi = hi_all + static_cast<size_t>(slot) * total;
+  __half* __restrict__ out_lo = lo_all + static_cast<size_t>(slot) * total;
+  const float amax = __uint_as_float(amax_all[slot]);
   int shift = 0;
   if (amax > 0.0f && isfinite(amax)) {
     int e;
@@ -148,7 +153,7 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w_in, const float* _
     shift = 11 - e;
   }
   const float scale = ldexpf(1.0f, shift);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = ldexpf(1.0f, -shift);
+  if (blockIdx.x == 0 && threadIdx.x == 0) inv_all[slot] = ldexpf(1.0f, -shift);
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total; idx += stride) {
     const int n = static_cast<int>(idx / K);
@@ -577,15 +582,16 @@ int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream) {
   launch_pdl(lstm_bwd_fused_kernel, dim3(grid), dim3(256), 0, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
-int launch_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
-                              int out_order, __half* out_hi, __half* out_lo, float* inv_scale_out,
-                              unsigned int* scratch_amax, cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(scratch_amax, 0, sizeof(unsigned int), stream);
+int launch_pack_dgrad_weights(const PackBatch& b, int n, int n_slots, int Cin, int Co, int in_order, int out_order,
+                              __half* out_hi, __half* out_lo, float* inv_scale_out, unsigned int* scratch_amax,
+                              cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(scratch_amax, 0, sizeof(unsigned int) * n_slots, stream);
   if (e != cudaSuccess) return static_cast<int>(e);
   const size_t na = static_cast<size_t>(4 * Co) * Cin * 9, nb = static_cast<size_t>(4 * Co) * Co * 9;
-  amax2_kernel<<<296, 256, 0, stream>>>(w_in, na, w_h, nb, scratch_amax);
-  pack_dgrad_kernel<<<1184, 256, 0, stream>>>(w_in, w_h, Cin, Co, in_order, out_order, scratch_amax, out_hi,
-                                              out_lo, inv_scale_out);
+  const int bx = n >= 4 ? 148 : 296;
+  amax2_kernel<<<dim3(bx, n), 256, 0, stream>>>(b, na, nb, scratch_amax);
+  pack_dgrad_kernel<<<dim3(4 * bx, n), 256, 0, stream>>>(b, Cin, Co, in_order, out_order, scratch_amax, out_hi, out_lo,
+                                                         inv_scale_out);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,

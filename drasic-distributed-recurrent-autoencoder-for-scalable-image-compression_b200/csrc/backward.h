@@ -86,9 +86,9 @@ struct HeadBwdParams {
 };
 
 int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream);
-int launch_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
-                              int out_order, __half* out_hi, __half* out_lo, float* inv_scale_out,
-                              unsigned int* scratch_amax, cudaStream_t stream);
+int launch_pack_dgrad_weights(const PackBatch& b, int n, int n_slots, int Cin, int Co, int in_order, int out_order,
+                              __half* out_hi, __half* out_lo, float* inv_scale_out, unsigned int* scratch_amax,
+                              cudaStream_t stream);
 int launch_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,
                         float* dw_h, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, bool split, bool pair, int num_sms, cudaStream_t stream);

@@ -139,20 +139,40 @@ size_t drasic_packed_weight_bytes(int Cin, int Co) {
   return static_cast<size_t>(4) * Co * 9 * (Cin + Co) * 2;
 }
 
-int drasic_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
-                             int out_order, int block_n, void* out_hi, void* out_lo,
-                             float* inv_scale_out, void* scratch4, void* stream) {
-  if (!w_in || !w_h || !out_hi || !out_lo || !inv_scale_out || !scratch4)
-    return fail(DRASIC_ERR_INVALID, "pack_lstm_weights: null pointer");
+static int fill_pack_batch(drasic::PackBatch& b, const char* who, const float* const* w_in, const float* const* w_h,
+                           const int* slots, int n, int n_slots) {
+  if (!w_in || !w_h || !slots || n < 1 || n > DRASIC_MAX_GROUPS || n_slots < 1)
+    return fail(DRASIC_ERR_INVALID, "%s: n=%d weight groups (1..%d)", who, n, DRASIC_MAX_GROUPS);
+  for (int i = 0; i < n; ++i) {
+    if (!w_in[i] || !w_h[i] || slots[i] < 0 || slots[i] >= n_slots) return fail(DRASIC_ERR_INVALID, "%s: group %d: null weights or slot out of range", who, i);
+    b.w_in[i] = w_in[i]; b.w_h[i] = w_h[i]; b.slot[i] = slots[i];
+  }
+  return 0;
+}
+
+int drasic_pack_lstm_weights_batch(const float* const* w_in, const float* const* w_h, const int* slots, int n, int n_slots,
+                                   int Cin, int Co, int in_order, int out_order, int block_n, void* out_hi, void* out_lo,
+                                   float* inv_scale_out, void* scratch, void* stream) {
+  if (!out_hi || !out_lo || !inv_scale_out || !scratch) return fail(DRASIC_ERR_INVALID, "pack_lstm_weights: null pointer");
   if (Cin % 64 || Co % 64 || (block_n != 256 && block_n != 128 && block_n != 64) || (4 * Co) % block_n)
     return fail(DRASIC_ERR_INVALID, "pack_lstm_weights: Cin=%d Co=%d block_n=%d unsupported", Cin, Co, block_n);
   if ((in_order == DRASIC_ORDER_QUAD && Cin % 4) || (out_order == DRASIC_ORDER_QUAD && (Co / 4) % 16))
     return fail(DRASIC_ERR_INVALID, "pack_lstm_weights: quad order needs Co/4 %% 16 == 0");
-  return cuda_fail(drasic::launch_pack_lstm_weights(
-                       w_in, w_h, Cin, Co, in_order, out_order, block_n, static_cast<__half*>(out_hi),
-                       static_cast<__half*>(out_lo), inv_scale_out, static_cast<unsigned int*>(scratch4),
-                       static_cast<cudaStream_t>(stream)),
+  drasic::PackBatch b;
+  if (int rc = fill_pack_batch(b, "pack_lstm_weights", w_in, w_h, slots, n, n_slots)) return rc;
+  return cuda_fail(drasic::launch_pack_lstm_weights(b, n, n_slots, Cin, Co, in_order, out_order, block_n,
+                                                    static_cast<__half*>(out_hi), static_cast<__half*>(out_lo), inv_scale_out,
+                                                    static_cast<unsigned int*>(scratch), static_cast<cudaStream_t>(stream)),
                    "pack_lstm_weights launch");
+}
+
+int drasic_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
+                             int out_order, int block_n, void* out_hi, void* out_lo,
+                             float* inv_scale_out, void* scratch4, void* stream) {
+  if (!w_in || !w_h) return fail(DRASIC_ERR_INVALID, "pack_lstm_weights: null pointer");
+  const int slot = 0;
+  return drasic_pack_lstm_weights_batch(&w_in, &w_h, &slot, 1, 1, Cin, Co, in_order, out_order, block_n, out_hi, out_lo,
+                                        inv_scale_out, scratch4, stream);
 }
 
 // pixel box of one GEMM tile: bw*bh*bn == npix pixels.  bw is the largest power of two (<= npix) that
@@ -410,17 +430,26 @@ int drasic_lstm_bwd_fused(const drasic_lstm_bwd_fused_args* a, void* stream) {
   return cuda_fail(drasic::launch_lstm_bwd_fused(p, static_cast<cudaStream_t>(stream)), "lstm_bwd_fused launch");
 }
 
+int drasic_pack_dgrad_weights_batch(const float* const* w_in, const float* const* w_h, const int* slots, int n, int n_slots,
+                                    int Cin, int Co, int in_order, int out_order, void* out_hi, void* out_lo,
+                                    float* inv_scale_out, void* scratch, void* stream) {
+  if (!out_hi || !out_lo || !inv_scale_out || !scratch) return fail(DRASIC_ERR_INVALID, "pack_dgrad_weights: null pointer");
+  if (Cin % 64 || Co % 64) return fail(DRASIC_ERR_INVALID, "pack_dgrad_weights: Cin=%d Co=%d", Cin, Co);
+  drasic::PackBatch b;
+  if (int rc = fill_pack_batch(b, "pack_dgrad_weights", w_in, w_h, slots, n, n_slots)) return rc;
+  return cuda_fail(drasic::launch_pack_dgrad_weights(b, n, n_slots, Cin, Co, in_order, out_order, static_cast<__half*>(out_hi),
+                                                     static_cast<__half*>(out_lo), inv_scale_out,
+                                                     static_cast<unsigned int*>(scratch), static_cast<cudaStream_t>(stream)),
+                   "pack_dgrad_weights launch");
+}
+
 int drasic_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
                               int out_order, void* out_hi, void* out_lo, float* inv_scale_out,
                               void* scratch4, void* stream) {
-  if (!w_in || !w_h || !out_hi || !out_lo || !inv_scale_out || !scratch4)
-    return fail(DRASIC_ERR_INVALID, "pack_dgrad_weights: null pointer");
-  if (Cin % 64 || Co % 64) return fail(DRASIC_ERR_INVALID, "pack_dgrad_weights: Cin=%d Co=%d", Cin, Co);
-  return cuda_fail(drasic::launch_pack_dgrad_weights(w_in, w_h, Cin, Co, in_order, out_order,
-                                                     static_cast<__half*>(out_hi), static_cast<__half*>(out_lo),
-                                                     inv_scale_out, static_cast<unsigned int*>(scratch4),
-                                                     static_cast<cudaStream_t>(stream)),
-                   "pack_dgrad_weights launch");
+  if (!w_in || !w_h) return fail(DRASIC_ERR_INVALID, "pack_dgrad_weights: null pointer");
+  const int slot = 0;
+  return drasic_pack_dgrad_weights_batch(&w_in, &w_h, &slot, 1, 1, Cin, Co, in_order, out_order, out_hi, out_lo, inv_scale_out,
+                                         scratch4, stream);
 }
 
 int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {

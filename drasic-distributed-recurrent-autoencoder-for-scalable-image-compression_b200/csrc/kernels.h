@@ -59,6 +59,13 @@ enum DxMode : int {
   DX_INV_UP = 2,    // input came through pixel_shuffle:  ch c at (Y,X) -> producer (Y/2, X/2), ch q*Cin+c
 };
 
+// weight groups (nodes) packed by one launch: blockIdx.y = entry; `slot` = the group's plane in the packed arrays
+struct PackBatch {
+  const float* w_in[MAX_GROUPS];
+  const float* w_h[MAX_GROUPS];
+  int slot[MAX_GROUPS];
+};
+
 struct GateParams {
   CUtensorMap tm_x[2];  // layer input  NHWC fp16 {hi, lo}
   CUtensorMap tm_h[2];  // previous hidden state NHWC fp16 {hi, lo}

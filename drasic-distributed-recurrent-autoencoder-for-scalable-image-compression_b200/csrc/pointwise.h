@@ -57,8 +57,8 @@ int pixel_blocks_per_image(int B_pad, int HW, int pix_per_pass, int min_blocks);
 int launch_conv1x1(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout,
                    int HW, int act, cudaStream_t stream);
 int launch_quantize(const float* x, const float* u, float* y, size_t n, cudaStream_t stream);
-int launch_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
-                             int out_order, int block_n, __half* out_hi, __half* out_lo,
-                             float* inv_scale_out, unsigned int* scratch_amax, cudaStream_t stream);
+int launch_pack_lstm_weights(const PackBatch& b, int n, int n_slots, int Cin, int Co, int in_order, int out_order, int block_n,
+                             __half* out_hi, __half* out_lo, float* inv_scale_out, unsigned int* scratch_amax,
+                             cudaStream_t stream);
 
 }  // namespace drasic

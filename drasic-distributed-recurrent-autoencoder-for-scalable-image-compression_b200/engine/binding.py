@@ -87,7 +87,7 @@ DX_SAME, DX_INV_DOWN, DX_INV_UP = 0, 1, 2
 # every symbol include/drasic_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes',
            'drasic_stream_k_scratch_bytes', 'drasic_stream_k_flag_bytes', 'drasic_set_pdl',
-           'drasic_pack_lstm_weights', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
+           'drasic_pack_lstm_weights', 'drasic_pack_lstm_weights_batch', 'drasic_pack_dgrad_weights_batch', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
            'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_fused',
            'drasic_pack_dgrad_weights', 'drasic_convlstm_bwd_data', 'drasic_convlstm_bwd_weight',
            'drasic_unpack_wgrad', 'drasic_bottleneck_bwd', 'drasic_tail_bwd', 'drasic_head_bwd', 'drasic_adam_step')
@@ -120,6 +120,10 @@ def lib():
     L.drasic_stream_k_flag_bytes.argtypes = []
     L.drasic_pack_lstm_weights.restype = C.c_int
     L.drasic_pack_lstm_weights.argtypes = [vp, vp, ip, ip, ip, ip, ip, vp, vp, vp, vp, vp]
+    L.drasic_pack_lstm_weights_batch.restype = C.c_int
+    L.drasic_pack_lstm_weights_batch.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, vp, vp, vp, vp, vp]
+    L.drasic_pack_dgrad_weights_batch.restype = C.c_int
+    L.drasic_pack_dgrad_weights_batch.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, vp, vp, vp, vp, vp]
     L.drasic_convlstm_fwd.restype = C.c_int
     L.drasic_convlstm_fwd.argtypes = [C.POINTER(ConvLSTMArgs), vp]
     L.drasic_bottleneck_fwd.restype = C.c_int
@@ -164,3 +168,12 @@ def check(rc, what):
 def ptr(t):
     """device pointer of a torch tensor (or None)"""
     return None if t is None else t.data_ptr()
+
+
+def pointer_arrays(groups):
+    """host arrays for the *_batch packers: groups = [(slot, w_in tensor, w_h tensor), ...]"""
+    n = len(groups)
+    a_in = (C.c_void_p * n)(*[g[1].data_ptr() for g in groups])
+    a_h = (C.c_void_p * n)(*[g[2].data_ptr() for g in groups])
+    slots = (C.c_int * n)(*[int(g[0]) for g in groups])
+    return a_in, a_h, slots, n

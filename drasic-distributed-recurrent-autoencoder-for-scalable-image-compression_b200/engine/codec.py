@@ -431,21 +431,23 @@ class CodecEngine(object):
             lo = torch.empty((G * 4 * co, K), dtype=torch.float16, device=dev)
             inv = torch.empty((G,), dtype=torch.float32, device=dev)
             scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
-        plane = 4 * co * K * 2
-        w_in = w_h = None
+        todo, keep_alive = [], []
         for g, (w_in, w_h) in enumerate(weights):
             if tuple(w_in.shape) != (4 * co, cin, 3, 3) or tuple(w_h.shape) != (4 * co, co, 3, 3):
                 raise ValueError('Not valid ConvLSTM weight shape for {}'.format(name))
             if g in fresh or g not in need:
                 continue
-            w_in = w_in.detach().contiguous()
-            w_h = w_h.detach().contiguous()
+            w_in, w_h = w_in.detach().contiguous(), w_h.detach().contiguous()
+            keep_alive.append((w_in, w_h))
+            todo.append((g, w_in, w_h))
+        if todo:                                               # all groups of the layer in two launches
+            a_in, a_h, slots, n = B.pointer_arrays(todo)
             self._timed('pack_weights', 0.0, lambda: B.check(
-                L.drasic_pack_lstm_weights(w_in.data_ptr(), w_h.data_ptr(), cin, co, in_order, out_order,
-                                           block_n, hi.data_ptr() + g * plane, lo.data_ptr() + g * plane,
-                                           inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
+                L.drasic_pack_lstm_weights_batch(a_in, a_h, slots, n, G, cin, co, in_order, out_order, block_n,
+                                                 hi.data_ptr(), lo.data_ptr(), inv.data_ptr(), scratch.data_ptr(), stream),
                 'pack_lstm_weights'))
             self.launches += 2
+        w_in, w_h = keep_alive[-1] if keep_alive else (None, None)
         val = (hi, lo, inv, (w_in, w_h), scratch)
         self._wcache[name] = (key, val, fresh | need)
         return val
@@ -805,15 +807,12 @@ class CodecEngine(object):
             lo = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
             inv = torch.empty((G,), dtype=torch.float32, device=dev)
             scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
-        plane = n_out * K * 2
-        for g, (w_in, w_h) in enumerate(weights):
-            if g not in need:
-                continue
-            w_in, w_h = w_in.detach().contiguous(), w_h.detach().contiguous()
+        todo = [(g, w_in.detach().contiguous(), w_h.detach().contiguous()) for g, (w_in, w_h) in enumerate(weights) if g in need]
+        if todo:
+            a_in, a_h, slots, n = B.pointer_arrays(todo)
             self._timed('pack_dgrad_weights', 0.0, lambda: B.check(
-                L.drasic_pack_dgrad_weights(w_in.data_ptr(), w_h.data_ptr(), ly.cin, ly.co, ly.in_order,
-                                            ly.out_order, hi.data_ptr() + g * plane, lo.data_ptr() + g * plane,
-                                            inv.data_ptr() + 4 * g, scratch.data_ptr() + 4 * g, stream),
+                L.drasic_pack_dgrad_weights_batch(a_in, a_h, slots, n, G, ly.cin, ly.co, ly.in_order, ly.out_order,
+                                                  hi.data_ptr(), lo.data_ptr(), inv.data_ptr(), scratch.data_ptr(), stream),
                 'pack_dgrad_weights'))
             self.launches += 2
         self._wcache['dgrad_' + ly.name] = (key, (hi, lo, inv, scratch), need)

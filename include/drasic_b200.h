@@ -67,6 +67,13 @@ size_t drasic_stream_k_flag_bytes(void);
 int drasic_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
                              int out_order, int block_n, void* out_hi, void* out_lo,
                              float* inv_scale_out, void* scratch4, void* stream);
+/* The same for n weight groups (nodes) of one layer in two launches: w_in / w_h / slots are HOST arrays of n entries
+ * (device pointers of each group's weights; the group's plane index in the packed arrays).  out_hi / out_lo /
+ * inv_scale_out / scratch are the BASES of the [n_slots] packed arrays (drasic_packed_weight_bytes per plane, one
+ * float, 4 bytes per slot); only the planes named by slots[] are rewritten. */
+int drasic_pack_lstm_weights_batch(const float* const* w_in, const float* const* w_h, const int* slots, int n, int n_slots,
+                                   int Cin, int Co, int in_order, int out_order, int block_n, void* out_hi, void* out_lo,
+                                   float* inv_scale_out, void* scratch, void* stream);
 
 /*
  * One ConvLSTMCell step for the whole (node-grouped) batch, replacing ConvLSTMCell.forward
@@ -187,6 +194,9 @@ int drasic_lstm_bwd_fused(const drasic_lstm_bwd_fused_args* a, void* stream);
 int drasic_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
                               int out_order, void* out_hi, void* out_lo, float* inv_scale_out,
                               void* scratch4, void* stream);
+int drasic_pack_dgrad_weights_batch(const float* const* w_in, const float* const* w_h, const int* slots, int n, int n_slots,
+                                    int Cin, int Co, int in_order, int out_order, void* out_hi, void* out_lo,
+                                    float* inv_scale_out, void* scratch, void* stream);
 
 /* backward-data of one ConvLSTMCell step: [dX | dH_prev] = conv3x3^T(dGates) on tcgen05, the input
  * gradient routed through the inverse pixel (un)shuffle (dx_mode) into the producer's layout. */
