@@ -40,7 +40,7 @@ METRIC = 'images/s train & encode+decode at T=16 (CIFAR-10 32x32), 1/2/4/8 B200;
 # one CPU sample per mode, used by BOTH `cpu_baseline` (our arm) and `--impl reference`
 CPU_SAMPLE = {'train': 64, 'eval': 256}
 PARITY_SAMPLE = 256
-PDL_OFF = False
+PDL_ON = False
 STREAM_K = 'auto'          # --stream-k: schedule of the gate / dgrad GEMMs (auto: stream-K for launches of few work items per SM)
 
 
@@ -359,7 +359,7 @@ class Arm(object):
                          'tests/test_gpu_train.py)') if train else ''),
             'config': workload_config(r['mode'], B, world, self.channels, self.nodes),
             'impl_config': {'precision': self.precision, 'grad_precision': self.grad_precision if train else None,
-                            'cuda_graph': r['graph'], 'stream_k': STREAM_K, 'pdl': not PDL_OFF,
+                            'cuda_graph': r['graph'], 'stream_k': STREAM_K, 'pdl': PDL_ON,
                             'parallelism': (('dp{}: sharded by source (rank r owns nodes r mod N), one NCCL all-reduce of the joint '
                                              "decoder's gradients per step" if self.by_source else
                                              'dp{}: batch sharded, one NCCL all-reduce of gradients per step').format(world) if train
@@ -529,9 +529,9 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     import config
     config.init()
-    if args.no_pdl:
+    if args.pdl:
         from engine import binding
-        binding.lib().drasic_set_pdl(0)
+        binding.lib().drasic_set_pdl(1)
     arm = Arm(dev, rank, world, precision=args.precision, grad_precision=args.grad_precision, shard=args.shard)
     B, K, W = args.batch, args.steps, args.warmup
     main_mode = 'train' if args.mode in ('all', 'train') else 'eval'
@@ -617,7 +617,7 @@ def main():
                          "'auto' = source when there are at least as many nodes as ranks")
     ap.add_argument('--multi-parity', action='store_true', help='N>1: run the in-line gradient parity check in train / eval mode too')
     ap.add_argument('--stream-k', default='auto', choices=['auto', 'on', 'off'])
-    ap.add_argument('--no-pdl', action='store_true', help='plain stream order instead of programmatic dependent launches')
+    ap.add_argument('--pdl', action='store_true', help='experimental: programmatic dependent launches (hangs intermittently in training)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-fast', action='store_true', help='skip the secondary fast-precision measurement')
     args = ap.parse_args()
@@ -626,8 +626,8 @@ def main():
         # and only the joint decoder's gradients are exchanged
         world = int(os.environ.get('WORLD_SIZE', '1'))
         args.shard = 'source' if (world > 1 and M_NODES >= world) else 'batch'
-    global STREAM_K, PDL_OFF
-    STREAM_K, PDL_OFF = args.stream_k, args.no_pdl
+    global STREAM_K, PDL_ON
+    STREAM_K, PDL_ON = args.stream_k, args.pdl
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -47,9 +47,11 @@ const char* drasic_last_error(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int drasic_device_sms(void);
 
-/* Programmatic dependent launch of the loop's kernels (on by default): each kernel may be scheduled and run its
- * prologue while the tail of its predecessor in the stream still executes, and waits (griddepcontrol.wait) before it
- * touches global memory.  Process-wide switch; returns the previous setting.  Results are identical either way. */
+/* Programmatic dependent launch of the loop's kernels (EXPERIMENTAL, off by default): each kernel may be scheduled
+ * and run its prologue while the tail of its predecessor in the stream still executes, and waits
+ * (griddepcontrol.wait) before it touches global memory.  Results are identical either way and inference gains 1-2 %,
+ * but the training step -- main-stream kernels next to the weight-gradient GEMMs of a side stream -- was observed to
+ * hang intermittently with it on.  Process-wide switch; returns the previous setting. */
 int drasic_set_pdl(int enable);
 
 /* bytes of one packed fp16 plane for a ConvLSTM cell: 4*Co * 9*(Cin+Co) * 2 */
