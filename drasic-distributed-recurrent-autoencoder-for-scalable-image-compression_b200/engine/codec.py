@@ -934,7 +934,9 @@ class CodecEngine(object):
             a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
             a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
             a.pos_order, a.pos_imgs = P(ly.pos_order), ly.pos_imgs
-            if self._use_stream_k(ly, (ly.cin + (ly.co if t > 0 else 0) + 255) // 256):
+            # (not next to the weight-gradient GEMMs of the side stream: stream-K workers wait for one another, and
+            # would do so holding SMs the other stream's kernels are queued for)
+            if not overlap and self._use_stream_k(ly, (ly.cin + (ly.co if t > 0 else 0) + 255) // 256):
                 a.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
                 a.sk_scratch, a.sk_flags = P(sk_s), P(sk_f)
             a.B_pad, a.H, a.W, a.Cin, a.Co = Bp, ly.h, ly.w, ly.cin, ly.co
