@@ -306,6 +306,7 @@ def test_stream_k_schedule_vs_oracle(M, B, T, cta_pair):
     noise = torch.rand(T, Bt, 8, 4, 4, generator=g)
     rt = O.codec_forward(sdg, img[:Bt], label[:Bt], T, M, training=True, noise=[n for n in noise])
     rt['loss'].backward()
+    m._engine.overlap_wgrad = False      # (the backward uses stream-K only when wgrad shares its stream)
     tr = train_step(m, img[:Bt], label[:Bt], noise)
     assert int((tr['code_pm1'].cpu() != torch.stack(rt['code_pm1'])).sum()) == 0
     assert abs(tr['loss'].item() - rt['loss'].item()) < 1e-5
