@@ -143,8 +143,10 @@ __global__ void pack_dgrad_kernel(const __grid_constant__ PackBatch b, int Cin, 
   const int K = 9 * 4 * Co;
   const int N = Cin + Co;
   const size_t total = static_cast<size_t>(N) * K;
-  __half* __restrict__ out_hi = hi_all + static_cast<size_t>(slot) * total;
-  __half* __restrict__ out_lo = lo_all + static_cast<size_t>(slot) * total;
+  // tile-contiguous layout [N tile of 256 rows][K block of 64][256 rows][64]; a group's plane holds whole tiles
+  const size_t plane = static_cast<size_t>((N + 255) / 256 * 256) * K;
+  __half* __restrict__ out_hi = hi_all + static_cast<size_t>(slot) * plane;
+  __half* __restrict__ out_lo = lo_all + static_cast<size_t>(slot) * plane;
   const float amax = __uint_as_float(amax_all[slot]);
   int shift = 0;
   if (amax > 0.0f && isfinite(amax)) {
@@ -168,8 +170,9 @@ __global__ void pack_dgrad_kernel(const __grid_constant__ PackBatch b, int Cin, 
     else v = w_h[(static_cast<size_t>(orow) * Co + logical_of_b(n - Cin, Co, out_order)) * 9 + tap];
     v *= scale;
     const __half hi = __float2half_rn(v);
-    out_hi[idx] = hi;
-    out_lo[idx] = __float2half_rn(v - __half2float(hi));
+    const size_t off = ((static_cast<size_t>(n >> 8) * (K / 64) + k / 64) * 256 + (n & 255)) * 64 + (k & 63);
+    out_hi[off] = hi;
+    out_lo[off] = __float2half_rn(v - __half2float(hi));
   }
 }
 

@@ -88,19 +88,20 @@ int make_act_map_chunked(CUtensorMap* m, const void* base, int N, int H, int W, 
   return 0;
 }
 
-// packed weights [rows, K] fp16 K-major; box = (64, block_n)
-int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, int block_n) {
+// packed weights, tile-contiguous ([N tile][K block][tile rows][64] fp16): `rows` rows of 64 elements, 128 bytes apart;
+// box = (64, box_rows) = one contiguous run of box_rows * 128 bytes
+int make_weight_map(CUtensorMap* m, const void* base, long long rows, int box_rows) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(DRASIC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
-  const cuuint32_t box[2] = {drasic::BLOCK_K, static_cast<cuuint32_t>(block_n)};
+  const cuuint64_t dims[2] = {drasic::BLOCK_K, static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {drasic::BLOCK_K * 2};
+  const cuuint32_t box[2] = {drasic::BLOCK_K, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(DRASIC_ERR_TENSORMAP, "weight tensor map rejected (CUresult %d) rows=%d K=%d", static_cast<int>(r), rows, K);
+    return fail(DRASIC_ERR_TENSORMAP, "weight tensor map rejected (CUresult %d) rows=%lld box_rows=%d", static_cast<int>(r), rows, box_rows);
   return 0;
 }
 
@@ -137,6 +138,9 @@ size_t drasic_stream_k_flag_bytes(void) { return drasic::SK_MAX_WORKERS * sizeof
 
 size_t drasic_packed_weight_bytes(int Cin, int Co) {
   return static_cast<size_t>(4) * Co * 9 * (Cin + Co) * 2;
+}
+size_t drasic_packed_dgrad_weight_bytes(int Cin, int Co) {
+  return static_cast<size_t>((Cin + Co + 255) / 256 * 256) * 36 * Co * 2;
 }
 
 static int fill_pack_batch(drasic::PackBatch& b, const char* who, const float* const* w_in, const float* const* w_h,
@@ -313,13 +317,15 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   if (a->n_units <= 0 || (a->n_groups > 1 && (!a->group_mtile_start || !a->group_unit_end || !a->group_img_end)))
     return fail(DRASIC_ERR_INVALID, "convlstm_fwd: n_units and (n_groups > 1) group_mtile_start / group_unit_end / group_img_end");
   const int w_box_rows = pair ? a->block_n / 2 : a->block_n;   // each CTA of a pair stages half of the N tile
-  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * 4 * Co, K, w_box_rows))) return rc;
-  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * 4 * Co, K, w_box_rows))) return rc;
+  const long long w_rows = static_cast<long long>(a->n_groups) * 4 * Co * (K / 64);
+  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, w_rows, w_box_rows))) return rc;
+  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, w_rows, w_box_rows))) return rc;
   p.c_state = a->c_state;
   p.c_prev = a->c_prev;
   p.gates_out = a->gates_out;
   p.gates_f32 = a->gates_f32;
-  p.w_group_rows = 4 * Co;
+  p.w_group_tiles = 4 * Co / a->block_n;
+  p.w_nkb = K / 64;
   p.h_out[0] = static_cast<__half*>(a->h_out_hi);
   p.h_out[1] = static_cast<__half*>(a->h_out_lo);
   p.next[0] = a->next_hi;
@@ -474,8 +480,10 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   const bool pair = a->cta_pair != 0;
   if (a->n_units <= 0 || (a->n_groups > 1 && (!a->group_mtile_start || !a->group_unit_end || !a->group_img_end)))
     return fail(DRASIC_ERR_INVALID, "convlstm_bwd_data: n_units and (n_groups > 1) group_mtile_start / group_unit_end / group_img_end");
-  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, a->n_groups * Nout, K, pair ? 128 : 256))) return rc;
-  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, a->n_groups * Nout, K, pair ? 128 : 256))) return rc;
+  const int w_tiles = (Nout + 255) / 256;        // a group's plane holds whole 256-row tiles (drasic_pack_dgrad_weights)
+  const long long w_rows = static_cast<long long>(a->n_groups) * w_tiles * 256 * (K / 64);
+  if ((rc = make_weight_map(&p.tm_w[0], a->w_hi, w_rows, pair ? 128 : 256))) return rc;
+  if (a->split && (rc = make_weight_map(&p.tm_w[1], a->w_lo, w_rows, pair ? 128 : 256))) return rc;
   p.w_inv_scale = a->w_inv_scale; p.a_inv_scale = a->dg_inv_scale;
   p.H = H; p.W = W; p.Cin = Cg; p.Co = Co;
   p.bw = bw; p.bh = bh; p.bn = bn;
@@ -489,7 +497,7 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   p.n_groups = a->n_groups; p.group_mtile_end = a->group_mtile_end;
   p.group_mtile_start = a->group_mtile_start; p.group_unit_end = a->group_unit_end; p.group_img_end = a->group_img_end;
   p.n_munits = a->n_units;
-  p.w_group_rows = Nout; p.n_out = Nuse; p.n_x = Cin; p.dx_mode = a->dx_mode;
+  p.w_group_tiles = w_tiles; p.w_nkb = K / 64; p.n_out = Nuse; p.n_x = Cin; p.dx_mode = a->dx_mode;
   p.dx_out = a->dx_out; p.dhrec_out = a->dhrec_out;
   if ((rc = setup_pos_tiles(p, "convlstm_bwd_data", a->pos_order, a->pos_imgs, a->n_groups, pair, B, H, W, a->n_units))) return rc;
   if (p.pos_units) {

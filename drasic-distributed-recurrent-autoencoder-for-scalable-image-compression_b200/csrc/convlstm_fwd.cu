@@ -479,11 +479,13 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
       while (walk.next(p, sg)) {
         const int nt = sg.nt;
         const MUnit un = m_unit<PAIR>(p, sg.mu, static_cast<int>(cta_rank), tiles_x, tiles_per_img);
-        int wrow = un.g * p.w_group_rows + nt * BLOCK_N;
+        // weight tiles are stored [group][N tile][K block][BLOCK_N rows][64]: row of K block 0 of this item's N tile
+        const int wtile = (un.g * p.w_group_tiles + nt) * p.w_nkb;
+        int whalf = 0;
         if (PAIR) {  // this CTA stages its half of the (possibly narrower, dgrad) N tile
           int width = BLOCK_N;
           if (EPI == EPI_DGRAD) width = min(BLOCK_N, p.n_out - nt * BLOCK_N);
-          wrow += static_cast<int>(cta_rank) * (width >> 1);
+          whalf = static_cast<int>(cta_rank) * (width >> 1);
         }
         // K blocks walk (source x | h, tap, 64-channel chunk); taps that lie in the zero padding for every row of a
         // position-major tile are skipped (the MMA issuer counts the same blocks); kb numbers the blocks of the item,
@@ -492,14 +494,14 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
         for (int src = 0; src < (p.has_hidden ? 2 : 1); ++src) {
           const CUtensorMap* ta = un.pos ? (src ? p.tm_hp : p.tm_xp) : (src ? p.tm_h : p.tm_x);
           const int chunks = src ? ch_chunks : cx_chunks;
-          const int kbase = src ? 9 * cx_chunks * BLOCK_K : 0;
+          const int kbase = src ? 9 * cx_chunks : 0;   // K block of the weight matrix where this source starts
           for (int tap = 0; tap < 9; ++tap) {
             if (!((un.taps >> tap) & 1u)) continue;
             const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            int kcol = kbase + tap * chunks * BLOCK_K;
             if (kb + chunks <= sg.kb_lo || kb >= sg.kb_hi) { kb += chunks; continue; }
-            for (int cc = 0; cc < chunks; ++cc, kcol += BLOCK_K, ++kb) {
+            for (int cc = 0; cc < chunks; ++cc, ++kb) {
               if (kb < sg.kb_lo || kb >= sg.kb_hi) continue;
+              const int wrow = (wtile + kbase + tap * chunks + cc) * BLOCK_N + whalf;
               ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* st = smem + stage * C::STAGE_BYTES;
               uint8_t* sb = st + (SPLIT ? 2 : 1) * A_TILE_BYTES;
@@ -510,17 +512,17 @@ conv_gemm_kernel(const __grid_constant__ GateParams p) {
                 ptx::tma_load_4d_pair(st, &ta[0], fb, cc * BLOCK_K, un.x0 + dx, un.y0 + dy, un.n0);
                 if (SPLIT)
                   ptx::tma_load_4d_pair(st + A_TILE_BYTES, &ta[1], fb, cc * BLOCK_K, un.x0 + dx, un.y0 + dy, un.n0);
-                ptx::tma_load_2d_pair(sb, &p.tm_w[0], fb, kcol, wrow);
-                if (SPLIT) ptx::tma_load_2d_pair(sb + C::B_TILE_BYTES, &p.tm_w[1], fb, kcol, wrow);
+                ptx::tma_load_2d_pair(sb, &p.tm_w[0], fb, 0, wrow);
+                if (SPLIT) ptx::tma_load_2d_pair(sb + C::B_TILE_BYTES, &p.tm_w[1], fb, 0, wrow);
               } else {
                 ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
                 ptx::tma_load_4d(st, &ta[0], &full_bar[stage], cc * BLOCK_K, un.x0 + dx, un.y0 + dy, un.n0);
                 if (SPLIT)
                   ptx::tma_load_4d(st + A_TILE_BYTES, &ta[1], &full_bar[stage], cc * BLOCK_K, un.x0 + dx,
                                    un.y0 + dy, un.n0);
-                ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], kcol, wrow);
+                ptx::tma_load_2d(sb, &p.tm_w[0], &full_bar[stage], 0, wrow);
                 if (SPLIT)
-                  ptx::tma_load_2d(sb + C::B_TILE_BYTES, &p.tm_w[1], &full_bar[stage], kcol, wrow);
+                  ptx::tma_load_2d(sb + C::B_TILE_BYTES, &p.tm_w[1], &full_bar[stage], 0, wrow);
               }
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }

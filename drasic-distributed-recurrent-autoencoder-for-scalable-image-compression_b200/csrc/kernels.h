@@ -69,7 +69,7 @@ struct PackBatch {
 struct GateParams {
   CUtensorMap tm_x[2];  // layer input  NHWC fp16 {hi, lo}
   CUtensorMap tm_h[2];  // previous hidden state NHWC fp16 {hi, lo}
-  CUtensorMap tm_w[2];  // packed gate weights [groups*4Co, 9Cin+9Co] fp16 {hi, lo}
+  CUtensorMap tm_w[2];  // packed weights, tile-contiguous: [groups][N tile][K block][tile rows][64] fp16 {hi, lo}, seen as rows of 64
   float* c_state;       // [B,H,W,Co] fp32 new cell state (in place when c_prev == nullptr)
   const float* c_prev;  // nullable: previous cell state in a separate buffer (training keeps every c_t)
   void* gates_out;      // nullable: post-activation gates [B,H,W,4,Co] (fp16, or fp32 when gates_f32), saved for backward
@@ -117,7 +117,8 @@ struct GateParams {
   float* sk_scratch;           // [workers][CTAs per worker][BLOCK_N/16][128 rows][16] fp32
   unsigned int* sk_flags;      // [workers][CTAs per worker]: 1 while a published partial waits for its consumer
   // ---- dgrad epilogue (EPI_DGRAD): D[pixels, Nout] = conv3x3^T(dG) ; Cin here = 4*Co of the layer
-  int w_group_rows;            // weight-matrix rows per group (4Co for gates, Nout rounded for dgrad)
+  int w_group_tiles;           // N tiles per weight group (4Co / BLOCK_N for gates, ceil(Nout / 256) for dgrad)
+  int w_nkb;                   // K blocks of the packed weight matrix (9 (Cin + Co) / 64 for gates, 36 Co / 64 for dgrad)
   int n_out;                   // dgrad: output columns = layer Cin + layer Co
   int n_x;                     // dgrad: columns [0,n_x) are dX, [n_x,n_out) are dH_{t-1}
   int dx_mode;                 // DxMode

@@ -1,6 +1,7 @@
 // Weight packing for the gate kernel: fp32 OIHW conv weights of one ConvLSTMCell
 // (modules/cell.py:82-100: cell[0]['in'] [4Co,Cin,3,3] and cell[0]['hidden'] [4Co,Co,3,3], no bias)
-// -> K-major fp16 {hi, lo} matrix [4Co rows, 9*Cin + 9*Co] in the tile order the kernel expects:
+// -> K-major fp16 {hi, lo} matrix [4Co rows, 9*Cin + 9*Co], stored tile by tile ([N tile][K block of 64][block_n rows][64]),
+//    in the tile order the kernel expects:
 //   row  r = nt*BLOCK_N + gate*SLOTS + s     (SLOTS = BLOCK_N/4, physical channel p = nt*SLOTS + s)
 //   col  k = [x part: tap*Cin + pin] [h part: 9*Cin + tap*Co + ph]
 // Physical->logical channel maps follow ChanOrder (kernels.h). Values are multiplied by a per-tensor
@@ -78,8 +79,11 @@ __global__ void pack_kernel(const __grid_constant__ PackBatch b, int Cin, int Co
     }
     v *= scale;
     const __half hi = __float2half_rn(v);
-    out_hi[idx] = hi;
-    out_lo[idx] = __float2half_rn(v - __half2float(hi));
+    // tile-contiguous layout [N tile][K block][block_n rows][64]: the (N tile, K block) operand tile one TMA box brings
+    // is one contiguous run of block_n * 128 bytes (streams from HBM at full rate when the weights do not fit the L2)
+    const size_t off = ((static_cast<size_t>(nt) * (K / BLOCK_K) + k / BLOCK_K) * block_n + rr) * BLOCK_K + (k % BLOCK_K);
+    out_hi[off] = hi;
+    out_lo[off] = __float2half_rn(v - __half2float(hi));
   }
 }
 

@@ -85,7 +85,7 @@ class AdamTensor(C.Structure):
 DX_SAME, DX_INV_DOWN, DX_INV_UP = 0, 1, 2
 
 # every symbol include/drasic_b200.h declares (tests check the library exports all of them)
-SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes',
+SYMBOLS = ('drasic_version', 'drasic_last_error', 'drasic_device_sms', 'drasic_packed_weight_bytes', 'drasic_packed_dgrad_weight_bytes',
            'drasic_stream_k_scratch_bytes', 'drasic_stream_k_flag_bytes', 'drasic_set_pdl',
            'drasic_pack_lstm_weights', 'drasic_pack_lstm_weights_batch', 'drasic_pack_dgrad_weights_batch', 'drasic_convlstm_fwd', 'drasic_bottleneck_fwd', 'drasic_tail_head_fwd',
            'drasic_conv1x1_fwd', 'drasic_quantize_fwd', 'drasic_lstm_bwd_fused',
@@ -112,6 +112,8 @@ def lib():
     L.drasic_device_sms.restype = C.c_int
     L.drasic_packed_weight_bytes.restype = C.c_size_t
     L.drasic_packed_weight_bytes.argtypes = [C.c_int, C.c_int]
+    L.drasic_packed_dgrad_weight_bytes.restype = C.c_size_t
+    L.drasic_packed_dgrad_weight_bytes.argtypes = [C.c_int, C.c_int]
     L.drasic_set_pdl.restype = C.c_int
     L.drasic_set_pdl.argtypes = [C.c_int]
     L.drasic_stream_k_scratch_bytes.restype = C.c_size_t

@@ -799,12 +799,13 @@ class CodecEngine(object):
             return hit[1][:3]
         L = B.lib()
         dev = weights[0][0].device
-        G, n_out, K = len(weights), ly.cin + ly.co, 36 * ly.co
+        G, K = len(weights), 36 * ly.co
+        n_pad = (ly.cin + ly.co + 255) // 256 * 256            # a group's plane holds whole 256-row N tiles
         if hit is not None:
             hi, lo, inv, scratch = hit[1]
         else:
-            hi = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
-            lo = torch.empty((G * n_out, K), dtype=torch.float16, device=dev)
+            hi = torch.zeros((G * n_pad, K), dtype=torch.float16, device=dev)
+            lo = torch.zeros((G * n_pad, K), dtype=torch.float16, device=dev)
             inv = torch.empty((G,), dtype=torch.float32, device=dev)
             scratch = torch.zeros((G,), dtype=torch.int32, device=dev)
         todo = [(g, w_in.detach().contiguous(), w_h.detach().contiguous()) for g, (w_in, w_h) in enumerate(weights) if g in need]
@@ -924,7 +925,7 @@ class CodecEngine(object):
                 planes_ready.record(main)
             hi, lo, inv = dpk[ly.name]
             a = B.DgradArgs()
-            dplane = ly.g0 * (ly.cin + ly.co) * 36 * ly.co * 2
+            dplane = ly.g0 * ((ly.cin + ly.co + 255) // 256 * 256) * 36 * ly.co * 2
             a.dg_hi, a.dg_lo, a.w_hi, a.w_lo = P(dg_hi), P(dg_lo), P(hi) + dplane, P(lo) + dplane
             a.w_inv_scale, a.dg_inv_scale = P(inv) + 4 * ly.g0, P(inv_dg)
             a.dx_out = P(dx_of[ly.name][0])

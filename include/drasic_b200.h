@@ -63,7 +63,9 @@ size_t drasic_stream_k_flag_bytes(void);
 /*
  * Pack the gate weights of one ConvLSTMCell (modules/cell.py:82-100: cell[0]['in'].weight
  * [4Co,Cin,3,3], cell[0]['hidden'].weight [4Co,Co,3,3], fp32 OIHW, no bias) into the K-major,
- * gate-interleaved fp16 {hi,lo} planes the gate kernel reads, scaled by a power of two.
+ * gate-interleaved fp16 {hi,lo} planes the gate kernel reads, scaled by a power of two.  The planes are stored
+ * tile by tile -- [N tile of block_n rows][K block of 64][block_n][64] -- so that the operand tile of one TMA box is
+ * one contiguous run (weights that do not fit the L2 stream from HBM at full rate).
  * out_hi/out_lo: drasic_packed_weight_bytes each; inv_scale_out: 1 float; scratch: 4 bytes.
  */
 int drasic_pack_lstm_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
@@ -192,7 +194,10 @@ typedef struct {
 int drasic_lstm_bwd_fused(const drasic_lstm_bwd_fused_args* a, void* stream);
 
 /* conv-transpose weights of one cell for the dgrad GEMM: rows = Cin+Co input channels (physical
- * order), K = 9 taps (flipped) x 4Co gate channels.  Planes of (Cin+Co)*36*Co fp16 each. */
+ * order), K = 9 taps (flipped) x 4Co gate channels, stored tile by tile ([256-row N tile][K block of 64][256][64]);
+ * planes of drasic_packed_dgrad_weight_bytes(Cin, Co) = roundup(Cin+Co, 256)*36*Co fp16 each (zero the planes once:
+ * the rows that pad the last tile are never written). */
+size_t drasic_packed_dgrad_weight_bytes(int Cin, int Co);
 int drasic_pack_dgrad_weights(const float* w_in, const float* w_h, int Cin, int Co, int in_order,
                               int out_order, void* out_hi, void* out_lo, float* inv_scale_out,
                               void* scratch4, void* stream);
