@@ -12,6 +12,7 @@ with its own value / e2e / roofline:
     eval          encode+decode of the same workload (the other half of BASELINE.json's metric)
     b128          training step and encode+decode at 128 images per GPU (SURVEY 8d config 2's batch)
     config1       BASELINE configs[0]: MNIST-shaped single source, eval, batch 64
+    config5       BASELINE configs[4]: 768x512 images tiled into 32x32 patches, eval, 4096 patches per batch and GPU
     grad_parity   the training step with fp32-grade (split-fp16) backward GEMMs
     parity        codes / reconstructions / PSNR of this build against the CPU oracle on 256 images
     multi_gpu_parity   (N > 1) all-reduced gradients of a sharded batch against the same batch on one GPU
@@ -190,13 +191,14 @@ class Arm(object):
     """one model + optimizer on this rank's GPU, measured through the public API"""
 
     def __init__(self, dev, rank, world, channels=CHANNELS, nodes=M_NODES, precision='parity', grad_precision='fp16',
-                 shard='batch'):
+                 shard='batch', workload=None):
         import torch
         import config
         import utils
         self.torch, self.config = torch, config
         self.dev, self.rank, self.world = dev, rank, world
         self.channels, self.nodes, self.precision, self.grad_precision = channels, nodes, precision, grad_precision
+        self.workload = workload
         self.by_source = shard == 'source' and world > 1 and nodes >= world
         self._apply_config()
         import models
@@ -357,7 +359,8 @@ class Arm(object):
                          'per tensor, tests/test_gpu_train.py)' if self.grad_precision == 'fp16' else
                          ', f16x2-split backward GEMMs, fp32 saved gates, fp32 gradients (tolerance 5e-4 relative per tensor, '
                          'tests/test_gpu_train.py)') if train else ''),
-            'config': workload_config(r['mode'], B, world, self.channels, self.nodes),
+            'config': dict(workload_config(r['mode'], B, world, self.channels, self.nodes),
+                           **({'workload': self.workload} if self.workload else {})),
             'impl_config': {'precision': self.precision, 'grad_precision': self.grad_precision if train else None,
                             'cuda_graph': r['graph'], 'stream_k': STREAM_K, 'pdl': PDL_ON,
                             'parallelism': (('dp{}: sharded by source (rank r owns nodes r mod N), one NCCL all-reduce of the joint '
@@ -579,6 +582,13 @@ def run_ours(args):
             extras['config1']['parity'] = parity_check(c1, 64)
         c1.release()
         del c1
+        # BASELINE configs[4]: 768x512 images tiled into 32x32 patches, 4096 patches per batch (10.67 images), one source
+        c5 = Arm(dev, rank, world, channels=3, nodes=1, precision=args.precision,
+                 workload='kodak_768x512_tiled_into_32x32_patches_single_source_T16_eval_encode_decode')
+        extras['config5'] = c5.record(c5.measure('eval', 4096, max(2, min(K, 5)), W))
+        extras['config5']['kodak_images_per_s'] = extras['config5']['value'] / 384.0
+        c5.release()
+        del c5
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

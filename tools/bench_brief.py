@@ -15,7 +15,7 @@ for path in sys.argv[1:]:
     d = json.loads(open(path).read().strip().splitlines()[-1])
     print(path, d['config']['workload'], 'n_gpus', d['n_gpus'])
     brief(d, 'main')
-    for k in ('eval', 'grad_parity', 'config1'):
+    for k in ('eval', 'grad_parity', 'config1', 'config5'):
         if k in d:
             brief(d[k], k)
     for k, v in d.get('b128', {}).items():
