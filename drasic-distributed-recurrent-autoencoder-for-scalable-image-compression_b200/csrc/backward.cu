@@ -496,36 +496,10 @@ __global__ void __launch_bounds__(TB_THREADS, 3) head_bwd_kernel(const HeadBwdPa
   }
   for (int pass = 0; pass < n_pass; ++pass, i += 8) {
     float4 da, db;
-    // the saved head output of this lane's eight channels ({4 sub ..} and {16 + 4 sub ..} of pixel i): issued before the
-    // wait on the streamed gradient
-    uint2 eh0 = make_uint2(0u, 0u), eh1 = eh0, el0 = eh0, el1 = eh0;
-    if (p.e_hi) {
-      const size_t eo = (static_cast<size_t>(slot) * HW + i) * FEATB + 4 * sub;
-      eh0 = *reinterpret_cast<const uint2*>(p.e_hi + eo);
-      eh1 = *reinterpret_cast<const uint2*>(p.e_hi + eo + 16);
-      if (p.e_lo) {
-        el0 = *reinterpret_cast<const uint2*>(p.e_lo + eo);
-        el1 = *reinterpret_cast<const uint2*>(p.e_lo + eo + 16);
-      }
-    }
     ws.wait(pass);
     ws.read(pass, 0, lane, da, db);
     ws.release(pass, lane);
     const float du[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-    float es[8];
-    if (p.e_hi) {
-      const __half2* h0 = reinterpret_cast<const __half2*>(&eh0);
-      const __half2* h1 = reinterpret_cast<const __half2*>(&eh1);
-      const __half2* l0 = reinterpret_cast<const __half2*>(&el0);
-      const __half2* l1 = reinterpret_cast<const __half2*>(&el1);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float2 a = __half22float2(h0[q]), b = __half22float2(h1[q]);
-        const float2 c = __half22float2(l0[q]), d = __half22float2(l1[q]);
-        es[2 * q] = (a.x + c.x) * ACT_INV_SCALE; es[2 * q + 1] = (a.y + c.y) * ACT_INV_SCALE;
-        es[4 + 2 * q] = (b.x + d.x) * ACT_INV_SCALE; es[4 + 2 * q + 1] = (b.y + d.y) * ACT_INV_SCALE;
-      }
-    }
     const float im_c = im, rp_c = rp, ga_c = ga;
     const size_t gi = img_base + rpix;
     if (pass + 1 < n_pass) {  // next pass's small loads (uniform branch)
@@ -549,15 +523,10 @@ __global__ void __launch_bounds__(TB_THREADS, 3) head_bwd_kernel(const HeadBwdPa
       float w[NC];
 #pragma unroll
       for (int c = 0; c < NC; ++c) w[c] = s_w0[sub][j][c];
-      float e;
-      if (p.e_hi) {            // (uniform) the forward's own value
-        e = es[j];
-      } else {
-        float a = s_b0[sub][j];
+      float a = s_b0[sub][j];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) a = fmaf(w[c], x[c], a);
-        e = tanhf(a);
-      }
+      for (int c = 0; c < NC; ++c) a = fmaf(w[c], x[c], a);
+      const float e = tanhf(a);
       const float dpre = du[j] * (1.0f - e * e);
       bacc[j] += dpre;
 #pragma unroll

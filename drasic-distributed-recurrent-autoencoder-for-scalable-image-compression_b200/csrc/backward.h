@@ -83,10 +83,6 @@ struct HeadBwdParams {
   const int* perm;
   const int* group_img_end;
   int B_pad, C, H, W, first, propagate, n_enc_groups;
-  // nullable: the head's output e0 = tanh(W0 x + b) of this iteration as the forward stored it (the first encoder
-  // ConvLSTM's input planes, fp16(e * 2^8) {hi, lo}, same indexing as du1); without it e0 is recomputed
-  const __half* e_hi;
-  const __half* e_lo;
 };
 
 int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream);

@@ -601,7 +601,6 @@ int drasic_head_bwd(const drasic_head_bwd_args* a, void* stream) {
   p.dw_e0 = a->dw_e0; p.db_e0 = a->db_e0; p.perm = a->perm; p.group_img_end = a->group_img_end;
   p.B_pad = a->B_pad; p.C = a->C; p.H = a->H; p.W = a->W; p.first = a->first; p.propagate = a->propagate;
   p.n_enc_groups = a->n_enc_groups < 1 ? 1 : a->n_enc_groups;
-  p.e_hi = static_cast<const __half*>(a->e_hi); p.e_lo = a->e_hi ? static_cast<const __half*>(a->e_lo) : nullptr;
   return cuda_fail(drasic::launch_head_bwd(p, static_cast<cudaStream_t>(stream)), "head_bwd launch");
 }
 

@@ -75,8 +75,7 @@ class TailBwdArgs(C.Structure):
 class HeadBwdArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('du1', 'w_e0', 'b_e0', 'img', 'recon_prev', 'gacc', 'dw_e0', 'db_e0', 'perm',
                                   'group_img_end')] + \
-               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'propagate', 'n_enc_groups')] + \
-               [('e_hi', vp), ('e_lo', vp)]
+               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'propagate', 'n_enc_groups')]
 
 
 class AdamTensor(C.Structure):

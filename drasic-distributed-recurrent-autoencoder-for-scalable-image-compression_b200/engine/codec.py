@@ -1006,8 +1006,6 @@ class CodecEngine(object):
             h.perm, h.group_img_end = P(plan.perm), P(plan.group_img_end)
             h.B_pad, h.C, h.H, h.W = Bp, Cc, H, W
             h.first, h.propagate, h.n_enc_groups = int(t == 0), int((not self.separate) and t > 0), self.M
-            # the head's output of iteration t is the first encoder ConvLSTM's saved input: read, not recomputed
-            h.e_hi, h.e_lo = P(A['e1_in'][t][0]), P(A['e1_in'][t][1]) if self.gsplit else None
             self._timed('head_bwd', 0.0, lambda: B.check(L.drasic_head_bwd(h, stream), 'head_bwd'))
             self.launches += 3
 

@@ -266,9 +266,6 @@ typedef struct {
   const float* du1; const float* w_e0; const float* b_e0; const float* img; const float* recon_prev;
   float* gacc; float* dw_e0; float* db_e0; const int* perm; const int* group_img_end;
   int B_pad, C, H, W, first, propagate, n_enc_groups;
-  /* nullable: the head's output of this iteration as drasic_tail_head_fwd stored it (e1_in_hi / e1_in_lo, fp16 planes of
-   * tanh(W0 x + b) * 2^8, indexed like du1); the kernel then reads it instead of recomputing 32 tanh per pixel */
-  const void* e_hi; const void* e_lo;
 } drasic_head_bwd_args;
 int drasic_head_bwd(const drasic_head_bwd_args* a, void* stream);
 

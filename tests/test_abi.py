@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(B.WgradArgs) == 9 * 8 + 10 * 4
     assert ctypes.sizeof(B.BottleneckBwdArgs) == 11 * 8 + 6 * 4
     assert ctypes.sizeof(B.TailBwdArgs) == 9 * 8 + 4 + 8 * 4 + 4 + 8 + 2 * 4
-    assert ctypes.sizeof(B.HeadBwdArgs) == 10 * 8 + 7 * 4 + 4 + 2 * 8
+    assert ctypes.sizeof(B.HeadBwdArgs) == 10 * 8 + 7 * 4 + 4
     assert ctypes.sizeof(B.BottleneckArgs) == 12 * 8 + 8 * 4 + 8
     assert ctypes.sizeof(B.AdamTensor) == 4 * 8 + 8
     assert ctypes.sizeof(B.TailHeadArgs) == 13 * 8 + 10 * 4 + 8 + 4 + 4   # trailing pad to 8
