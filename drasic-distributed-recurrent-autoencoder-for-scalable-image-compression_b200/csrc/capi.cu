@@ -194,6 +194,16 @@ static int pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
   return 0;
 }
 
+// positions of an H x W plane by number of in-bounds 3x3 taps: count[t], t = 1..9
+static void tap_class_counts(int H, int W, int* count) {
+  for (int i = 0; i < 10; ++i) count[i] = 0;
+  int cy[4] = {0, 0, 0, 0}, cx[4] = {0, 0, 0, 0};     // rows / columns with 1, 2, 3 in-bounds taps along the axis
+  if (H == 1) cy[1] = 1; else { cy[2] = 2; cy[3] = H - 2; }
+  if (W == 1) cx[1] = 1; else { cx[2] = 2; cx[3] = W - 2; }
+  for (int ty = 1; ty <= 3; ++ty)
+    for (int tx = 1; tx <= 3; ++tx) count[ty * tx] += cy[ty] * cx[tx];
+}
+
 // position-major region of a conv GEMM launch (see drasic_convlstm_args): validates, builds the (64 ch, 1, 1, 128
 // images) tensor maps of the planes in `hi` / `lo` and fills the unit bookkeeping
 static int setup_pos_tiles(drasic::GateParams& p, const char* who, const int* pos_order, int pos_imgs, int n_groups,
@@ -205,6 +215,18 @@ static int setup_pos_tiles(drasic::GateParams& p, const char* who, const int* po
     return fail(DRASIC_ERR_INVALID, "%s: pos_imgs=%d needs one group, a pos_order table and a multiple of %d slots <= B_pad", who, pos_imgs, unit_imgs);
   p.pos_upp = pos_imgs / unit_imgs;
   p.pos_units = H * W * p.pos_upp;
+  {  // classes of positions by in-bounds tap count, in the order of pos_order (9, 6, 4, 3, 2, 1 taps)
+    int count[10];
+    tap_class_counts(H, W, count);
+    int c = 0, pos0 = 0;
+    for (int taps = 9; taps >= 1; --taps) {
+      if (!count[taps]) continue;
+      p.pos_class_unit0[c] = pos0 * p.pos_upp; p.pos_class_pos0[c] = pos0; p.pos_class_n[c] = count[taps];
+      pos0 += count[taps];
+      ++c;
+    }
+    p.pos_classes = c;
+  }
   p.pos_tile_base = static_cast<int>(static_cast<long long>(pos_imgs) * H * W / 128);
   p.pos_order = pos_order;
   const int rest = p.n_mtiles - p.pos_tile_base;
@@ -222,13 +244,7 @@ static int setup_stream_k(drasic::GateParams& p, const char* who, int stream_k, 
   if (!scratch || !flags) return fail(DRASIC_ERR_INVALID, "%s: stream_k needs sk_scratch and sk_flags", who);
   if (max_workers < 1) return fail(DRASIC_ERR_NO_DEVICE, "%s: stream_k: no co-resident workers on this device", who);
   int count[10] = {0};
-  if (p.pos_units) {
-    int cy[4] = {0, 0, 0, 0}, cx[4] = {0, 0, 0, 0};     // rows / columns with 1, 2, 3 in-bounds taps along the axis
-    if (p.H == 1) cy[1] = 1; else { cy[2] = 2; cy[3] = p.H - 2; }
-    if (p.W == 1) cx[1] = 1; else { cx[2] = 2; cx[3] = p.W - 2; }
-    for (int ty = 1; ty <= 3; ++ty)
-      for (int tx = 1; tx <= 3; ++tx) count[ty * tx] += cy[ty] * cx[tx];
-  }
+  if (p.pos_units) tap_class_counts(p.H, p.W, count);
   // classes of the whole launch: (first item, items, K blocks per item)
   int c_item[8], c_n[8], c_nkb[8], nc = 0, item = 0;
   for (int taps = 9; taps >= 1; --taps) {

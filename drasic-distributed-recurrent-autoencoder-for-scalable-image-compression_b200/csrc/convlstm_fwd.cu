@@ -120,8 +120,11 @@ __device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank, i
   MUnit u;
   if (mu < p.pos_units) {
     // position-major: both CTAs of a pair sit on the same position (same taps), adjacent blocks of 128 images
-    const int pi = mu / p.pos_upp, it = mu - pi * p.pos_upp;
-    const int pos = __ldg(&p.pos_order[pi]);
+    int c = 0;
+    while (c + 1 < p.pos_classes && mu >= p.pos_class_unit0[c + 1]) ++c;
+    const int l = mu - p.pos_class_unit0[c];
+    const int it = l / p.pos_class_n[c];                     // block of images: slow inside the class
+    const int pos = __ldg(&p.pos_order[p.pos_class_pos0[c] + (l - it * p.pos_class_n[c])]);
     u.y0 = pos / p.W;
     u.x0 = pos - u.y0 * p.W;
     u.n0 = (PAIR ? 2 * it + rank : it) * TILE_M;
@@ -210,8 +213,10 @@ struct Walk {
     item += stride;
     tile_split(p, it, p.n_munits, s.nt, s.mu);
     int taps = 9;
-    if (s.mu < p.pos_units) {
-      const int pos = __ldg(&p.pos_order[s.mu / p.pos_upp]);
+    if (s.mu < p.pos_units) {     // every position of a class has the class's tap count: its first one will do
+      int c = 0;
+      while (c + 1 < p.pos_classes && s.mu >= p.pos_class_unit0[c + 1]) ++c;
+      const int pos = __ldg(&p.pos_order[p.pos_class_pos0[c]]);
       taps = __popc(pos_taps(p, pos / p.W, pos % p.W));
     }
     s.nkb = taps * cpt;

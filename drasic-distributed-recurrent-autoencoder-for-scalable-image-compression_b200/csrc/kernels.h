@@ -102,6 +102,11 @@ struct GateParams {
   int pos_units, pos_upp;      // units in the position-major region; units (image tiles / pairs of them) per position
   int pos_tile_base;
   const int* pos_order;        // [H*W] pixel positions (y*W + x), most in-bounds taps first
+  // positions with the same number of in-bounds taps form a class; inside a class the units walk the positions for one
+  // block of images, then for the next (neighbouring positions of the same images share most of their halo in the L2).
+  // Class c: units [pos_class_unit0[c], pos_class_unit0[c+1]), positions pos_order[pos_class_pos0[c] ...] (pos_class_n[c])
+  int pos_classes;
+  int pos_class_unit0[8], pos_class_pos0[8], pos_class_n[8];
   // ---- stream-K schedule (sk_on) of the LAST, partial wave: the first sk_static items are dealt whole, round
   // robin, like without it (the workers then run in lockstep over the same weight K blocks, which is what the L2
   // likes); the K blocks of the remaining items, laid end to end in item order, are cut into one equal range per
