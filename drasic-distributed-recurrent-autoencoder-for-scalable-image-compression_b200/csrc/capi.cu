@@ -206,27 +206,41 @@ static void tap_class_counts(int H, int W, int* count) {
 
 // position-major region of a conv GEMM launch (see drasic_convlstm_args): validates, builds the (64 ch, 1, 1, 128
 // images) tensor maps of the planes in `hi` / `lo` and fills the unit bookkeeping
-static int setup_pos_tiles(drasic::GateParams& p, const char* who, const int* pos_order, int pos_imgs, int n_groups,
-                           bool pair, int B, int H, int W, int n_units) {
-  p.pos_units = 0; p.pos_upp = 1; p.pos_tile_base = 0; p.pos_order = nullptr;
+static int setup_pos_tiles(drasic::GateParams& p, const char* who, const int* pos_order, int pos_imgs, int pos_pairs,
+                           int n_groups, bool pair, int B, int H, int W, int n_units) {
+  p.pos_units = 0; p.pos_upp = 1; p.pos_tile_base = 0; p.pos_order = nullptr; p.pos_classes = 0; p.pos_pair_mode = 0;
   if (pos_imgs == 0) return 0;
-  const int unit_imgs = pair ? 256 : 128;
+  if (pos_pairs && (!pair || H < 4 || W < 4 || ((H | W) & 1)))
+    return fail(DRASIC_ERR_INVALID, "%s: pos_pairs needs cta_pair and an even plane of at least 4x4 (H=%d W=%d)", who, H, W);
+  const int unit_imgs = (pair && !pos_pairs) ? 256 : 128;
   if (pos_imgs < 0 || pos_imgs > B || pos_imgs % unit_imgs || n_groups != 1 || !pos_order)
     return fail(DRASIC_ERR_INVALID, "%s: pos_imgs=%d needs one group, a pos_order table and a multiple of %d slots <= B_pad", who, pos_imgs, unit_imgs);
-  p.pos_upp = pos_imgs / unit_imgs;
-  p.pos_units = H * W * p.pos_upp;
-  {  // classes of positions by in-bounds tap count, in the order of pos_order (9, 6, 4, 3, 2, 1 taps)
-    int count[10];
-    tap_class_counts(H, W, count);
-    int c = 0, pos0 = 0;
-    for (int taps = 9; taps >= 1; --taps) {
-      if (!count[taps]) continue;
-      p.pos_class_unit0[c] = pos0 * p.pos_upp; p.pos_class_pos0[c] = pos0; p.pos_class_n[c] = count[taps];
-      pos0 += count[taps];
+  p.pos_upp = pos_imgs / unit_imgs;            // blocks of images, each walked by every table entry
+  p.pos_pair_mode = pos_pairs ? 1 : 0;
+  int c = 0, e0 = 0;
+  if (pos_pairs) {
+    // pairs of positions with equal tap sets: interior (9 taps), then edges and the two corner pairs (6 taps)
+    const int n9 = (H - 2) * (W - 2) / 2, n6 = (H - 2) + (W - 2) + 2;
+    const int n[2] = {n9, n6}, taps[2] = {9, 6};
+    for (int k = 0; k < 2; ++k) {
+      if (!n[k]) continue;
+      p.pos_class_unit0[c] = e0 * p.pos_upp; p.pos_class_pos0[c] = e0; p.pos_class_n[c] = n[k]; p.pos_class_taps[c] = taps[k];
+      e0 += n[k];
       ++c;
     }
-    p.pos_classes = c;
+  } else {
+    // classes of positions by in-bounds tap count, in the order of pos_order (9, 6, 4, 3, 2, 1 taps)
+    int count[10];
+    tap_class_counts(H, W, count);
+    for (int taps = 9; taps >= 1; --taps) {
+      if (!count[taps]) continue;
+      p.pos_class_unit0[c] = e0 * p.pos_upp; p.pos_class_pos0[c] = e0; p.pos_class_n[c] = count[taps]; p.pos_class_taps[c] = taps;
+      e0 += count[taps];
+      ++c;
+    }
   }
+  p.pos_classes = c;
+  p.pos_units = e0 * p.pos_upp;
   p.pos_tile_base = static_cast<int>(static_cast<long long>(pos_imgs) * H * W / 128);
   p.pos_order = pos_order;
   const int rest = p.n_mtiles - p.pos_tile_base;
@@ -243,13 +257,10 @@ static int setup_stream_k(drasic::GateParams& p, const char* who, int stream_k, 
   if (!stream_k) return 0;
   if (!scratch || !flags) return fail(DRASIC_ERR_INVALID, "%s: stream_k needs sk_scratch and sk_flags", who);
   if (max_workers < 1) return fail(DRASIC_ERR_NO_DEVICE, "%s: stream_k: no co-resident workers on this device", who);
-  int count[10] = {0};
-  if (p.pos_units) tap_class_counts(p.H, p.W, count);
   // classes of the whole launch: (first item, items, K blocks per item)
-  int c_item[8], c_n[8], c_nkb[8], nc = 0, item = 0;
-  for (int taps = 9; taps >= 1; --taps) {
-    if (!count[taps]) continue;
-    c_item[nc] = item; c_n[nc] = count[taps] * p.pos_upp * p.n_ntiles; c_nkb[nc] = taps * chunks_per_tap;
+  int c_item[9], c_n[9], c_nkb[9], nc = 0, item = 0;
+  for (int c = 0; c < p.pos_classes; ++c) {
+    c_item[nc] = item; c_n[nc] = p.pos_class_n[c] * p.pos_upp * p.n_ntiles; c_nkb[nc] = p.pos_class_taps[c] * chunks_per_tap;
     item += c_n[nc++];
   }
   const int rest = (p.n_munits - p.pos_units) * p.n_ntiles;
@@ -363,7 +374,7 @@ int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream) {
   p.group_mtile_end = a->group_mtile_end;
   p.group_mtile_start = a->group_mtile_start; p.group_unit_end = a->group_unit_end; p.group_img_end = a->group_img_end;
   p.n_munits = a->n_units;
-  if ((rc = setup_pos_tiles(p, "convlstm_fwd", a->pos_order, a->pos_imgs, a->n_groups, pair, B, H, W, a->n_units))) return rc;
+  if ((rc = setup_pos_tiles(p, "convlstm_fwd", a->pos_order, a->pos_imgs, a->pos_pairs, a->n_groups, pair, B, H, W, a->n_units))) return rc;
   if (p.pos_units) {
     if ((rc = make_act_map(&p.tm_xp[0], a->x_hi, B, H, W, Cin, 1, 1, 128))) return rc;
     if (a->split && (rc = make_act_map(&p.tm_xp[1], a->x_lo, B, H, W, Cin, 1, 1, 128))) return rc;
@@ -515,7 +526,7 @@ int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream) {
   p.n_munits = a->n_units;
   p.w_group_tiles = w_tiles; p.w_nkb = K / 64; p.n_out = Nuse; p.n_x = Cin; p.dx_mode = a->dx_mode;
   p.dx_out = a->dx_out; p.dhrec_out = a->dhrec_out;
-  if ((rc = setup_pos_tiles(p, "convlstm_bwd_data", a->pos_order, a->pos_imgs, a->n_groups, pair, B, H, W, a->n_units))) return rc;
+  if ((rc = setup_pos_tiles(p, "convlstm_bwd_data", a->pos_order, a->pos_imgs, a->pos_pairs, a->n_groups, pair, B, H, W, a->n_units))) return rc;
   if (p.pos_units) {
     if ((rc = make_act_map(&p.tm_xp[0], a->dg_hi, B, H, W, Cg, 1, 1, 128))) return rc;
     if (a->split && (rc = make_act_map(&p.tm_xp[1], a->dg_lo, B, H, W, Cg, 1, 1, 128))) return rc;

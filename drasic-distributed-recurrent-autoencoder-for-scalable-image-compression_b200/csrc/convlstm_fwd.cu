@@ -124,12 +124,21 @@ __device__ __forceinline__ MUnit m_unit(const GateParams& p, int mu, int rank, i
     while (c + 1 < p.pos_classes && mu >= p.pos_class_unit0[c + 1]) ++c;
     const int l = mu - p.pos_class_unit0[c];
     const int it = l / p.pos_class_n[c];                     // block of images: slow inside the class
-    const int pos = __ldg(&p.pos_order[p.pos_class_pos0[c] + (l - it * p.pos_class_n[c])]);
+    const int e = p.pos_class_pos0[c] + (l - it * p.pos_class_n[c]);
+    int pos;
+    if (p.pos_pair_mode) {   // two positions, one per CTA of the pair, on the same 128 images
+      const int pa = __ldg(&p.pos_order[2 * e]), pb = __ldg(&p.pos_order[2 * e + 1]);
+      pos = rank ? pb : pa;
+      u.taps = pos_taps(p, pa / p.W, pa % p.W) | pos_taps(p, pb / p.W, pb % p.W);
+      u.n0 = it * TILE_M;
+    } else {                 // one position; the CTAs of a pair take adjacent blocks of 128 images
+      pos = __ldg(&p.pos_order[e]);
+      u.taps = pos_taps(p, pos / p.W, pos % p.W);
+      u.n0 = (PAIR ? 2 * it + rank : it) * TILE_M;
+    }
     u.y0 = pos / p.W;
     u.x0 = pos - u.y0 * p.W;
-    u.n0 = (PAIR ? 2 * it + rank : it) * TILE_M;
     u.g = 0; u.img_lo = 0; u.img_hi = 0x7fffffff; u.own = true; u.pos = true;
-    u.taps = pos_taps(p, u.y0, u.x0);
     return u;
   }
   mu -= p.pos_units;
@@ -213,11 +222,10 @@ struct Walk {
     item += stride;
     tile_split(p, it, p.n_munits, s.nt, s.mu);
     int taps = 9;
-    if (s.mu < p.pos_units) {     // every position of a class has the class's tap count: its first one will do
+    if (s.mu < p.pos_units) {
       int c = 0;
       while (c + 1 < p.pos_classes && s.mu >= p.pos_class_unit0[c + 1]) ++c;
-      const int pos = __ldg(&p.pos_order[p.pos_class_pos0[c]]);
-      taps = __popc(pos_taps(p, pos / p.W, pos % p.W));
+      taps = p.pos_class_taps[c];
     }
     s.nkb = taps * cpt;
     s.kb_lo = 0; s.kb_hi = s.nkb; s.g0 = 0;

@@ -106,7 +106,11 @@ struct GateParams {
   // block of images, then for the next (neighbouring positions of the same images share most of their halo in the L2).
   // Class c: units [pos_class_unit0[c], pos_class_unit0[c+1]), positions pos_order[pos_class_pos0[c] ...] (pos_class_n[c])
   int pos_classes;
-  int pos_class_unit0[8], pos_class_pos0[8], pos_class_n[8];
+  int pos_class_unit0[8], pos_class_pos0[8], pos_class_n[8], pos_class_taps[8];
+  // pos_pair_mode (CTA pairs on fewer than 256 slots): a unit is TWO positions of one block of 128 images, one per
+  // CTA of the pair -- pos_order then holds pairs (entries 2e, 2e+1) chosen with equal tap sets where possible; the
+  // unit walks the union of the two sets (TMA zero fill covers a tap that is out of bounds for one of them)
+  int pos_pair_mode;
   // ---- stream-K schedule (sk_on) of the LAST, partial wave: the first sk_static items are dealt whole, round
   // robin, like without it (the workers then run in lockstep over the same weight K blocks, which is what the L2
   // likes); the K blocks of the remaining items, laid end to end in item order, are cut into one equal range per

@@ -22,7 +22,7 @@ class ConvLSTMArgs(C.Structure):
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'has_state', 'next_mode',
                                   'next_f32', 'split', 'precise', 'block_n', 'gates_f32', 'cta_pair')] + \
                [('group_mtile_start', vp), ('group_unit_end', vp), ('group_img_end', vp), ('n_units', ip),
-                ('pos_order', vp), ('pos_imgs', ip), ('stream_k', ip), ('sk_scratch', vp), ('sk_flags', vp)]
+                ('pos_order', vp), ('pos_imgs', ip), ('stream_k', ip), ('sk_scratch', vp), ('sk_flags', vp), ('pos_pairs', ip)]
 
 
 class BottleneckArgs(C.Structure):
@@ -44,7 +44,7 @@ class DgradArgs(C.Structure):
                                   'dhrec_out', 'group_mtile_end')] + \
                [(n, ip) for n in ('B_pad', 'H', 'W', 'Cin', 'Co', 'n_groups', 'dx_mode', 'split', 'cta_pair')] + \
                [('group_mtile_start', vp), ('group_unit_end', vp), ('group_img_end', vp), ('n_units', ip),
-                ('pos_order', vp), ('pos_imgs', ip), ('stream_k', ip), ('sk_scratch', vp), ('sk_flags', vp)]
+                ('pos_order', vp), ('pos_imgs', ip), ('stream_k', ip), ('sk_scratch', vp), ('sk_flags', vp), ('pos_pairs', ip)]
 
 
 class WgradArgs(C.Structure):

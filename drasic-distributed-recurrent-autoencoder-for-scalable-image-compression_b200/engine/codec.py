@@ -172,6 +172,22 @@ class _Layer(object):
     pass
 
 
+def position_pairs(h, w):
+    """the h*w/2 pairs of pixel positions a CTA pair walks on ONE block of 128 images (even planes of at least 4x4):
+    partners share their set of in-bounds 3x3 taps wherever they can -- interior positions (9 taps) pair with their
+    right neighbour, edge positions (6 taps) with the next one along the same edge -- and the four corners pair
+    left-right (4 taps each, 6 in the union).  Order: the 9-tap pairs first (the long K loops), then the 6-tap ones."""
+    pairs = []
+    for y in range(1, h - 1):
+        pairs += [(y * w + x, y * w + x + 1) for x in range(1, w - 1, 2)]
+    for y in (0, h - 1):
+        pairs += [(y * w + x, y * w + x + 1) for x in range(1, w - 1, 2)]
+    for x in (0, w - 1):
+        pairs += [(y * w + x, (y + 1) * w + x) for y in range(1, h - 1, 2)]
+    pairs += [(0, w - 1), ((h - 1) * w, (h - 1) * w + w - 1)]
+    return np.asarray(pairs, dtype=np.int32).reshape(-1)
+
+
 def position_order(h, w):
     """pixel positions y*w + x of an h x w plane, most in-bounds 3x3 taps first (interior 9, edges 6, corners 4):
     the order in which the conv GEMMs walk their position-major tiles, so that the persistent CTAs -- dealt the
@@ -253,10 +269,10 @@ class CodecEngine(object):
         self.stream_k = stream_k
         self._sk = {}
 
-    def _pos_order(self, h, w, dev):
-        key = (h, w, str(dev))
+    def _pos_order(self, h, w, dev, pairs=False):
+        key = (h, w, str(dev), pairs)
         if key not in self._pos_tables:
-            self._pos_tables[key] = torch.from_numpy(position_order(h, w)).to(dev)
+            self._pos_tables[key] = torch.from_numpy(position_pairs(h, w) if pairs else position_order(h, w)).to(dev)
         return self._pos_tables[key]
 
     SK_WAVES = 2
@@ -294,17 +310,22 @@ class CodecEngine(object):
         units (128 images, 256 with CTA pairs) followed by pixel-major tiles over the rest"""
         hw = ly.h * ly.w
         n_mtiles = Bp * hw // 128
-        ly.units, ly.pos_imgs, ly.pos_order = None, 0, None
+        ly.units, ly.pos_imgs, ly.pos_order, ly.pos_pairs = None, 0, None, 0
         if getattr(ly, 'gemm_groups', ly.groups) > 1:
             ly.units, ly.n_units = plan.m_units(hw, ly.pair)
             return
         unit_imgs = 256 if ly.pair else 128
+        pos_units = 0
         if self.pos_major:
             ly.pos_imgs = Bp // unit_imgs * unit_imgs
+            pos_units = hw * (ly.pos_imgs // unit_imgs)
+            if ly.pair and not ly.pos_imgs and Bp >= 128 and min(ly.h, ly.w) >= 4 and not ((ly.h | ly.w) & 1):
+                # a CTA pair on fewer than 256 slots: two positions of the first 128 slots per unit
+                ly.pos_imgs, ly.pos_pairs, pos_units = 128, 1, hw // 2
         rest = n_mtiles - ly.pos_imgs * hw // 128
-        ly.n_units = hw * (ly.pos_imgs // unit_imgs) + ((rest + 1) // 2 if ly.pair else rest)
+        ly.n_units = pos_units + ((rest + 1) // 2 if ly.pair else rest)
         if ly.pos_imgs:
-            ly.pos_order = self._pos_order(ly.h, ly.w, dev)
+            ly.pos_order = self._pos_order(ly.h, ly.w, dev, bool(ly.pos_pairs))
 
     def clone(self):
         """an engine with the same configuration and its own arenas / packed weight planes (a captured CUDA graph
@@ -368,10 +389,9 @@ class CodecEngine(object):
         if self.cta_pair == 'on':
             return True
         if self.stream_k != 'off':
-            # pairs, unless they cost position-major tiles that are worth more: a pair unit needs 256 slots, and below
-            # that only the 4x4 layers skip enough padding taps (30 %) to make up for single-CTA tiles (measured at
-            # B=128: D1 single + position-major 110 us vs 108; D2 363 vs 378; D3 166 vs 160 for pairs)
-            return groups > 1 or B_pad >= 256 or not self.pos_major or B_pad < 128 or hw > 64
+            # pairs everywhere: the 256-column pair tile moves the fewest L2 -> SMEM bytes per MMA, launches of few
+            # items are spread along K instead, and below 256 slots the pair walks two positions of one image block
+            return True
         return (n_mtiles + 1) // 2 * (4 * co // 256) >= self.sms() // 2
 
     def _get_arena(self, B_pad, H, W, device, T=0):
@@ -625,7 +645,7 @@ class CodecEngine(object):
             a.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
             a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
             a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
-            a.pos_order, a.pos_imgs = P(ly.pos_order), ly.pos_imgs
+            a.pos_order, a.pos_imgs, a.pos_pairs = P(ly.pos_order), ly.pos_imgs, ly.pos_pairs
             if self._use_stream_k(ly, 4 * ly.co // ly.block_n):
                 a.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
                 a.sk_scratch, a.sk_flags = P(sk_s), P(sk_f)
@@ -763,7 +783,7 @@ class CodecEngine(object):
                 g.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
                 g.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
                 g.group_img_end, g.n_units = P(plan.group_img_end), ly.n_units
-                g.pos_order, g.pos_imgs = P(ly.pos_order), ly.pos_imgs
+                g.pos_order, g.pos_imgs, g.pos_pairs = P(ly.pos_order), ly.pos_imgs, ly.pos_pairs
                 if self._use_stream_k(ly, 4 * ly.co // ly.block_n):
                     g.stream_k, (sk_s, sk_f) = 1, self._sk_buffers(dev)
                     g.sk_scratch, g.sk_flags = P(sk_s), P(sk_f)
@@ -934,7 +954,7 @@ class CodecEngine(object):
             a.group_mtile_end = ly.units[1].data_ptr() if ly.units is not None else None
             a.group_unit_end = ly.units[2].data_ptr() if ly.units is not None else None
             a.group_img_end, a.n_units = P(plan.group_img_end), ly.n_units
-            a.pos_order, a.pos_imgs = P(ly.pos_order), ly.pos_imgs
+            a.pos_order, a.pos_imgs, a.pos_pairs = P(ly.pos_order), ly.pos_imgs, ly.pos_pairs
             # (not next to the weight-gradient GEMMs of the side stream: stream-K workers wait for one another, and
             # would do so holding SMs the other stream's kernels are queued for)
             if not overlap and self._use_stream_k(ly, (ly.cin + (ly.co if t > 0 else 0) + 255) // 256):

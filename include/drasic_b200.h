@@ -128,6 +128,11 @@ typedef struct {
    * launches with few items per CTA -- small batches, the 4x4 layers -- where whole items would leave SMs idle. */
   int stream_k;
   void* sk_scratch; void* sk_flags;
+  /* pos_pairs != 0 (with cta_pair, fewer than 256 slots to tile, even planes of at least 4x4): a unit is TWO pixel
+   * positions of one block of 128 slots, one per CTA of the pair.  pos_order then holds H*W/2 PAIRS (2 ints each):
+   * first the (H-2)(W-2)/2 pairs of interior positions (all nine taps), then the pairs of edge positions that share
+   * their tap set and the two pairs of corners (six taps in their union); pos_imgs is a multiple of 128. */
+  int pos_pairs;
 } drasic_convlstm_args;
 int drasic_convlstm_fwd(const drasic_convlstm_args* a, void* stream);
 
@@ -221,6 +226,7 @@ typedef struct {
   int n_units;
   const int* pos_order; int pos_imgs;   /* position-major M tiles, as in drasic_convlstm_args */
   int stream_k; void* sk_scratch; void* sk_flags;   /* stream-K schedule, as in drasic_convlstm_args */
+  int pos_pairs;                                    /* as in drasic_convlstm_args */
 } drasic_dgrad_args;
 int drasic_convlstm_bwd_data(const drasic_dgrad_args* a, void* stream);
 

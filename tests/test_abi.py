@@ -33,8 +33,8 @@ def test_version_and_sizes():
 
 def test_struct_layouts_match_header():
     # pointer and int counts of the argument structs in include/drasic_b200.h
-    assert ctypes.sizeof(B.ConvLSTMArgs) == 15 * 8 + 14 * 4 + 3 * 8 + 4 + 4 + 8 + 4 + 4 + 2 * 8   # (n_units, pad) (pos_order) (pos_imgs, stream_k) (sk_*)
-    assert ctypes.sizeof(B.DgradArgs) == 9 * 8 + 9 * 4 + 4 + 3 * 8 + 4 + 4 + 8 + 4 + 4 + 2 * 8
+    assert ctypes.sizeof(B.ConvLSTMArgs) == 15 * 8 + 14 * 4 + 3 * 8 + 4 + 4 + 8 + 4 + 4 + 2 * 8 + 8   # (pos_pairs, pad) (n_units, pad) (pos_order) (pos_imgs, stream_k) (sk_*)
+    assert ctypes.sizeof(B.DgradArgs) == 9 * 8 + 9 * 4 + 4 + 3 * 8 + 4 + 4 + 8 + 4 + 4 + 2 * 8 + 8
     assert ctypes.sizeof(B.WgradArgs) == 9 * 8 + 10 * 4
     assert ctypes.sizeof(B.BottleneckBwdArgs) == 11 * 8 + 6 * 4
     assert ctypes.sizeof(B.TailBwdArgs) == 9 * 8 + 4 + 8 * 4 + 4 + 8 + 2 * 4

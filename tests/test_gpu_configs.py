@@ -238,12 +238,14 @@ def test_captured_graphs_own_their_buffers():
         assert torch.equal(got[0], e_eager[0]) and torch.equal(got[1], e_eager[1])
 
 
-@pytest.mark.parametrize('M,B,cta_pair', [(1, 256, 'on'), (1, 264, 'on'), (1, 136, 'off'), (4, 272, 'on')])
+@pytest.mark.parametrize('M,B,cta_pair', [(1, 256, 'on'), (1, 264, 'on'), (1, 136, 'off'), (4, 272, 'on'), (1, 136, 'on'),
+                                          (4, 200, 'auto')])
 def test_position_major_tiles_are_bit_identical_to_pixel_major(M, B, cta_pair):
     """The position-major M tiles (one pixel position x 128 images; padding taps never issued) skip only MMAs whose A
     operand is TMA zero fill, so every output bit equals the pixel-major walk's: forward (codes, reconstructions)
     and -- up to the atomics' order in wgrad -- the gradients.  M=1: encoder and decoder layers; M=4: the joint
-    decoder only.  B=264 / 136 / 272 leave a pixel-major remainder behind the position-major region."""
+    decoder only.  B=264 / 136 / 272 leave a pixel-major remainder behind the position-major region; with CTA pairs on
+    fewer than 256 slots (B=136 'on', B=200) a pair walks two positions of the first 128 slots."""
     T = 3
     # (static schedule: under stream-K the two walks cut the K sequence at different places, which changes the order
     # of the fp32 partial sums -- test_stream_k_schedule_vs_oracle covers that combination against the oracle)
@@ -274,7 +276,7 @@ def test_position_major_tiles_are_bit_identical_to_pixel_major(M, B, cta_pair):
 
 
 @pytest.mark.parametrize('M,B,T,cta_pair', [(8, 61, 6, 'off'), (8, 61, 6, 'on'), (1, 264, 3, 'on'), (3, 20, 16, 'auto'),
-                                            (1, 136, 3, 'off')])
+                                            (1, 136, 3, 'off'), (1, 136, 3, 'on')])
 def test_stream_k_schedule_vs_oracle(M, B, T, cta_pair):
     """stream_k='on': every gate / dgrad GEMM cuts its K-block sequence into one range per CTA (pair) and exchanges
     partial accumulators.  Same fp32-grade numerics (the partial sums are added in another order): codes equal the

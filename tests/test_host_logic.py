@@ -341,14 +341,31 @@ def test_plan_units_position_major():
     eng = CodecEngine(3, 8, 1)
     for Bp, h, w, pair, want_pos, want_units in [(1024, 4, 4, True, 1024, 16 * 4), (1040, 8, 8, True, 1024, 64 * 4 + 4),
                                                  (128, 4, 4, False, 128, 16), (200, 16, 16, False, 128, 256 + 144),
-                                                 (64, 8, 8, False, 0, 32), (128, 4, 4, True, 0, 8)]:
+                                                 (64, 8, 8, False, 0, 32), (128, 4, 4, True, 128, 8), (200, 8, 8, True, 128, 32 + 18),
+                                                 (64, 8, 8, True, 0, 16)]:
         ly = _Layer()
         ly.h, ly.w, ly.pair, ly.groups = h, w, pair, 1
         eng._plan_units(ly, Bp, None, 'cpu')
         assert (ly.pos_imgs, ly.n_units) == (want_pos, want_units), (Bp, h, w, pair, ly.pos_imgs, ly.n_units)
         assert (ly.pos_order is not None) == (want_pos > 0)
+        assert ly.pos_pairs == int(pair and 128 <= Bp < 256)       # a pair on fewer than 256 slots walks two positions
     eng.pos_major = False
     ly = _Layer()
     ly.h, ly.w, ly.pair, ly.groups = 4, 4, True, 1
     eng._plan_units(ly, 1024, None, 'cpu')
     assert (ly.pos_imgs, ly.n_units) == (0, 64)
+
+
+def test_position_pairs_share_their_tap_sets():
+    """engine.codec.position_pairs: every position once; 9-tap pairs first, then 6-tap unions (edges, corner pairs)"""
+    from engine.codec import position_pairs
+
+    def taps(pos, h, w):
+        y, x = divmod(int(pos), w)
+        return sum(1 << t for t in range(9) if 0 <= y + t // 3 - 1 < h and 0 <= x + t % 3 - 1 < w)
+    for h, w in [(4, 4), (8, 8), (16, 16), (4, 8)]:
+        pairs = position_pairs(h, w).reshape(-1, 2)
+        assert sorted(pairs.reshape(-1).tolist()) == list(range(h * w))
+        union = [bin(taps(a, h, w) | taps(b, h, w)).count('1') for a, b in pairs]
+        n9 = (h - 2) * (w - 2) // 2
+        assert union[:n9] == [9] * n9 and union[n9:] == [6] * ((h - 2) + (w - 2) + 2)
