@@ -14,7 +14,8 @@ with its own value / e2e / roofline:
     config1       BASELINE configs[0]: MNIST-shaped single source, eval, batch 64
     config5       BASELINE configs[4]: 768x512 images tiled into 32x32 patches, eval, 4096 patches per batch and GPU
     grad_parity   the training step with fp32-grade (split-fp16) backward GEMMs
-    parity        codes / reconstructions / PSNR of this build against the CPU oracle on 256 images
+    parity        codes / reconstructions / PSNR of this build against the CPU oracle on 256 images (initial weights;
+                  parity_after_training: the same on the weights the run's training steps leave behind)
     multi_gpu_parity   (N > 1) all-reduced gradients of a sharded batch against the same batch on one GPU
 `--impl reference` times the CPU oracle (the reference's algorithm on torch CPU ops, all host threads)
 on a bounded sample of the same workload: the SAME sample `cpu_baseline` of our arm is timed on.
@@ -540,6 +541,12 @@ def run_ours(args):
     main_mode = 'train' if args.mode in ('all', 'train') else 'eval'
     everything = args.mode == 'all'
 
+    parity_init = None
+    if world == 1 and not args.no_cpu:
+        # on the seeded initial weights (deterministic); once more below on the weights the training steps leave behind
+        parity_init = parity_check(arm, PARITY_SAMPLE)
+        parity_init['weights'] = 'initial (torch.manual_seed(0))'
+        arm.release()
     main = arm.measure(main_mode, B, K, W, graph=args.graph, fast=not args.no_fast, clocks=True)
     line = {'metric': METRIC, 'n_gpus': world, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'data': 'synthetic'}
@@ -573,7 +580,10 @@ def run_ours(args):
                                     'note': 'same global batch as the N=1 line; efficiency = value / (N x the N=1 value)'}
     if world == 1 and not args.no_cpu:
         arm.release()
-        extras['parity'] = parity_check(arm, PARITY_SAMPLE)
+        extras['parity'] = parity_init
+        if main_mode == 'train':
+            extras['parity_after_training'] = parity_check(arm, PARITY_SAMPLE)
+            extras['parity_after_training']['weights'] = 'after the training steps of this run'
     if everything:
         arm.release()
         c1 = Arm(dev, rank, world, channels=1, nodes=1, precision=args.precision)

@@ -21,6 +21,6 @@ for path in sys.argv[1:]:
     for k, v in d.get('b128', {}).items():
         brief(v, 'b128 ' + k)
     print('   kernels', {k: round(v, 2) for k, v in d['kernels_ms_per_step'].items()})
-    for k in ('parity', 'multi_gpu_parity', 'cpu_baseline', 'clocks'):
+    for k in ('parity', 'parity_after_training', 'multi_gpu_parity', 'cpu_baseline', 'clocks'):
         if k in d:
             print('  ', k, {a: b for a, b in d[k].items() if a not in ('note', 'sample', 'tolerance')})
