@@ -103,6 +103,29 @@ class ClockSampler(object):
                 'samples': len(sm)}
 
 
+def captured_traffic(mode, B, nodes, precision):
+    """DRAM bytes per launch of the dominant kernel (forward gate GEMM) from the committed `ncu --set full` capture of
+    the SAME mode and configuration, or None: profiles/r2_ncu_full_gates_eval_B1024_summary.csv holds the six gate
+    launches of one eval iteration at B=1024, M=8, parity precision (tools/ncu_round2.sh gates)"""
+    if not (mode == 'eval' and B == 1024 and nodes == 8 and precision == 'parity'):
+        return None, 'no ncu --set full capture of this mode / configuration under profiles/'
+    path = os.path.join(ROOT, 'profiles', 'r2_ncu_full_gates_eval_B1024_summary.csv')
+    try:
+        import csv
+        rows = list(csv.reader(open(path)))
+        unit = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+        cols = {}
+        for i, h in enumerate(rows[0]):
+            for key in ('dram_rd', 'dram_wr'):
+                if h.startswith(key):
+                    cols[key] = (i, unit[h[h.index('[') + 1:h.index(']')]])
+        per = [sum(float(r[cols[k][0]]) * cols[k][1] for k in ('dram_rd', 'dram_wr')) for r in rows[1:] if 'conv_gemm' in r[0]]
+        return sum(per) / len(per), ('dram__bytes_read.sum + dram__bytes_write.sum, mean over the {} gate launches of one iteration, '
+                                     'profiles/r2_ncu_full_gates_eval_B1024_summary.csv').format(len(per))
+    except Exception as e:          # the capture is evidence, not a dependency
+        return None, 'capture unreadable: {}'.format(e)
+
+
 def workload_name(mode, channels=CHANNELS, nodes=M_NODES):
     data = 'cifar10_32x32' if channels == 3 else 'mnist_32x32'
     src = 'm{}_random_subsets'.format(nodes) if nodes > 1 else 'single_source'
@@ -351,6 +374,7 @@ class Arm(object):
             ms = sum(v[1] for k, v in gate if k.startswith(kk))
             return sum(v[2] for k, v in gate if k.startswith(kk)) / max(1e-9, ms) / 1e9
         fwd = kind_tflops('gates')
+        traffic, traffic_note = captured_traffic(r['mode'], B, self.nodes, self.precision)
         rec = {
             'value': world * B / r['ms'] * 1e3, 'unit': 'images/s', 'ms_per_step': r['ms'], 'steps': r['steps'],
             'warmup': r['warmup'],
@@ -379,9 +403,7 @@ class Arm(object):
                                     if train else 'conv_gemm_kernel<gates> (6 layers x 16 iterations)'),
                          'achieved': achieved, 'peak': sust, 'unit': 'TFLOP/s', 'frac': achieved / sust,
                          'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained ({}); burst {}'.format(how, burst),
-                         'traffic': None,
-                         'traffic_note': 'not measurable inside bench.py; per-kernel dram__bytes of the same kernels are in the ncu '
-                                         'captures under profiles/ (r2_ncu_full_*_summary.csv)',
+                         'traffic': traffic, 'traffic_note': traffic_note,
                          'launches': g_n, 'avg_launch_ms': g_ms / max(g_n, 1), 'share_of_step': g_ms / max(all_ms, 1e-9),
                          'dominant_kernel': {'name': 'conv_gemm_kernel<gates> (forward gate GEMMs)', 'achieved': fwd,
                                              'frac': fwd / sust, 'tensor_mma_per_algorithmic_mac': fwd_mma,
