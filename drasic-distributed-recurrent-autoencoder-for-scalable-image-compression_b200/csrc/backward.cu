@@ -201,6 +201,18 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ gw, int Cin, int C
 
 // ------------------------------------------------------------------ bottleneck backward
 // forward (pointwise.cu bottleneck_kernel): z = tanh(W4 h3); q = Q(z) (straight-through); d0 = tanh(W0 q)
+// Weight-gradient accumulation across blocks.  Default: float atomics (the sum depends on the order in which the
+// blocks arrive -- run-to-run differences at the 1e-6 level).  Deterministic mode (fix_scale > 0): the destination is
+// an int64 buffer and every partial sum is added as round(v * fix_scale); integer addition is associative, so the
+// result does not depend on the order (the host converts back, engine/codec.py).
+__device__ __forceinline__ unsigned long long to_fix(float v, double scale) {
+  return static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v) * scale));
+}
+__device__ __forceinline__ void accum_grad(float* dst, size_t i, float v, double fix_scale) {
+  if (fix_scale > 0.0) atomicAdd(reinterpret_cast<unsigned long long*>(dst) + i, to_fix(v, fix_scale));
+  else atomicAdd(dst + i, v);
+}
+
 __global__ void __launch_bounds__(128) bottleneck_bwd_kernel(const BottleneckBwdParams p) {
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(128) bottleneck_bwd_kernel(const BottleneckBwd
     const int m = o / code, k = o - m * code;
     float acc = 0.0f;
     for (int pix = 0; pix < HW; ++pix) acc = fmaf(s_a[pix * CH + m], s_q[pix * code + k], acc);
-    atomicAdd(p.dw_d0 + static_cast<size_t>(gd) * CH * code + o, acc);
+    accum_grad(p.dw_d0, static_cast<size_t>(gd) * CH * code + o, acc, p.fix_scale);
   }
   // dq = W0^T dpre0 ; straight-through quantizer ; dprez = dq * (1 - z^2)
   for (int o = threadIdx.x; o < n_code; o += blockDim.x) {
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(128) bottleneck_bwd_kernel(const BottleneckBwd
     const int k = o / CH, c = o - k * CH;
     float acc = 0.0f;
     for (int pix = 0; pix < HW; ++pix) acc = fmaf(s_dz[pix * code + k], s_h[pix * CH + c], acc);
-    atomicAdd(p.dw_e4 + static_cast<size_t>(ge) * code * CH + o, acc);
+    accum_grad(p.dw_e4, static_cast<size_t>(ge) * code * CH + o, acc, p.fix_scale);
   }
   // dh3[pix,c] = sum_k W4[k,c] * dprez[pix,k]
   for (int o = threadIdx.x; o < HW * CH; o += blockDim.x) {
@@ -304,7 +316,9 @@ __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdPa
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();
   __shared__ float s_acc[MAXC * FEATB];
+  __shared__ unsigned long long s_fix[MAXC * FEATB];   // deterministic mode: the block's partial sums in fixed point
   __shared__ alignas(16) float s_w4[MAXC][4][8];   // [c][sub][j]
+  const bool fix = p.fix_scale > 0.0;
   const int HW = p.H * p.W;
   const int bpi = gridDim.x / p.B_pad;
   const int slot = blockIdx.x / bpi;
@@ -331,6 +345,7 @@ __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdPa
     const int c = t >> 5, sb = (t >> 3) & 3, j = t & 7;
     s_w4[c][sb][j] = c < C ? p.w_d4[(static_cast<size_t>(gd) * C + c) * FEATB + slice_channel(sb, j)] : 0.0f;
     s_acc[t] = 0.0f;
+    s_fix[t] = 0ull;
   }
   __syncthreads();
   float wacc[NC][8];
@@ -429,11 +444,17 @@ __global__ void __launch_bounds__(TB_THREADS, 3) tail_bwd_kernel(const TailBwdPa
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (lane < 4) atomicAdd(&s_acc[c * FEATB + slice_channel(sub, j)], v);
+      if (lane < 4) {
+        if (fix) atomicAdd(&s_fix[c * FEATB + slice_channel(sub, j)], to_fix(v, p.fix_scale));
+        else atomicAdd(&s_acc[c * FEATB + slice_channel(sub, j)], v);
+      }
     }
   __syncthreads();
-  if (threadIdx.x < C * FEATB)
-    atomicAdd(p.dw_d4 + static_cast<size_t>(gd) * C * FEATB + threadIdx.x, s_acc[threadIdx.x]);
+  if (threadIdx.x < C * FEATB) {
+    const size_t o = static_cast<size_t>(gd) * C * FEATB + threadIdx.x;
+    if (fix) atomicAdd(reinterpret_cast<unsigned long long*>(p.dw_d4) + o, s_fix[threadIdx.x]);
+    else atomicAdd(p.dw_d4 + o, s_acc[threadIdx.x]);
+  }
 }
 
 // iteration t: e0 = tanh(W0 x + b) recomputed; backward to W0, b and (dist codec, t > 0) to recon_{t-1}
@@ -442,7 +463,9 @@ __global__ void __launch_bounds__(TB_THREADS, 3) head_bwd_kernel(const HeadBwdPa
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();
   __shared__ float s_acc[FEATB * MAXC + FEATB];
+  __shared__ unsigned long long s_fix[FEATB * MAXC + FEATB];   // deterministic mode
   __shared__ alignas(16) float s_w0[4][8][MAXC];   // [sub][j][c]
+  const bool fix = p.fix_scale > 0.0;
   __shared__ alignas(16) float s_b0[4][8];
   const int HW = p.H * p.W;
   const int bpi = gridDim.x / p.B_pad;
@@ -458,7 +481,7 @@ __global__ void __launch_bounds__(TB_THREADS, 3) head_bwd_kernel(const HeadBwdPa
   const int lane_base = lane & ~3;
   const bool mine = sub < C;
   const QuadMapB qm(p.W);
-  for (int t = threadIdx.x; t < FEATB * MAXC + FEATB; t += TB_THREADS) s_acc[t] = 0.0f;
+  for (int t = threadIdx.x; t < FEATB * MAXC + FEATB; t += TB_THREADS) { s_acc[t] = 0.0f; s_fix[t] = 0ull; }
   for (int t = threadIdx.x; t < MAXC * FEATB; t += TB_THREADS) {
     const int c = t >> 5, sb = (t >> 3) & 3, j = t & 7;
     const int k = slice_channel(sb, j);
@@ -559,15 +582,24 @@ __global__ void __launch_bounds__(TB_THREADS, 3) head_bwd_kernel(const HeadBwdPa
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (lane < 4) atomicAdd(&s_acc[c == NC ? FEATB * MAXC + k : k * MAXC + c], v);
+      if (lane < 4) {
+        const int si = c == NC ? FEATB * MAXC + k : k * MAXC + c;
+        if (fix) atomicAdd(&s_fix[si], to_fix(v, p.fix_scale)); else atomicAdd(&s_acc[si], v);
+      }
     }
   }
   __syncthreads();
   for (int t = threadIdx.x; t < FEATB * C; t += blockDim.x) {
     const int k = t / C, c = t - k * C;
-    atomicAdd(p.dw_e0 + static_cast<size_t>(ge) * FEATB * C + t, s_acc[k * MAXC + c]);
+    const size_t o = static_cast<size_t>(ge) * FEATB * C + t;
+    if (fix) atomicAdd(reinterpret_cast<unsigned long long*>(p.dw_e0) + o, s_fix[k * MAXC + c]);
+    else atomicAdd(p.dw_e0 + o, s_acc[k * MAXC + c]);
   }
-  if (p.db_e0 && threadIdx.x < FEATB) atomicAdd(p.db_e0 + static_cast<size_t>(ge) * FEATB + threadIdx.x, s_acc[FEATB * MAXC + threadIdx.x]);
+  if (p.db_e0 && threadIdx.x < FEATB) {
+    const size_t o = static_cast<size_t>(ge) * FEATB + threadIdx.x;
+    if (fix) atomicAdd(reinterpret_cast<unsigned long long*>(p.db_e0) + o, s_fix[FEATB * MAXC + threadIdx.x]);
+    else atomicAdd(p.db_e0 + o, s_acc[FEATB * MAXC + threadIdx.x]);
+  }
 }
 
 inline int grid_for(size_t work_items, int threads) {

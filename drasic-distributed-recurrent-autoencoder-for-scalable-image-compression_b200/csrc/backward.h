@@ -53,6 +53,7 @@ struct BottleneckBwdParams {
   float* dw_e4;            // [n_enc_groups][code, Ch] accumulated
   float* dw_d0;            // [n_dec_groups][Ch, code] accumulated
   int B_pad, HW, Ch, code, n_enc_groups, n_dec_groups;
+  double fix_scale;        // > 0: deterministic accumulation, dw_e4 / dw_d0 are int64 fixed-point buffers (value * fix_scale)
 };
 
 struct TailBwdParams {
@@ -69,6 +70,7 @@ struct TailBwdParams {
   int B_pad, C, H, W, first, loss_kind, n_dec_groups, has_acc;
   const int* group_iters;  // nullable: per-node iteration budget (heterogeneous rates)
   int iter, n_enc_groups;
+  double fix_scale;        // > 0: deterministic accumulation, dw_d4 is an int64 fixed-point buffer
 };
 
 struct HeadBwdParams {
@@ -83,6 +85,7 @@ struct HeadBwdParams {
   const int* perm;
   const int* group_img_end;
   int B_pad, C, H, W, first, propagate, n_enc_groups;
+  double fix_scale;        // > 0: deterministic accumulation, dw_e0 / db_e0 are int64 fixed-point buffers
 };
 
 int launch_lstm_bwd_fused(const LstmBwdFusedParams& p, cudaStream_t stream);

@@ -599,6 +599,7 @@ int drasic_bottleneck_bwd(const drasic_bottleneck_bwd_args* a, void* stream) {
   p.perm = a->perm; p.group_img_end = a->group_img_end; p.dh_e3 = a->dh_e3; p.dw_e4 = a->dw_e4; p.dw_d0 = a->dw_d0;
   p.B_pad = a->B_pad; p.HW = a->HW; p.Ch = a->Ch; p.code = a->code;
   p.n_enc_groups = a->n_enc_groups < 1 ? 1 : a->n_enc_groups; p.n_dec_groups = a->n_dec_groups < 1 ? 1 : a->n_dec_groups;
+  p.fix_scale = a->fix_scale;
   return cuda_fail(drasic::launch_bottleneck_bwd(p, static_cast<cudaStream_t>(stream)), "bottleneck_bwd launch");
 }
 
@@ -615,6 +616,7 @@ int drasic_tail_bwd(const drasic_tail_bwd_args* a, void* stream) {
   p.loss_kind = a->loss_kind; p.n_dec_groups = a->n_dec_groups < 1 ? 1 : a->n_dec_groups; p.has_acc = a->has_acc;
   p.group_iters = a->group_iters; p.iter = a->iter; p.n_enc_groups = a->n_enc_groups < 1 ? 1 : a->n_enc_groups;
   if (a->group_iters && p.n_enc_groups > 1 && !a->group_img_end) return fail(DRASIC_ERR_INVALID, "tail_bwd: group_iters needs group_img_end");
+  p.fix_scale = a->fix_scale;
   return cuda_fail(drasic::launch_tail_bwd(p, static_cast<cudaStream_t>(stream)), "tail_bwd launch");
 }
 
@@ -628,6 +630,7 @@ int drasic_head_bwd(const drasic_head_bwd_args* a, void* stream) {
   p.dw_e0 = a->dw_e0; p.db_e0 = a->db_e0; p.perm = a->perm; p.group_img_end = a->group_img_end;
   p.B_pad = a->B_pad; p.C = a->C; p.H = a->H; p.W = a->W; p.first = a->first; p.propagate = a->propagate;
   p.n_enc_groups = a->n_enc_groups < 1 ? 1 : a->n_enc_groups;
+  p.fix_scale = a->fix_scale;
   return cuda_fail(drasic::launch_head_bwd(p, static_cast<cudaStream_t>(stream)), "head_bwd launch");
 }
 

@@ -62,20 +62,20 @@ class LstmBwdFusedArgs(C.Structure):
 class BottleneckBwdArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('dd0', 'h_e3', 'z', 'codes', 'w_e4', 'w_d0', 'perm', 'group_img_end', 'dh_e3',
                                   'dw_e4', 'dw_d0')] + \
-               [(n, ip) for n in ('B_pad', 'HW', 'Ch', 'code', 'n_enc_groups', 'n_dec_groups')]
+               [(n, ip) for n in ('B_pad', 'HW', 'Ch', 'code', 'n_enc_groups', 'n_dec_groups')] + [('fix_scale', C.c_double)]
 
 
 class TailBwdArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('d3_next', 'w_d4', 'img', 'recon_t', 'gacc', 'dh_d3', 'dw_d4', 'perm',
                                   'group_img_end')] + [('loss_scale', C.c_float)] + \
                [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'loss_kind', 'n_dec_groups', 'has_acc')] + \
-               [('group_iters', vp), ('iter', ip), ('n_enc_groups', ip)]
+               [('group_iters', vp), ('iter', ip), ('n_enc_groups', ip), ('fix_scale', C.c_double)]
 
 
 class HeadBwdArgs(C.Structure):
     _fields_ = [(n, vp) for n in ('du1', 'w_e0', 'b_e0', 'img', 'recon_prev', 'gacc', 'dw_e0', 'db_e0', 'perm',
                                   'group_img_end')] + \
-               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'propagate', 'n_enc_groups')]
+               [(n, ip) for n in ('B_pad', 'C', 'H', 'W', 'first', 'propagate', 'n_enc_groups')] + [('fix_scale', C.c_double)]
 
 
 class AdamTensor(C.Structure):

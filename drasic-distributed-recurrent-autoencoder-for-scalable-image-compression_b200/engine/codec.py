@@ -216,7 +216,7 @@ class CodecEngine(object):
     functions (fp32-grade, bit-exact codes); 'fast' = single fp16 operands with tanh.approx."""
 
     def __init__(self, num_channel, code_size, num_node, separate=False, precision='parity', grad_precision='fp16',
-                 cta_pair='auto', stream_k='auto'):
+                 cta_pair='auto', stream_k='auto', deterministic=False):
         """grad_precision: 'fp16' = backward GEMMs on single fp16 operands, gates saved in fp16 (gradients
         within ~1e-3 relative of the fp32 reference); 'parity' = split-fp16 backward GEMMs and fp32 saved
         gates (fp32-grade gradients; needs precision='parity')."""
@@ -229,7 +229,13 @@ class CodecEngine(object):
         if stream_k not in ('auto', 'on', 'off'):
             raise ValueError('Not valid stream_k')
         self._ctor = dict(num_channel=num_channel, code_size=code_size, num_node=num_node, separate=separate,
-                          precision=precision, grad_precision=grad_precision, cta_pair=cta_pair, stream_k=stream_k)
+                          precision=precision, grad_precision=grad_precision, cta_pair=cta_pair, stream_k=stream_k,
+                          deterministic=deterministic)
+        # deterministic=True: gradients are bit-identical from run to run, like the reference's CPU path -- every
+        # weight-gradient element of the wgrad GEMM has a single writer per launch (no K split), and the pointwise
+        # backward kernels accumulate their weight gradients in int64 fixed point instead of with float atomics.  (The
+        # loss value itself is a sum of fp64 atomics: order dependent in its last bits, identical after rounding to fp32.)
+        self.deterministic = bool(deterministic)
         # counts the forwards that saved state for a backward, over this engine and the engines cloned from it (one
         # per captured graph): whoever holds packed weight planes re-packs when it has moved (see _stale below)
         self.train_count = [0]
@@ -881,9 +887,10 @@ class CodecEngine(object):
         WB = self._bwd_buffers(layers, Bp, H, W, dev)
         f32 = dict(dtype=torch.float32, device=dev)
         gacc = torch.empty((Bn, Cc, H, W), **f32)
-        dw_e0 = torch.zeros_like(ctx['w_e0'])
-        db_e0 = torch.zeros_like(ctx['b_e0']) if ctx['b_e0'] is not None else None
-        dw_e4, dw_d0, dw_d4 = torch.zeros_like(ctx['w_e4']), torch.zeros_like(ctx['w_d0']), torch.zeros_like(ctx['w_d4'])
+        acc_dtype = torch.int64 if self.deterministic else torch.float32     # (deterministic: fixed point, see below)
+        dw_e0 = torch.zeros_like(ctx['w_e0'], dtype=acc_dtype)
+        db_e0 = torch.zeros_like(ctx['b_e0'], dtype=acc_dtype) if ctx['b_e0'] is not None else None
+        dw_e4, dw_d0, dw_d4 = (torch.zeros_like(ctx[k], dtype=acc_dtype) for k in ('w_e4', 'w_d0', 'w_d4'))
         gw = {ly.name: torch.zeros((ly.groups, 4 * ly.co, 9 * (ly.cin + ly.co)), **f32) for ly in layers}
         self._repack = True      # once per step; parameter versions cannot be trusted (fused optimizers)
         dpk = {ly.name: self._packed_dgrad(ly, sd, stream) for ly in layers}
@@ -986,7 +993,7 @@ class CodecEngine(object):
             units = sms
             if w.cta_pair:
                 tiles, units = tiles // 2, sms // 2
-            w.k_splits = _pick_k_splits(tiles, units, max(1, kb_per_group // 16))
+            w.k_splits = 1 if self.deterministic else _pick_k_splits(tiles, units, max(1, kb_per_group // 16))
             if overlap:
                 side.wait_event(planes_ready)
                 B.check(L.drasic_convlstm_bwd_weight(w, side.cuda_stream), 'convlstm_bwd_weight')
@@ -998,6 +1005,9 @@ class CodecEngine(object):
             self.launches += 4
 
         loss_scale = 1.0 / (T * float(Bn * Cc * H * W))
+        # fixed-point unit of the deterministic accumulators: 2^-30 of the loss scale (block partial sums are O(1e-3..1e3)
+        # loss scales: ~1e-9 relative resolution, 2^62 / 2^30 = 4e9 loss scales of head room)
+        fix_scale = float(2 ** 30) / loss_scale if self.deterministic else 0.0
         for t in range(T - 1, -1, -1):
             a = B.TailBwdArgs()
             a.d3_next, a.w_d4, a.img = P(A['D3']['next'][t][0]), P(ctx['w_d4']), P(img)
@@ -1007,6 +1017,7 @@ class CodecEngine(object):
             a.B_pad, a.C, a.H, a.W = Bp, Cc, H, W
             a.first, a.loss_kind, a.n_dec_groups, a.has_acc = int(t == 0), B.LOSS_KINDS[ctx['loss_kind']], self.Md, int(t < T - 1)
             a.group_iters, a.iter, a.n_enc_groups = P(ctx['group_iters']), t, self.M
+            a.fix_scale = fix_scale
             self._timed('tail_bwd', 0.0, lambda: B.check(L.drasic_tail_bwd(a, stream), 'tail_bwd'))
             for name in ('D3', 'D2', 'D1'):
                 lstm_layer_bwd(by[name], t)
@@ -1016,6 +1027,7 @@ class CodecEngine(object):
             b.w_e4, b.w_d0, b.perm, b.group_img_end = P(ctx['w_e4']), P(ctx['w_d0']), P(plan.perm), P(plan.group_img_end)
             b.dh_e3, b.dw_e4, b.dw_d0 = P(WB['E3']['dh_above']), P(dw_e4), P(dw_d0)
             b.B_pad, b.HW, b.Ch, b.code, b.n_enc_groups, b.n_dec_groups = Bp, hc * wc, 128, code, self.M, self.Md
+            b.fix_scale = fix_scale
             self._timed('bottleneck_bwd', 0.0, lambda: B.check(L.drasic_bottleneck_bwd(b, stream), 'bottleneck_bwd'))
             for name in ('E3', 'E2', 'E1'):
                 lstm_layer_bwd(by[name], t)
@@ -1026,11 +1038,15 @@ class CodecEngine(object):
             h.perm, h.group_img_end = P(plan.perm), P(plan.group_img_end)
             h.B_pad, h.C, h.H, h.W = Bp, Cc, H, W
             h.first, h.propagate, h.n_enc_groups = int(t == 0), int((not self.separate) and t > 0), self.M
+            h.fix_scale = fix_scale
             self._timed('head_bwd', 0.0, lambda: B.check(L.drasic_head_bwd(h, stream), 'head_bwd'))
             self.launches += 3
 
         if overlap:
             main.wait_stream(side)          # join: the unpack below reads the accumulated weight gradients
+        if self.deterministic:              # fixed point -> fp32
+            dw_e0, dw_e4, dw_d0, dw_d4 = ((v.double() / fix_scale).float() for v in (dw_e0, dw_e4, dw_d0, dw_d4))
+            db_e0 = (db_e0.double() / fix_scale).float() if db_e0 is not None else None
         for ly in layers:
             WB[ly.name]['last_amax'].copy_(amax_tab[ly.name][T - 1:T])
         # Every gradient is a view of ONE flat fp32 buffer laid out in the state_dict's own order (model.encoder.* then

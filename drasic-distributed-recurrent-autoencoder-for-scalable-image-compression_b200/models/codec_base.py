@@ -181,11 +181,12 @@ class CodecModel(nn.Module):
     def _ensure_engine(self):
         key = (config.PARAM['num_channel'], config.PARAM['code_size'], config.PARAM['num_node'],
                config.PARAM.get('precision', 'parity'), config.PARAM.get('grad_precision', 'fp16'),
-               config.PARAM.get('cta_pair', 'auto'), config.PARAM.get('stream_k', 'auto'))
+               config.PARAM.get('cta_pair', 'auto'), config.PARAM.get('stream_k', 'auto'),
+               bool(config.PARAM.get('deterministic', False)))
         if self._engine_key != key:
             self._check_architecture()
             self._engine = CodecEngine(key[0], key[1], key[2], separate=self.separate, precision=key[3],
-                                       grad_precision=key[4], cta_pair=key[5], stream_k=key[6])
+                                       grad_precision=key[4], cta_pair=key[5], stream_k=key[6], deterministic=key[7])
             self._engine_key = key
             self._graphs = {}
 

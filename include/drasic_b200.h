@@ -252,6 +252,12 @@ typedef struct {
   const float* dd0; const float* h_e3; const float* z; const float* codes; const float* w_e4;
   const float* w_d0; const int* perm; const int* group_img_end; float* dh_e3; float* dw_e4; float* dw_d0;
   int B_pad, HW, Ch, code, n_enc_groups, n_dec_groups;
+  /* Deterministic accumulation (fix_scale > 0, also in drasic_tail_bwd_args / drasic_head_bwd_args): the weight-gradient
+   * destinations (dw_e4, dw_d0; dw_d4; dw_e0, db_e0) are then int64 buffers of the same shapes and every block adds
+   * round(partial * fix_scale) -- integer addition is associative, so the sums do not depend on the order in which the
+   * blocks arrive (float atomics, the default, differ from run to run at the 1e-6 level); the caller divides by
+   * fix_scale afterwards.  Choose fix_scale so that |sum| * fix_scale < 2^62, e.g. 2^30 / loss_scale. */
+  double fix_scale;
 } drasic_bottleneck_bwd_args;
 int drasic_bottleneck_bwd(const drasic_bottleneck_bwd_args* a, void* stream);
 
@@ -264,6 +270,7 @@ typedef struct {
   int B_pad, C, H, W, first, loss_kind, n_dec_groups, has_acc;
   const int* group_iters;         /* nullable, as in drasic_tail_head_args: frozen nodes pass no gradient to the decoder */
   int iter, n_enc_groups;
+  double fix_scale;               /* see drasic_bottleneck_bwd_args */
 } drasic_tail_bwd_args;
 int drasic_tail_bwd(const drasic_tail_bwd_args* a, void* stream);
 
@@ -272,6 +279,7 @@ typedef struct {
   const float* du1; const float* w_e0; const float* b_e0; const float* img; const float* recon_prev;
   float* gacc; float* dw_e0; float* db_e0; const int* perm; const int* group_img_end;
   int B_pad, C, H, W, first, propagate, n_enc_groups;
+  double fix_scale;               /* see drasic_bottleneck_bwd_args */
 } drasic_head_bwd_args;
 int drasic_head_bwd(const drasic_head_bwd_args* a, void* stream);
 

@@ -36,9 +36,9 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(B.ConvLSTMArgs) == 15 * 8 + 14 * 4 + 3 * 8 + 4 + 4 + 8 + 4 + 4 + 2 * 8 + 8   # (pos_pairs, pad) (n_units, pad) (pos_order) (pos_imgs, stream_k) (sk_*)
     assert ctypes.sizeof(B.DgradArgs) == 9 * 8 + 9 * 4 + 4 + 3 * 8 + 4 + 4 + 8 + 4 + 4 + 2 * 8 + 8
     assert ctypes.sizeof(B.WgradArgs) == 9 * 8 + 10 * 4
-    assert ctypes.sizeof(B.BottleneckBwdArgs) == 11 * 8 + 6 * 4
-    assert ctypes.sizeof(B.TailBwdArgs) == 9 * 8 + 4 + 8 * 4 + 4 + 8 + 2 * 4
-    assert ctypes.sizeof(B.HeadBwdArgs) == 10 * 8 + 7 * 4 + 4
+    assert ctypes.sizeof(B.BottleneckBwdArgs) == 11 * 8 + 6 * 4 + 8                      # + fix_scale (double)
+    assert ctypes.sizeof(B.TailBwdArgs) == 9 * 8 + 4 + 8 * 4 + 4 + 8 + 2 * 4 + 8
+    assert ctypes.sizeof(B.HeadBwdArgs) == 10 * 8 + 7 * 4 + 4 + 8
     assert ctypes.sizeof(B.BottleneckArgs) == 12 * 8 + 8 * 4 + 8
     assert ctypes.sizeof(B.AdamTensor) == 4 * 8 + 8
     assert ctypes.sizeof(B.TailHeadArgs) == 13 * 8 + 10 * 4 + 8 + 4 + 4   # trailing pad to 8
@@ -118,7 +118,7 @@ def header_structs():
                 item = item.strip()
                 ptr = item.startswith('*')
                 fname = item.lstrip('* ').strip()
-                kind = 'ptr' if ptr else {'int': 'int', 'float': 'float', 'size_t': 'size_t', 'long long': 'll'}[base]
+                kind = 'ptr' if ptr else {'int': 'int', 'float': 'float', 'double': 'double', 'size_t': 'size_t', 'long long': 'll'}[base]
                 fields.append((kind, fname))
         out[name] = fields
     return out
@@ -132,8 +132,8 @@ def test_binding_structs_follow_the_header_field_for_field():
              'drasic_bottleneck_bwd_args': B.BottleneckBwdArgs, 'drasic_tail_bwd_args': B.TailBwdArgs,
              'drasic_head_bwd_args': B.HeadBwdArgs, 'drasic_adam_tensor': B.AdamTensor}
     assert sorted(structs) == sorted(pairs)
-    ctype_of = {'ptr': ctypes.c_void_p, 'int': ctypes.c_int, 'float': ctypes.c_float, 'size_t': ctypes.c_size_t,
-                'll': ctypes.c_longlong}
+    ctype_of = {'ptr': ctypes.c_void_p, 'int': ctypes.c_int, 'float': ctypes.c_float, 'double': ctypes.c_double,
+                'size_t': ctypes.c_size_t, 'll': ctypes.c_longlong}
     for name, cls in pairs.items():
         want = [(f, ctype_of[k]) for k, f in structs[name]]
         got = [(f, t) for f, t in cls._fields_]
