@@ -899,6 +899,7 @@ class CodecEngine(object):
         sms = self.sms()
         # true amax (float bits) of every (layer, iteration) gate-gradient tensor of this backward pass
         amax_tab = {ly.name: torch.zeros((T,), dtype=torch.int32, device=dev) for ly in layers}
+        no_amax = torch.zeros((1,), dtype=torch.int32, device=dev)
         # The weight-gradient GEMMs are off the critical path of backward-through-time (nothing but the final
         # unpack reads their result): they go to a side stream, so the HBM-bound cell / tail / head backward
         # kernels of the main stream run next to them instead of between the GEMMs.
@@ -927,7 +928,9 @@ class CodecEngine(object):
             n_pix = Bp * ly.h * ly.w
             # fused cell backward -> scaled fp16 planes; scale predicted from the previously processed iteration
             am = amax_tab[ly.name]
-            prev = am[t + 1:t + 2] if t < T - 1 else wb['last_amax']
+            # (deterministic mode: no memory of the previous step -- the first iteration processed starts from "no
+            # prediction" and takes the exact scale through the verify pass, so the bits depend on this step's data only)
+            prev = am[t + 1:t + 2] if t < T - 1 else (no_amax if self.deterministic else wb['last_amax'])
             f = B.LstmBwdFusedArgs()
             f.gates, f.gates_f32 = P(Lb['gates'][t]), self.gsplit
             f.c_t, f.c_prev = P(Lb['c'][t]), P(Lb['c'][t - 1]) if t > 0 else None
