@@ -43,6 +43,7 @@ METRIC = 'images/s train & encode+decode at T=16 (CIFAR-10 32x32), 1/2/4/8 B200;
 CPU_SAMPLE = {'train': 64, 'eval': 256}
 PARITY_SAMPLE = 256
 PDL_ON = False
+DETERMINISTIC = False     # --deterministic: bit-reproducible gradients (single-writer wgrad, fixed-point pointwise accumulation)
 STREAM_K = 'auto'          # --stream-k: schedule of the gate / dgrad GEMMs (auto: stream-K for launches of few work items per SM)
 
 
@@ -234,7 +235,8 @@ class Arm(object):
     def _apply_config(self):
         c = self.config
         c.PARAM.update(device='cuda', data_name='CIFAR10' if self.channels == 3 else 'MNIST', precision=self.precision,
-                       pack_mode='reference', grad_precision=self.grad_precision, loss_fn='mae', stream_k=STREAM_K)
+                       pack_mode='reference', grad_precision=self.grad_precision, loss_fn='mae', stream_k=STREAM_K,
+                       deterministic=DETERMINISTIC)
         c.PARAM['control'] = {'normalization': 'none', 'activation': 'tanh', 'num_iter': str(T_ITER),
                               'code_size': '8', 'num_node': str(self.nodes)}
         import utils
@@ -387,7 +389,7 @@ class Arm(object):
             'config': dict(workload_config(r['mode'], B, world, self.channels, self.nodes),
                            **({'workload': self.workload} if self.workload else {})),
             'impl_config': {'precision': self.precision, 'grad_precision': self.grad_precision if train else None,
-                            'cuda_graph': r['graph'], 'stream_k': STREAM_K, 'pdl': PDL_ON,
+                            'cuda_graph': r['graph'], 'stream_k': STREAM_K, 'pdl': PDL_ON, 'deterministic': DETERMINISTIC,
                             'parallelism': (('dp{}: sharded by source (rank r owns nodes r mod N), one NCCL all-reduce of the joint '
                                              "decoder's gradients per step" if self.by_source else
                                              'dp{}: batch sharded, one NCCL all-reduce of gradients per step').format(world) if train
@@ -660,6 +662,7 @@ def main():
     ap.add_argument('--multi-parity', action='store_true', help='N>1: run the in-line gradient parity check in train / eval mode too')
     ap.add_argument('--stream-k', default='auto', choices=['auto', 'on', 'off'])
     ap.add_argument('--pdl', action='store_true', help='experimental: programmatic dependent launches (hangs intermittently in training)')
+    ap.add_argument('--deterministic', action='store_true', help='bit-reproducible training step (config.PARAM["deterministic"])')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-fast', action='store_true', help='skip the secondary fast-precision measurement')
     args = ap.parse_args()
@@ -668,8 +671,8 @@ def main():
         # and only the joint decoder's gradients are exchanged
         world = int(os.environ.get('WORLD_SIZE', '1'))
         args.shard = 'source' if (world > 1 and M_NODES >= world) else 'batch'
-    global STREAM_K, PDL_ON
-    STREAM_K, PDL_ON = args.stream_k, args.pdl
+    global STREAM_K, PDL_ON, DETERMINISTIC
+    STREAM_K, PDL_ON, DETERMINISTIC = args.stream_k, args.pdl, args.deterministic
     if args.impl == 'reference':
         run_reference(args)
     else:

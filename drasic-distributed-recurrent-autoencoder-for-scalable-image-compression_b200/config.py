@@ -3,7 +3,9 @@ caller scripts turn every key into a command-line flag, train_model.py:20-36).  
 B200-specific: 'precision' ('parity' = fp32-grade split-fp16 tensor-core path with bit-exact codes,
 'fast' = single fp16) and 'pack_mode' ('reference' = the reference's np.packbits semantics, 'bits' =
 the real 1 bit/symbol stream), 'grad_precision' ('fp16' | 'parity') and 'cuda_graph' (capture the whole T-iteration
-loop, forward and backward, as one CUDA graph per batch shape)."""
+loop, forward and backward, as one CUDA graph per batch shape).  Further optional keys read with .get(): 'cta_pair',
+'stream_k' ('auto' | 'on' | 'off'), 'node_iters' (per-node iteration budgets) and 'deterministic' (True: gradients are
+bit-identical from run to run, like the reference's CPU path; a few per cent slower)."""
 
 
 def init():
