@@ -244,6 +244,7 @@ class CodecEngine(object):
         # move fewer bytes per MMA but leave 9..180 work units for 74 CTA pairs; measured per step at B=1024 they are
         # slower on every layer (D1 7.8 vs 4.9 ms, E1 10.0 vs 8.5, D2 20.1 vs 17.9, D3 8.7 vs 8.5)
         self.wgrad_pair_mode = 1      # (an attribute, not an environment knob: tests set it to 2)
+        self.wgrad_min_kb = 256       # K blocks (of 64 pixels) every K split of a wgrad tile keeps at least
         self.gsplit = 1 if grad_precision == 'parity' else 0
         self.C, self.code, self.M, self.separate = num_channel, code_size, num_node, separate
         self.split = 1 if precision == 'parity' else 0
@@ -996,7 +997,12 @@ class CodecEngine(object):
             units = sms
             if w.cta_pair:
                 tiles, units = tiles // 2, sms // 2
-            w.k_splits = 1 if self.deterministic else _pick_k_splits(tiles, units, max(1, kb_per_group // 16))
+            # a K split costs its own accumulate pass over the tile (a 128 KB red.add per CTA): every split keeps at
+            # least wgrad_min_kb K blocks (256 x 64 pixels), which at small batch means no split at all -- the wgrad GEMMs
+            # run next to the main stream's kernels, where their memory traffic counts for more than their own latency
+            # (measured, training img/s at B=128 / B=1024 for 16, 64, 256 K blocks: 2 951 / 4 438, 2 997 / 4 435,
+            # 3 110 / 4 424; the stand-alone wgrad rate at B=1024 drops from 1 245 to 1 169 TFLOP/s)
+            w.k_splits = 1 if self.deterministic else _pick_k_splits(tiles, units, max(1, kb_per_group // self.wgrad_min_kb))
             if overlap:
                 side.wait_event(planes_ready)
                 B.check(L.drasic_convlstm_bwd_weight(w, side.cuda_stream), 'convlstm_bwd_weight')
