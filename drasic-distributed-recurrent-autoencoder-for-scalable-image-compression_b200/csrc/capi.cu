@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 
 #include "../../include/drasic_b200.h"
 #include "kernels.h"
@@ -45,9 +46,44 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached per (kind, base pointer, shape, box): a training step launches ~300 GEMMs that name
+// the same few dozen planes iteration after iteration, and cuTensorMapEncodeTiled is the most expensive thing the host
+// does per launch.  A map encodes only the pointer and the geometry, never contents, so a cached map stays valid for as
+// long as the same pointer is used with the same shape (a re-allocated buffer at the same address gets the same map).
+struct MapKey {
+  const void* base;
+  long long a, b, c, d;
+  int kind, e, f, g, h;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && a == o.a && b == o.b && c == o.c && d == o.d && kind == o.kind && e == o.e && f == o.f &&
+           g == o.g && h == o.h;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t x = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    const long long v[9] = {k.a, k.b, k.c, k.d, k.kind, k.e, k.f, k.g, k.h};
+    for (long long t : v) x = (x ^ static_cast<size_t>(t)) * 0x100000001B3ull;
+    return x;
+  }
+};
+thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+bool cached_map(const MapKey& k, CUtensorMap* m) {
+  auto it = g_maps.find(k);
+  if (it == g_maps.end()) return false;
+  *m = it->second;
+  return true;
+}
+void remember_map(const MapKey& k, const CUtensorMap& m) {
+  if (g_maps.size() > 4096) g_maps.clear();      // (arenas were re-allocated many times: start over)
+  g_maps.emplace(k, m);
+}
+
 // NHWC fp16 activation plane [N,H,W,C]; box = (64 channels, bw, bh, bn) pixels, 128B swizzle,
 // out-of-bounds elements (the conv halo) read as zero.
 int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
+  const MapKey key{base, N, H, W, C, 0, bw, bh, bn, 0};
+  if (cached_map(key, m)) return 0;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(DRASIC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
@@ -63,6 +99,7 @@ int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, i
   if (r != CUDA_SUCCESS)
     return fail(DRASIC_ERR_TENSORMAP, "activation tensor map rejected (CUresult %d) N=%d H=%d W=%d C=%d box=%dx%dx%d",
                 static_cast<int>(r), N, H, W, C, bw, bh, bn);
+  remember_map(key, *m);
   return 0;
 }
 
@@ -70,6 +107,8 @@ int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, i
 // box = `nchunk` stacked (64 ch x pixel-box) tiles, each in the MN-major SWIZZLE_128B layout (wgrad.cu)
 int make_act_map_chunked(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn,
                          int nchunk) {
+  const MapKey key{base, N, H, W, C, 1, bw, bh, bn, nchunk};
+  if (cached_map(key, m)) return 0;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(DRASIC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
   const cuuint64_t dims[5] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
@@ -85,12 +124,15 @@ int make_act_map_chunked(CUtensorMap* m, const void* base, int N, int H, int W, 
   if (r != CUDA_SUCCESS)
     return fail(DRASIC_ERR_TENSORMAP, "chunked activation tensor map rejected (CUresult %d) N=%d H=%d W=%d C=%d box=%dx%dx%dx%d",
                 static_cast<int>(r), N, H, W, C, bw, bh, bn, nchunk);
+  remember_map(key, *m);
   return 0;
 }
 
 // packed weights, tile-contiguous ([N tile][K block][tile rows][64] fp16): `rows` rows of 64 elements, 128 bytes apart;
 // box = (64, box_rows) = one contiguous run of box_rows * 128 bytes
 int make_weight_map(CUtensorMap* m, const void* base, long long rows, int box_rows) {
+  const MapKey key{base, rows, 0, 0, 0, 2, box_rows, 0, 0, 0};
+  if (cached_map(key, m)) return 0;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(DRASIC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
   const cuuint64_t dims[2] = {drasic::BLOCK_K, static_cast<cuuint64_t>(rows)};
@@ -102,6 +144,7 @@ int make_weight_map(CUtensorMap* m, const void* base, long long rows, int box_ro
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(DRASIC_ERR_TENSORMAP, "weight tensor map rejected (CUresult %d) rows=%lld box_rows=%d", static_cast<int>(r), rows, box_rows);
+  remember_map(key, *m);
   return 0;
 }
 
