@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import build_model, sd_digest
+from conftest import ROOT, build_model, sd_digest
 from engine import binding as B
 from engine.cell import from_nhwc, to_planes
 from engine.codec import BatchPlan, PAD
@@ -369,3 +369,44 @@ def test_position_pairs_share_their_tap_sets():
         union = [bin(taps(a, h, w) | taps(b, h, w)).count('1') for a, b in pairs]
         n9 = (h - 2) * (w - 2) // 2
         assert union[:n9] == [9] * n9 and union[n9:] == [6] * ((h - 2) + (w - 2) + 2)
+
+
+def test_pads_for_follow_the_smallest_layer():
+    """engine.codec.pads_for: node ranges are whole wgrad K blocks (64 pixels) of the smallest layer when a backward will
+    run, the batch whole M tiles (128 pixels); inference packs the nodes back to back"""
+    from engine.codec import pads_for, plan_arrays
+    assert pads_for(32, 32, True) == (4, 8) and pads_for(32, 32, False) == (1, 8)
+    assert pads_for(16, 16, True) == (16, 32) and pads_for(16, 16, False) == (1, 32)
+    assert pads_for(512, 768, True) == (4, 8)
+    # the 28 / 36 split of 16x16 inputs that used to put two nodes into one K block
+    pad, total = pads_for(16, 16, True)
+    perm, ends, counts = plan_arrays(np.array([0] * 28 + [1] * 36), 2, pad=pad, total_pad=total)
+    assert list(ends) == [32, 96] and perm.size == 96 and np.all((ends * 4) % 64 == 0)
+
+
+def test_active_groups_and_single_node_collapse():
+    """CodecEngine._active_groups: nodes without samples are not packed; a per-node layer with ONE active node runs as
+    one group on that node's planes"""
+    from engine.codec import BatchPlan, CodecEngine, _Layer
+    ly = _Layer()
+    ly.groups = 4
+    CodecEngine._active_groups(ly, BatchPlan(np.array([2, 2, 0, 2]), 4, 'cpu', pad=1))
+    assert (ly.active, ly.g0, ly.gemm_groups) == ([0, 2], 0, 4)
+    CodecEngine._active_groups(ly, BatchPlan(np.array([2, 2, 2]), 4, 'cpu', pad=1))
+    assert (ly.active, ly.g0, ly.gemm_groups) == ([2], 2, 1)
+    ly.groups = 1
+    CodecEngine._active_groups(ly, BatchPlan(np.array([0, 0]), 1, 'cpu', pad=1))
+    assert (ly.active, ly.g0, ly.gemm_groups) == (None, 0, 1)
+
+
+def test_bench_traffic_comes_from_the_committed_capture_of_the_same_configuration():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t, note = bench.captured_traffic('eval', 1024, 8, 'parity')
+    assert t is not None and 2e8 < t < 5e9 and 'r2_ncu_full_gates_eval_B1024_summary.csv' in note
+    for other in [('train', 1024, 8, 'parity'), ('eval', 128, 8, 'parity'), ('eval', 1024, 1, 'parity'), ('eval', 1024, 8, 'fast')]:
+        assert bench.captured_traffic(*other)[0] is None
+    a, b = bench.workload_config('train', 1024, 1), bench.workload_config('train', 1024, 1)
+    assert a == b and set(a) >= {'workload', 'batch_per_gpu', 'global_batch', 'num_node', 'num_iter'}
