@@ -134,15 +134,20 @@ __global__ void amax2_kernel(const __grid_constant__ PackBatch b, size_t na, siz
   if ((threadIdx.x & 31) == 0) atomicMax(out + b.slot[blockIdx.y], __float_as_uint(m));
 }
 
-__global__ void pack_dgrad_kernel(const __grid_constant__ PackBatch b, int Cin, int Co, int in_order, int out_order,
-                                  const unsigned int* __restrict__ amax_all, __half* __restrict__ hi_all,
-                                  __half* __restrict__ lo_all, float* __restrict__ inv_all) {
-  const float* __restrict__ w_in = b.w_in[blockIdx.y];
-  const float* __restrict__ w_h = b.w_h[blockIdx.y];
-  const int slot = b.slot[blockIdx.y];
+// Block = 64 consecutive packed gate channels r (one gate, 64 physical output channels = one 64-element run of K per
+// tap) x 16 consecutive output rows n (input channels): the 64 x 16 x 9 weights are staged in shared memory from runs of
+// contiguous taps, then every (n, tap) writes its 64 K elements as one 128-byte run.
+constexpr int PD_ROWS = 64, PD_CH = 16;
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const __grid_constant__ PackBatch b, int Cin, int Co, int in_order,
+                                                         int out_order, const unsigned int* __restrict__ amax_all,
+                                                         __half* __restrict__ hi_all, __half* __restrict__ lo_all,
+                                                         float* __restrict__ inv_all) {
+  __shared__ float s_w[PD_ROWS][PD_CH * 9 + 1];   // (odd row stride: the 64 rows of one (n, tap) sit in distinct banks)
+  const float* __restrict__ w_in = b.w_in[blockIdx.z];
+  const float* __restrict__ w_h = b.w_h[blockIdx.z];
+  const int slot = b.slot[blockIdx.z];
   const int K = 9 * 4 * Co;
   const int N = Cin + Co;
-  const size_t total = static_cast<size_t>(N) * K;
   // tile-contiguous layout [N tile of 256 rows][K block of 64][256 rows][64]; a group's plane holds whole tiles
   const size_t plane = static_cast<size_t>((N + 255) / 256 * 256) * K;
   __half* __restrict__ out_hi = hi_all + static_cast<size_t>(slot) * plane;
@@ -155,20 +160,28 @@ __global__ void pack_dgrad_kernel(const __grid_constant__ PackBatch b, int Cin, 
     shift = 11 - e;
   }
   const float scale = ldexpf(1.0f, shift);
-  if (blockIdx.x == 0 && threadIdx.x == 0) inv_all[slot] = ldexpf(1.0f, -shift);
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total; idx += stride) {
-    const int n = static_cast<int>(idx / K);
-    const int k = static_cast<int>(idx - static_cast<size_t>(n) * K);
-    const int tapf = k / (4 * Co);
-    const int r = k - tapf * 4 * Co;
-    const int gate = r / Co, pout = r - gate * Co;
-    const int orow = gate * Co + logical_of_b(pout, Co, out_order);
-    const int tap = 8 - tapf;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) inv_all[slot] = ldexpf(1.0f, -shift);
+  const int r0 = blockIdx.x * PD_ROWS;     // packed gate channels r0 .. r0+63 (Co is a multiple of 64: one gate)
+  const int n0 = blockIdx.y * PD_CH;       // output rows n0 .. n0+15 (Cin is a multiple of 64: all x or all h)
+  const int gate = r0 / Co, pout0 = r0 - gate * Co;
+  const bool is_x = n0 < Cin;
+  for (int i = threadIdx.x; i < PD_ROWS * PD_CH * 9; i += blockDim.x) {
+    const int row = i / (PD_CH * 9), rem = i - row * (PD_CH * 9);
+    const int ch = rem / 9, tap = rem - ch * 9;
+    const int orow = gate * Co + logical_of_b(pout0 + row, Co, out_order);
     float v;
-    if (n < Cin) v = w_in[(static_cast<size_t>(orow) * Cin + logical_of_b(n, Cin, in_order)) * 9 + tap];
-    else v = w_h[(static_cast<size_t>(orow) * Co + logical_of_b(n - Cin, Co, out_order)) * 9 + tap];
-    v *= scale;
+    if (is_x) v = w_in[(static_cast<size_t>(orow) * Cin + logical_of_b(n0 + ch, Cin, in_order)) * 9 + tap];
+    else v = w_h[(static_cast<size_t>(orow) * Co + logical_of_b(n0 + ch - Cin, Co, out_order)) * 9 + tap];
+    s_w[row][ch * 9 + tap] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PD_CH * 9 * PD_ROWS; i += blockDim.x) {
+    const int row = i & (PD_ROWS - 1);     // fastest: the 64 consecutive K elements of one (n, tap)
+    const int ct = i >> 6;
+    const int ch = ct / 9, tapf = ct - ch * 9;
+    const int n = n0 + ch;
+    const int k = tapf * 4 * Co + r0 + row;
+    const float v = s_w[row][ch * 9 + 8 - tapf] * scale;   // conv transpose: tap flipped
     const __half hi = __float2half_rn(v);
     const size_t off = ((static_cast<size_t>(n >> 8) * (K / 64) + k / 64) * 256 + (n & 255)) * 64 + (k & 63);
     out_hi[off] = hi;
@@ -625,8 +638,8 @@ int launch_pack_dgrad_weights(const PackBatch& b, int n, int n_slots, int Cin, i
   const size_t na = static_cast<size_t>(4 * Co) * Cin * 9, nb = static_cast<size_t>(4 * Co) * Co * 9;
   const int bx = n >= 4 ? 148 : 296;
   amax2_kernel<<<dim3(bx, n), 256, 0, stream>>>(b, na, nb, scratch_amax);
-  pack_dgrad_kernel<<<dim3(4 * bx, n), 256, 0, stream>>>(b, Cin, Co, in_order, out_order, scratch_amax, out_hi, out_lo,
-                                                         inv_scale_out);
+  pack_dgrad_kernel<<<dim3(4 * Co / PD_ROWS, (Cin + Co) / PD_CH, n), 256, 0, stream>>>(b, Cin, Co, in_order, out_order,
+                                                                                       scratch_amax, out_hi, out_lo, inv_scale_out);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_unpack_wgrad(const float* gw, int Cin, int Co, int in_order, int out_order, float* dw_in,

@@ -35,11 +35,13 @@ __global__ void amax_kernel(const __grid_constant__ PackBatch b, size_t na, size
   if ((threadIdx.x & 31) == 0) atomicMax(out + b.slot[blockIdx.y], __float_as_uint(m));  // non-negative floats order as uints
 }
 
-__global__ void pack_kernel(const __grid_constant__ PackBatch b, int Cin, int Co, int in_order, int out_order, int block_n,
-                            const unsigned int* __restrict__ amax_all, __half* __restrict__ hi_all,
-                            __half* __restrict__ lo_all, float* __restrict__ inv_all) {
-  const float* __restrict__ w_in = b.w_in[blockIdx.y];
-  const float* __restrict__ w_h = b.w_h[blockIdx.y];
+// One packed row (output channel) per block: the row's OIHW weights -- Cin*9 + Co*9 contiguous floats -- are staged in
+// shared memory with coalesced reads, then written out in packed order, 64 consecutive K elements = one 128-byte run.
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackBatch b, int Cin, int Co, int in_order,
+                                                   int out_order, int block_n, const unsigned int* __restrict__ amax_all,
+                                                   __half* __restrict__ hi_all, __half* __restrict__ lo_all,
+                                                   float* __restrict__ inv_all) {
+  extern __shared__ float s_row[];   // [Cin*9 | Co*9]
   const int slot = b.slot[blockIdx.y];
   const int K = 9 * (Cin + Co);
   const size_t total = static_cast<size_t>(4 * Co) * K;
@@ -55,27 +57,27 @@ __global__ void pack_kernel(const __grid_constant__ PackBatch b, int Cin, int Co
   const float scale = ldexpf(1.0f, shift);
   if (blockIdx.x == 0 && threadIdx.x == 0) inv_all[slot] = ldexpf(1.0f, -(shift + ACT_SHIFT));
   const int slots = block_n >> 2;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += stride) {
-    const int r = static_cast<int>(idx / K);
-    const int k = static_cast<int>(idx - static_cast<size_t>(r) * K);
-    const int nt = r / block_n;
-    const int rr = r - nt * block_n;
-    const int gate = rr / slots;
-    const int s = rr - gate * slots;
-    const int co = logical_of(nt * slots + s, Co, out_order);
-    const int orow = gate * Co + co;  // gates.chunk(4, 1): i, f, g, o blocks (cell.py:133)
+  const int r = blockIdx.x;                       // packed row
+  const int nt = r / block_n;
+  const int rr = r - nt * block_n;
+  const int gate = rr / slots;
+  const int sl = rr - gate * slots;
+  const int co = logical_of(nt * slots + sl, Co, out_order);
+  const int orow = gate * Co + co;  // gates.chunk(4, 1): i, f, g, o blocks (cell.py:133)
+  const float* __restrict__ src_in = b.w_in[blockIdx.y] + static_cast<size_t>(orow) * Cin * 9;
+  const float* __restrict__ src_h = b.w_h[blockIdx.y] + static_cast<size_t>(orow) * Co * 9;
+  for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) s_row[i] = src_in[i];
+  for (int i = threadIdx.x; i < Co * 9; i += blockDim.x) s_row[Cin * 9 + i] = src_h[i];
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float v;
     if (k < 9 * Cin) {
       const int tap = k / Cin, pin = k - tap * Cin;
-      const int ci = logical_of(pin, Cin, in_order);
-      v = w_in[(static_cast<size_t>(orow) * Cin + ci) * 9 + tap];
+      v = s_row[logical_of(pin, Cin, in_order) * 9 + tap];
     } else {
       const int kk = k - 9 * Cin;
       const int tap = kk / Co, ph = kk - tap * Co;
-      const int ch = logical_of(ph, Co, out_order);
-      v = w_h[(static_cast<size_t>(orow) * Co + ch) * 9 + tap];
+      v = s_row[Cin * 9 + logical_of(ph, Co, out_order) * 9 + tap];
     }
     v *= scale;
     const __half hi = __float2half_rn(v);
@@ -98,8 +100,8 @@ int launch_pack_lstm_weights(const PackBatch& b, int n, int n_slots, int Cin, in
   const size_t na = static_cast<size_t>(4 * Co) * Cin * 9, nb = static_cast<size_t>(4 * Co) * Co * 9;
   const int bx = n >= 4 ? 148 : 296;
   amax_kernel<<<dim3(bx, n), 256, 0, stream>>>(b, na, nb, scratch_amax);
-  pack_kernel<<<dim3(4 * bx, n), 256, 0, stream>>>(b, Cin, Co, in_order, out_order, block_n, scratch_amax, out_hi, out_lo,
-                                                   inv_scale_out);
+  pack_kernel<<<dim3(4 * Co, n), 256, static_cast<size_t>(9) * (Cin + Co) * sizeof(float), stream>>>(
+      b, Cin, Co, in_order, out_order, block_n, scratch_amax, out_hi, out_lo, inv_scale_out);
   return static_cast<int>(cudaGetLastError());
 }
 
