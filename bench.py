@@ -106,23 +106,28 @@ class ClockSampler(object):
 
 def captured_traffic(mode, B, nodes, precision):
     """DRAM bytes per launch of the dominant kernel (forward gate GEMM) from the committed `ncu --set full` capture of
-    the SAME mode and configuration, or None: profiles/r2_ncu_full_gates_eval_B1024_summary.csv holds the six gate
-    launches of one eval iteration at B=1024, M=8, parity precision (tools/ncu_round2.sh gates)"""
-    if not (mode == 'eval' and B == 1024 and nodes == 8 and precision == 'parity'):
+    the SAME mode and configuration, or None.  profiles/r2_ncu_full_gates_eval_B1024_summary.csv holds the six gate
+    launches of one eval iteration at B=1024, M=8, parity precision (tools/ncu_round2.sh gates);
+    profiles/r2_ncu_full_gates_train_fwd_B1024_summary.csv the twelve of a training forward's first two iterations
+    (tools/ncu_round2.sh train_fwd), of which the last six (t = 1: hidden convolution included, as in 15 of the 16
+    iterations) are averaged."""
+    if not (B == 1024 and nodes == 8 and precision == 'parity'):
         return None, 'no ncu --set full capture of this mode / configuration under profiles/'
-    path = os.path.join(ROOT, 'profiles', 'r2_ncu_full_gates_eval_B1024_summary.csv')
+    name = 'r2_ncu_full_gates_{}_B1024_summary.csv'.format('eval' if mode == 'eval' else 'train_fwd')
+    path = os.path.join(ROOT, 'profiles', name)
     try:
         import csv
         rows = list(csv.reader(open(path)))
-        unit = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+        unit = {'Tbyte': 1e12, 'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
         cols = {}
         for i, h in enumerate(rows[0]):
             for key in ('dram_rd', 'dram_wr'):
                 if h.startswith(key):
                     cols[key] = (i, unit[h[h.index('[') + 1:h.index(']')]])
         per = [sum(float(r[cols[k][0]]) * cols[k][1] for k in ('dram_rd', 'dram_wr')) for r in rows[1:] if 'conv_gemm' in r[0]]
-        return sum(per) / len(per), ('dram__bytes_read.sum + dram__bytes_write.sum, mean over the {} gate launches of one iteration, '
-                                     'profiles/r2_ncu_full_gates_eval_B1024_summary.csv').format(len(per))
+        per = per[-6:]
+        return sum(per) / len(per), ('dram__bytes_read.sum + dram__bytes_write.sum, mean over the {} forward gate launches of one '
+                                     'iteration, profiles/{}').format(len(per), name)
     except Exception as e:          # the capture is evidence, not a dependency
         return None, 'capture unreadable: {}'.format(e)
 
