@@ -89,15 +89,13 @@ class BatchPlan(object):
         self._kb_end, self._units = {}, {}
         self.static = static_hw is not None
         pre = tuple(dict.fromkeys(static_hw if static_hw is not None else (hws or ())))
-        parts = [perm, ends]
-        for hw in pre:
-            parts.append(self._kb_host(hw))
-            parts.extend(self._units_host(hw, pair).reshape(-1) for pair in (False, True))
-        flat = np.concatenate(parts).astype(np.int32, copy=False)
+        self._pre = pre
+        flat = self._flat_host()
         on_gpu = torch.device(device).type == 'cuda'
         host = torch.empty(flat.size, dtype=torch.int32, pin_memory=on_gpu)
         host.numpy()[:] = flat
         buf = host.to(device, non_blocking=True) if on_gpu else host
+        self._buf, self._stage, self._n_update = buf, [], 0
         M, off = num_node, 0
 
         def take(n):
@@ -110,6 +108,15 @@ class BatchPlan(object):
             self._kb_end[hw] = take(M)
             for pair in (False, True):
                 self._units[(hw, pair)] = take(3 * M).view(3, M)
+
+    def _flat_host(self):
+        """perm, node ends and the K-block / unit tables of the pre-registered layer sizes as one int32 array (the layout
+        of the device buffer the tables are views of)"""
+        parts = [self.perm_host, self.group_img_end_host]
+        for hw in self._pre:
+            parts.append(self._kb_host(hw))
+            parts.extend(self._units_host(hw, pair).reshape(-1) for pair in (False, True))
+        return np.concatenate(parts).astype(np.int32, copy=False)
 
     def kb_end(self, hw):
         """exclusive end K block (64 pixels) of each node, for the wgrad GEMM (node ranges are multiples of 4
@@ -160,12 +167,28 @@ class BatchPlan(object):
             raise ValueError('Not valid batch size for this static plan')
         self._frozen = True
         self.counts, self.group_img_end_host, self.perm_host = counts, ends, perm
-        self.perm.copy_(torch.from_numpy(perm), non_blocking=False)
-        self.group_img_end.copy_(torch.from_numpy(ends))
-        for hw, t in self._kb_end.items():
-            t.copy_(torch.from_numpy(self._kb_host(hw)))
+        flat = self._flat_host()
+        for hw, t in self._kb_end.items():                      # (tables asked for outside the pre-registered sizes)
+            if hw not in self._pre:
+                t.copy_(torch.from_numpy(self._kb_host(hw)))
         for (hw, pair), t in self._units.items():
-            t.copy_(torch.from_numpy(self._units_host(hw, pair)))
+            if hw not in self._pre:
+                t.copy_(torch.from_numpy(self._units_host(hw, pair)))
+        if not self._buf.is_cuda:
+            self._buf.numpy()[:] = flat
+            return
+        # ONE asynchronous copy from pinned memory (the tables are views of one device buffer).  Two staging buffers
+        # take turns; one is rewritten only after the copy that last read it has completed.
+        if len(self._stage) < 2:
+            self._stage.append([torch.empty(flat.size, dtype=torch.int32, pin_memory=True), None])
+        stage = self._stage[self._n_update % len(self._stage)]
+        self._n_update += 1
+        if stage[1] is not None:
+            stage[1].synchronize()
+        stage[0].numpy()[:] = flat
+        self._buf.copy_(stage[0], non_blocking=True)
+        stage[1] = torch.cuda.Event()
+        stage[1].record(torch.cuda.current_stream(self._buf.device))
 
 
 class _Layer(object):

@@ -279,6 +279,10 @@ class CodecModel(nn.Module):
             self._free_hidden()
             raise RuntimeError('all elements of input should be between 0 and 1')
         T = recon.shape[0]
+        if use_graph:
+            # a graph's output buffers are rewritten by its next replay: the lazily built code list below reads copies
+            # (device to device on the launching stream -- no host synchronisation, unlike materialising it here)
+            codes, bits = codes.clone(), bits.clone()
         output = {'loss': loss, 'img': [recon[t] for t in range(T)], 'code_pm1': codes, 'bits': bits}
         if mse is not None:
             output['mse'] = mse                                     # metrics.psnr_per_iteration(output)
@@ -295,7 +299,5 @@ class CodecModel(nn.Module):
                     out.append(per_iter[t] if t == 0 else np.concatenate((out[t - 1], per_iter[t]), axis=1))
                 return out
         output['code'] = CodeList(T, make)                          # materialised at the first access
-        if use_graph:
-            output['code']._get()                                   # a graph's output buffers are rewritten by its next replay
         self._free_hidden()                                         # dist_codec.py:64
         return output

@@ -218,12 +218,19 @@ def test_cuda_graph_matches_eager_eval_and_train():
         with torch.no_grad():
             eager.append(m({'img': img.cuda(), 'label': label.cuda()}))
     config.PARAM['cuda_graph'] = True
+    graphed = []
     for (img, label), ref in zip(batches, eager):
         with torch.no_grad():
             out = m({'img': img.cuda(), 'label': label.cuda()})
         assert torch.equal(out['code_pm1'], ref['code_pm1'])
         assert torch.equal(torch.stack(out['img']), torch.stack(ref['img']))
         assert out['loss'].item() == ref['loss'].item()
+        graphed.append(out)
+    # the code lists are built lazily from copies of the graph's output buffers: later replays must not leak into them
+    for out, ref in zip(graphed, eager):
+        assert torch.equal(out['code_pm1'], ref['code_pm1']) and torch.equal(out['bits'], ref['bits'])
+        assert len(out['code']) == len(ref['code'])
+        assert all(np.array_equal(a, b) for a, b in zip(out['code'], ref['code']))
     # ---- train: gradients from the graph == eager gradients; then an optimizer step and again
     opt = torch.optim.SGD(m.parameters(), lr=0.05)
     for step in range(2):

@@ -48,6 +48,37 @@ def test_inference_plan_packs_nodes_back_to_back():
     assert u.numpy().tolist() == [[0, 0], [1, 4], [1, 5]] and total == 5
 
 
+def test_static_plan_update_rewrites_every_table_in_place():
+    """what a captured graph reads: the tables of a static plan are views of ONE buffer; update() refreshes all of them
+    (one copy) and they then equal the tables of a fresh plan of the same padded size"""
+    from engine.codec import worst_case_pad
+    rng = np.random.RandomState(0)
+    for pad in (1, 4):
+        Bn, M, hws = 48, 4, (16, 64, 256)
+        total = worst_case_pad(Bn, M, pad, 8)
+        p = BatchPlan(np.arange(Bn) % M, M, 'cpu', pad_total=total, static_hw=hws, pad=pad)
+        views = [p.perm, p.group_img_end] + [p.kb_end(hw) for hw in hws] + [p.m_units(hw, pr)[0] for hw in hws for pr in (False, True)]
+        ptrs = [v.data_ptr() for v in views]
+        for _ in range(3):
+            label = rng.randint(0, M, Bn)
+            label[label == 1] = 0                                    # an empty node
+            p.update(label)
+            q = BatchPlan(label, M, 'cpu', pad_total=total, pad=pad)
+            assert p.perm.numpy().tolist() == q.perm_host.tolist() == p.perm_host.tolist()
+            assert p.group_img_end.numpy().tolist() == q.group_img_end_host.tolist()
+            for hw in hws:
+                assert p.kb_end(hw).numpy().tolist() == q.kb_end(hw).numpy().tolist()
+                for pr in (False, True):
+                    assert p.m_units(hw, pr)[0].numpy().tolist() == q.m_units(hw, pr)[0].numpy().tolist()
+                    assert p.m_units(hw, pr)[1] >= q.m_units(hw, pr)[1]      # the static launch bound covers any labelling
+            assert [v.data_ptr() for v in [p.perm, p.group_img_end] + [p.kb_end(hw) for hw in hws]
+                    + [p.m_units(hw, pr)[0] for hw in hws for pr in (False, True)]] == ptrs
+        with pytest.raises(ValueError):
+            p.update(np.zeros(Bn + 1, dtype=np.int64))
+        with pytest.raises(RuntimeError):
+            p.kb_end(4)                                              # a frozen static plan has no buffer for a new size
+
+
 def test_batch_plan_rejects_bad_labels_like_the_reference():
     with pytest.raises(IndexError):
         BatchPlan(np.array([0, 4]), 4, 'cpu')
