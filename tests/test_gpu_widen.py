@@ -172,3 +172,36 @@ def test_kodak_size_image_properties():
     assert torch.equal(rec[1], out['img'][1])
     mse = out['mse'].cpu().numpy()
     assert np.all(np.isfinite(mse)) and mse[0] > 0
+
+
+def test_host_resident_labels_give_the_same_results():
+    """input['label'] may stay a CPU tensor (the node ids are consumed on the host: batch plan, grid sizes): eval, a
+    training step and a graph replay give exactly what CUDA labels give"""
+    import config
+    M, T, B = 3, 3, 20
+    m = build_model('dist_codec', 'CIFAR10', M, T, seed=11)
+    img, label, g = _batch(B, 3, M, 71)
+    noise = torch.rand(T, B, 8, 4, 4, generator=g).cuda()
+    img = img.cuda()
+    m.train(False)
+    outs = []
+    for graph in (False, True):
+        config.PARAM['cuda_graph'] = graph
+        try:
+            with torch.no_grad():
+                outs.append([m({'img': img, 'label': lab}) for lab in (label.cuda(), label)])
+        finally:
+            config.PARAM['cuda_graph'] = False
+    for on_dev, on_host in outs:
+        assert torch.equal(on_dev['code_pm1'], on_host['code_pm1']) and on_dev['loss'].item() == on_host['loss'].item()
+        assert all(np.array_equal(a, b) for a, b in zip(on_dev['code'], on_host['code']))
+    assert torch.equal(outs[0][0]['code_pm1'], outs[1][1]['code_pm1'])
+    m.train(True)
+    res = []
+    for lab in (label.cuda(), label):
+        m.zero_grad(set_to_none=True)
+        out = m({'img': img, 'label': lab}, noise=noise)
+        out['loss'].backward()
+        res.append((out['code_pm1'].clone(), out['loss'].item()))
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+    assert torch.equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
